@@ -1,0 +1,139 @@
+"""Seeded synthetic molecular inputs (host side, numpy) for tests and bench.py.
+
+Follows the generator specified in SURVEY.md §8(d): QM9-shaped random-walk molecules,
+ball-packed 500-atom graphs, radius-cutoff edges, PyG-collated batch layout
+(reference record layout: qm9_allprop.py:11-19).  No file I/O, no network.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+ELEMENTS = np.array([1, 6, 7, 8, 9], dtype=np.int64)          # H C N O F
+ELEMENT_P = np.array([0.50, 0.35, 0.06, 0.08, 0.01])
+CUTOFF = 5.0
+
+
+def _pairs_ok(pos: np.ndarray, cutoff: float, margin: float) -> bool:
+    d = np.linalg.norm(pos[:, None, :] - pos[None, :, :], axis=-1)
+    iu = np.triu_indices(len(pos), 1)
+    return bool(np.all(np.abs(d[iu] - cutoff) > margin))
+
+
+def synth_mol(n: int, rng: np.random.Generator, cutoff: float = CUTOFF,
+              margin: float = 1e-3):
+    """Random-walk molecule: n atoms, bond length U[1.00,1.55] A, >=0.95 A exclusion,
+    no pair within `margin` of the cutoff (keeps edge sets stable under fp32 rounding)."""
+    while True:
+        pos = np.zeros((1, 3))
+        while len(pos) < n:
+            a = pos[rng.integers(len(pos))]
+            v = rng.normal(size=3)
+            v /= np.linalg.norm(v)
+            cand = a + v * rng.uniform(1.00, 1.55)
+            if np.min(np.linalg.norm(pos - cand, axis=1)) >= 0.95:
+                pos = np.vstack([pos, cand])
+        if _pairs_ok(pos, cutoff, margin):
+            break
+    z = rng.choice(ELEMENTS, size=n, p=ELEMENT_P)
+    return pos.astype(np.float32), z
+
+
+def synth_ball(n: int, rng: np.random.Generator, density: float = 0.1,
+               cutoff: float = CUTOFF, margin: float = 1e-3):
+    """n atoms uniformly in a ball at `density` atoms/A^3 with 0.95 A exclusion."""
+    radius = (3.0 * n / (4.0 * np.pi * density)) ** (1.0 / 3.0)
+    while True:
+        pts = []
+        while len(pts) < n:
+            c = rng.uniform(-radius, radius, size=3)
+            if np.linalg.norm(c) > radius:
+                continue
+            if pts and np.min(np.linalg.norm(np.asarray(pts) - c, axis=1)) < 0.95:
+                continue
+            pts.append(c)
+        pos = np.asarray(pts)
+        if _pairs_ok(pos, cutoff, margin):
+            break
+    z = rng.choice(ELEMENTS, size=n, p=ELEMENT_P)
+    return pos.astype(np.float32), z
+
+
+def radius_edges(pos: np.ndarray, cutoff: float = CUTOFF) -> np.ndarray:
+    """All ordered pairs with 0 < d < cutoff, lexicographic (i, then j): [2,E] int64."""
+    p = pos.astype(np.float64)
+    d = np.linalg.norm(p[:, None, :] - p[None, :, :], axis=-1)
+    adj = (d < cutoff) & (d > 0)
+    return np.argwhere(adj).T.astype(np.int64)
+
+
+def collate(mols, cutoff: float = CUTOFF, pair_dim: int = 338, seed: int = 0):
+    """PyG-style collation of (pos, z) molecules -> dict of numpy arrays:
+    x[N] i64, atom_pos[N,3] f32, edge_index[2,E] i64 (per-graph node offsets),
+    edge_attr[E,pair_dim] f32 ~ N(0,0.1^2), edge_num[B], batch[N], y[B], num_graphs."""
+    rng = np.random.default_rng(seed + 7919)
+    xs, ps, eis, en, bt = [], [], [], [], []
+    off = 0
+    for g, (pos, z) in enumerate(mols):
+        ei = radius_edges(pos, cutoff)
+        xs.append(z)
+        ps.append(pos)
+        eis.append(ei + off)
+        en.append(ei.shape[1])
+        bt.append(np.full(len(z), g, dtype=np.int64))
+        off += len(z)
+    edge_index = np.concatenate(eis, axis=1)
+    E = edge_index.shape[1]
+    return dict(
+        x=np.concatenate(xs), atom_pos=np.concatenate(ps).astype(np.float32),
+        edge_index=edge_index,
+        edge_attr=(rng.normal(size=(E, pair_dim)) * 0.1).astype(np.float32),
+        edge_num=np.asarray(en, dtype=np.int64), batch=np.concatenate(bt),
+        y=np.zeros(len(mols), dtype=np.float32), num_graphs=len(mols))
+
+
+def qm9_batch(num_mols: int, seed: int = 0, nmin: int = 9, nmax: int = 29, **kw):
+    """BASELINE.json configs[0]/[1]: `num_mols` QM9-sized molecules (9..29 atoms)."""
+    rng = np.random.default_rng(seed)
+    mols = [synth_mol(int(rng.integers(nmin, nmax + 1)), rng) for _ in range(num_mols)]
+    return collate(mols, seed=seed, **kw)
+
+
+def ball_batch(num_mols: int, n_atoms: int = 500, seed: int = 0, **kw):
+    """BASELINE.json configs[3]: ball-packed `n_atoms`-atom graphs."""
+    rng = np.random.default_rng(seed)
+    return collate([synth_ball(n_atoms, rng) for _ in range(num_mols)], seed=seed, **kw)
+
+
+def triplets_host(edge_index: np.ndarray, num_nodes: int):
+    """Host-side triplet enumeration (SURVEY.md App. E ordering) used ONLY to size
+    synthetic conv inputs for bench/tests set-up; the product path builds triplets on the
+    GPU (edge_graph.vertex_to_edge_2)."""
+    src, dst = edge_index
+    E = src.shape[0]
+    order = np.lexsort((dst, src))
+    s_sorted, d_sorted = src[order], dst[order]
+    start = np.searchsorted(s_sorted, np.arange(num_nodes + 1))
+    deg = start[1:] - start[:-1]
+    cnt = deg[dst]
+    tgt = np.repeat(np.arange(E), cnt)
+    base = np.repeat(start[dst], cnt)
+    within = np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+    f_sorted_pos = base + within
+    k = d_sorted[f_sorted_pos]
+    f = order[f_sorted_pos]
+    keep = k != src[tgt]
+    return np.stack([f[keep], tgt[keep]]).astype(np.int64), dst[tgt][keep], src[tgt][keep], k[keep]
+
+
+def conv_inputs(E: int, trip_index: np.ndarray, D: int = 128, S: int = 42, R: int = 6,
+                A: int = 128, seed: int = 0):
+    """SURVEY.md §8(d) config-4 style tensor inputs for one SBFTransformerConv call:
+    x, sbf, edge_attr ~ N(0,1); rbf ~ U(-1,1)."""
+    rng = np.random.default_rng(seed + 104729)
+    T = trip_index.shape[1]
+    return dict(
+        x=rng.normal(size=(E, D)).astype(np.float32),
+        rbf=rng.uniform(-1, 1, size=(E, R)).astype(np.float32),
+        sbf=rng.normal(size=(T, S)).astype(np.float32),
+        edge_attr=rng.normal(size=(T, A)).astype(np.float32),
+        edge_index=trip_index.astype(np.int64))

@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the X2-GNN hot path on B200.
+
+Metric (BASELINE.json): SBF-conv edge-messages/s, forward + backward, fp32.  One "step" = one
+SBFTransformerConv layer (config.json dims D=128 H=16 S=42 R=6 A=128) forward + backward over one
+synthetic QM9-shaped batch of 128 molecules (BASELINE.json configs[1]); one edge-message = one
+triplet through the layer.  Inputs are resident in HBM for `value`; `e2e` repeats the measurement
+through the public module call with pinned HOST buffers (H2D of every input, line-graph metadata
+build, forward, backward, D2H of the results inside the timed region).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+N > 1: graph batches are sharded per GPU (rank r draws its own 128-molecule batch, weak scaling);
+the only collective is the NCCL all-reduce of the layer's parameter gradients, inside the step.
+`--impl reference` times the reference's CPU path (the oracle port of the reference's composite
+PyTorch ops -- the reference has no native code to compile) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sbfconv_edge_messages_per_sec_fwd_bwd"
+UNIT = "edge-messages/s"
+DIMS = dict(D=128, H=16, S=42, R=6, A=128)       # reference config.json:2-7
+NMOL = 128                                       # BASELINE.json configs[1]: batch 128
+
+
+def algorithmic_bytes(E, T, D, S, R, A):
+    """every interface tensor touched once, fp32, int64 indices."""
+    fwd = 4 * (E * (D + R) + T * (S + A) + E * D) + 16 * T
+    bwd = 4 * (E * D + E * (D + R) + T * (S + A)) + 16 * T + 4 * (E * (D + R) + T * A)
+    return fwd, bwd
+
+
+def host_workload(seed: int, nmol: int = NMOL):
+    from x2gnn_b200 import synth
+    b = synth.qm9_batch(nmol, seed=seed)
+    tri = synth.triplets_host(b["edge_index"], len(b["x"]))[0]
+    E = b["edge_index"].shape[1]
+    ci = synth.conv_inputs(E, tri, DIMS["D"], DIMS["S"], DIMS["R"], DIMS["A"], seed=seed)
+    return dict(N=len(b["x"]), E=E, T=tri.shape[1], **ci)
+
+
+# ---------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index: int, period_s: float = 0.01):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+        self.period = period_s
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------- reference / CPU arm
+def oracle_step_fn(w, nthreads):
+    """The reference's CPU path for this workload: composite PyTorch ops of the oracle port."""
+    import torch
+    from oracle import conv as oconv
+    torch.set_num_threads(nthreads)
+    torch.manual_seed(0)
+    layer = oconv.OracleSBFTransformerConv(DIMS["D"], DIMS["D"] // DIMS["H"], heads=DIMS["H"],
+                                           sbf_dim=DIMS["S"], rbf_dim=DIMS["R"], edge_dim=DIMS["A"])
+    x = torch.from_numpy(w["x"]).requires_grad_(True)
+    rbf = torch.from_numpy(w["rbf"]).requires_grad_(True)
+    ea = torch.from_numpy(w["edge_attr"]).requires_grad_(True)
+    sbf = torch.from_numpy(w["sbf"])
+    ei = torch.from_numpy(w["edge_index"])
+    gout = torch.randn(w["E"], DIMS["D"], generator=torch.Generator().manual_seed(1))
+    params = list(layer.parameters())
+
+    def step():
+        out = layer(sbf, rbf, x=x, edge_index=ei, edge_attr=ea)
+        torch.autograd.grad(out, [x, rbf, ea] + params, gout)
+    return step
+
+
+def time_cpu(step, iters, warmup=1):
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        step()
+    return (time.perf_counter() - t0) / iters
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncores = os.cpu_count() or 1
+    steps, warmup = args.steps, args.warmup
+    # bounded sample: pick the number of molecules so that (steps + warmup) steps fit ~150 s
+    probe = host_workload(0, 16)
+    t_probe = time_cpu(oracle_step_fn(probe, ncores), 1, warmup=1)
+    rate = probe["T"] / t_probe
+    full = host_workload(0, NMOL)
+    budget_T = rate * 150.0 / max(steps + warmup, 1)
+    nmol = NMOL if budget_T >= full["T"] else max(4, min(NMOL, int(NMOL * budget_T / full["T"])))
+    w = full if nmol == NMOL else host_workload(0, nmol)
+    sec = time_cpu(oracle_step_fn(w, ncores), steps, warmup=warmup)
+    value = w["T"] / sec
+    sample = (f"{nmol} of {NMOL} molecules of the seed-0 batch (E={w['E']}, T={w['T']}), "
+              f"{warmup} warm-up + {steps} timed fwd+bwd steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "qm9_b128_sbfconv_layer_fwd_bwd (BASELINE.json configs[1])", **DIMS,
+                   "E": w["E"], "T": w["T"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from x2gnn_b200 import _lib, graph_meta
+    from x2gnn_b200.sbftransformer_conv import SBFTransformerConv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU path; use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    w = host_workload(seed=rank)
+    E, T = w["E"], w["T"]
+    D, H, S, R, A = (DIMS[k] for k in "DHSRA")
+    torch.manual_seed(0)
+    layer = SBFTransformerConv(D, D // H, heads=H, sbf_dim=S, rbf_dim=R, dropout=0, edge_dim=A).to(dev)
+    params = list(layer.parameters())
+    pin = {k: torch.from_numpy(w[k]).pin_memory() for k in ("x", "rbf", "sbf", "edge_attr", "edge_index")}
+    x = pin["x"].to(dev).requires_grad_(True)
+    rbf = pin["rbf"].to(dev).requires_grad_(True)
+    ea = pin["edge_attr"].to(dev).requires_grad_(True)
+    sbf = pin["sbf"].to(dev)
+    ei = pin["edge_index"].to(dev)
+    gout = torch.randn(E, D, device=dev, generator=torch.Generator(dev).manual_seed(1))
+    flat = torch.empty(sum(p.numel() for p in params), device=dev)
+
+    def step():
+        out = layer(sbf, rbf, x=x, edge_index=ei, edge_attr=ea)
+        grads = torch.autograd.grad(out, [x, rbf, ea] + params, gout)
+        if world > 1:      # data-parallel training: one flat all-reduce of the parameter gradients
+            torch.cat([g.reshape(-1) for g in grads[3:]], out=flat)
+            dist.all_reduce(flat)
+        return out, grads
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------ resident-input throughput (`value`)
+    for _ in range(warmup):
+        step()
+    barrier()
+    n0 = _lib.launch_count()
+    _lib.timing_read()
+    _lib.timing_enable(rank == 0)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            step()
+        ev1.record()
+        barrier()
+    _lib.timing_enable(False)
+    launches = (_lib.launch_count() - n0) // max(steps, 1)
+    phases = _lib.timing_read() if rank == 0 else {}
+    ms = ev0.elapsed_time(ev1)
+    t_all = torch.tensor([ms, float(T)], device=dev, dtype=torch.float64)
+    if world > 1:
+        tmax = t_all.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_all, op=dist.ReduceOp.SUM)
+        ms, total_T = float(tmax[0]), float(t_all[1])
+    else:
+        total_T = float(T)
+    ms_per_step = ms / steps
+    value = total_T / (ms_per_step * 1e-3)
+
+    # ------------------------------------------------ end to end through the module call (`e2e`)
+    d_x, d_rbf, d_ea, d_sbf, d_ei = (torch.empty_like(t, device=dev) for t in
+                                     (pin["x"], pin["rbf"], pin["edge_attr"], pin["sbf"], pin["edge_index"]))
+    d_x.requires_grad_(True); d_rbf.requires_grad_(True); d_ea.requires_grad_(True)
+    h_out = torch.empty(E, D).pin_memory()
+    h_dx = torch.empty(E, D).pin_memory()
+    h_drbf = torch.empty(E, R).pin_memory()
+    h_flat = torch.empty(flat.numel()).pin_memory()
+
+    def e2e_step():
+        with torch.no_grad():
+            d_x.copy_(pin["x"], non_blocking=True)
+            d_rbf.copy_(pin["rbf"], non_blocking=True)
+            d_ea.copy_(pin["edge_attr"], non_blocking=True)
+            d_sbf.copy_(pin["sbf"], non_blocking=True)
+            d_ei.copy_(pin["edge_index"], non_blocking=True)   # bumps _version => metadata is rebuilt
+        out = layer(d_sbf, d_rbf, x=d_x, edge_index=d_ei, edge_attr=d_ea)
+        grads = torch.autograd.grad(out, [d_x, d_rbf, d_ea] + params, gout)
+        torch.cat([g.reshape(-1) for g in grads[3:]], out=flat)
+        if world > 1:
+            dist.all_reduce(flat)
+        h_out.copy_(out.detach(), non_blocking=True)
+        h_dx.copy_(grads[0], non_blocking=True)
+        h_drbf.copy_(grads[1], non_blocking=True)
+        h_flat.copy_(flat, non_blocking=True)
+        torch.cuda.synchronize()            # the host owns the results before the next step
+
+    h2d = sum(pin[k].numel() * pin[k].element_size() for k in pin)
+    d2h = sum(t.numel() * t.element_size() for t in (h_out, h_dx, h_drbf, h_flat))
+    e2e_steps = max(3, min(steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    ev0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    e_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = float(t[0])
+    e2e_value = total_T / (e_ms / e2e_steps * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------ roofline of the layer's kernels (rank 0)
+    fwd_b, bwd_b = algorithmic_bytes(E, T, D, S, R, A)
+    kernel_ms = sum(v[0] for v in phases.values()) / max(steps, 1)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = (fwd_b + bwd_b) / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    phase_ms = {k: round(v[0] / max(steps, 1), 4) for k, v in phases.items()}
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "all launches of x2_sbfconv_fwd + x2_sbfconv_bwd (one layer step)",
+                "algorithmic_bytes_per_step": fwd_b + bwd_b, "kernel_ms_per_step": kernel_ms,
+                "phase_ms_per_step": phase_ms}
+
+    # ------------------------------------------------ CPU baseline (N = 1 only, bounded)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ncores = os.cpu_count() or 1
+        sec = time_cpu(oracle_step_fn(w, ncores), 3, warmup=1)
+        cpu = {"value": T / sec, "unit": UNIT, "cores": ncores, "kind": "port",
+               "sample": f"full seed-0 batch (E={E}, T={T}), 1 warm-up + 3 timed fwd+bwd steps, "
+                         f"oracle port of the reference's composite PyTorch path, fp32"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "qm9_b128_sbfconv_layer_fwd_bwd (BASELINE.json configs[1])", **DIMS,
+                   "molecules_per_gpu": NMOL, "E": E, "T": T, "precision_mode": "fp32 (1e-5 parity)",
+                   "parallelism": f"dp{world} (graph batches sharded per GPU, NCCL grad all-reduce)",
+                   "l2": f"no flush: per-step T-row inputs {680 * T / 1e6:.0f} MB > 126 MB L2"},
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps},
+        "gpu_launches": int(launches) * steps, "gpu_launches_per_step": int(launches),
+        "clocks": clocks.summary(),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,197 @@
+/*
+ * x2gnn.h -- C ABI of libx2gnn.so, the B200 (sm_100a) implementation of the X2-GNN
+ * message-passing hot path.
+ *
+ * The reference (zfwangDP/X2-GNN) is pure Python and has no FFI; its boundary for this
+ * path is the Python API of seven modules.  Each entry point below is what the Python
+ * drop-in module of the same reference file binds through ctypes:
+ *
+ *   x2_dij / x2_bonds_*          replace  atom_graph.py:32-35 (calculate_Dij), :42-45 (gen_bonds_mini)
+ *   x2_radius_graph_*            batched form of the same two functions (positions -> edge_index)
+ *   x2_triplets_*                replace  edge_graph.py:12-30 (vertex_to_edge_2)
+ *   x2_envelope_fwd              replaces envelop.py:16-21 (poly_envelop.forward), :23-32
+ *   x2_radial_fwd / _bwd         replace  radial_basis_layer.py:36-40 (RadialBasis.forward) + autograd
+ *   x2_sbf_table / x2_sbf_fwd    replace  angular_basis_layer.py:80-93 (F_B_2D.forward)
+ *   x2_angular_fwd               replaces angular_basis_layer.py:28-32 (AngularBasisLayer.forward)
+ *   x2_meta_*                    CSR metadata of the line graph (replaces what PyG's
+ *                                propagate/softmax/scatter derive from edge_index,
+ *                                sbftransformer_conv.py:109,151)
+ *   x2_sbfconv_fwd / _bwd        replace  sbftransformer_conv.py:93-162 (forward + message + PyG
+ *                                propagate/softmax/aggregate) and its autograd backward
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative X2_E* code; x2_last_error() gives a
+ *     thread-local message.  Nothing throws.
+ *   - all data pointers are DEVICE pointers to contiguous row-major buffers owned by the caller;
+ *     the library never allocates or frees caller-visible memory and never synchronises the
+ *     stream (exception: none).  Scratch space is passed in (`ws`, sized by *_workspace_bytes).
+ *   - `stream` is a cudaStream_t passed as void*.  Calls are re-entrant across streams.
+ *   - floating tensors are fp32, index tensors of the reference API are int64, internal CSR
+ *     metadata is int32 (so E, T < 2^31).
+ */
+#ifndef X2GNN_H_
+#define X2GNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define X2_OK 0
+#define X2_EINVAL (-1)   /* bad argument / unsupported shape */
+#define X2_ECUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define X2_EWORKSPACE (-3) /* workspace too small */
+#define X2_EDEVICE (-4)  /* device is not sm_100 */
+
+int x2_version(void);
+const char* x2_last_error(void);
+/* 0 iff `device` exists and is compute capability 10.x (B200). */
+int x2_device_check(int device);
+
+/* ---------------------------------------------------------------- instrumentation (bench.py)
+ * x2_launch_count: number of kernels this library has launched in this process.
+ * x2_timing_*:     optional CUDA-event brackets around the phases of x2_sbfconv_fwd/_bwd, recorded
+ *                  on the caller's stream.  read() synchronises on the recorded events, ADDS the
+ *                  elapsed milliseconds / call counts per phase into ms[]/calls[] (n entries) and
+ *                  clears the recording.  Phase ids: X2_PHASE_*. */
+int64_t x2_launch_count(void);
+int x2_timing_enable(int on);
+int x2_timing_read(double* ms, int64_t* calls, int n);
+const char* x2_timing_phase_name(int phase);
+#define X2_PHASE_NODE_PROJ 0   /* rbf filter + Q|K|V|skip GEMM */
+#define X2_PHASE_TROW_PROJ 1   /* lin_edge / lin_sbf on T rows */
+#define X2_PHASE_ATTN_FWD 2    /* segmented attention forward */
+#define X2_PHASE_ATTN_BWD_TGT 3
+#define X2_PHASE_ATTN_BWD_SRC 4
+#define X2_PHASE_TROW_DGRAD 5  /* d edge_attr, d sbf */
+#define X2_PHASE_TROW_WGRAD 6  /* dW_edge, dW_sbf, db_sbf */
+#define X2_PHASE_NODE_BWD 7    /* node-level wgrad/dgrad, filter backward */
+#define X2_NUM_PHASES 8
+
+/* ---------------------------------------------------------------- radius graph
+ * atom_graph.py:32-35.  dij[n,n] = relu(sqrt(|a|^2 + |b|^2 - 2 a.b)) (Gram form, fp32). */
+int x2_dij(const float* pos, int64_t n, float* dij, void* stream);
+/* atom_graph.py:42-45.  adj = (dij < cutoff) & (dij != 0).  rowptr[n+1] int32: exclusive scan of
+ * the per-row counts (E = rowptr[n], read back by the caller).  ws >= x2_scan_workspace_bytes(n). */
+int x2_bonds_count(const float* dij, int64_t n, float cutoff, int32_t* rowptr, void* ws,
+                   size_t ws_bytes, void* stream);
+/* edge_index[2,E] int64, lexicographic (i, then j) -- the order np.argwhere produces. */
+int x2_bonds_fill(const float* dij, int64_t n, float cutoff, const int32_t* rowptr,
+                  int64_t* edge_index, int64_t E, void* stream);
+/* Batched: atoms of graph g are ptr[g]..ptr[g+1] (ptr int64 [B+1]), batch[n] int64 sorted.  Same
+ * arithmetic as x2_dij per pair; edge_index carries global atom ids, sorted by (i, j). */
+int x2_radius_graph_count(const float* pos, const int64_t* batch, const int64_t* ptr, int64_t n,
+                          float cutoff, int32_t* rowptr, void* ws, size_t ws_bytes, void* stream);
+int x2_radius_graph_fill(const float* pos, const int64_t* batch, const int64_t* ptr, int64_t n,
+                         float cutoff, const int32_t* rowptr, int64_t* edge_index, int64_t E,
+                         void* stream);
+size_t x2_scan_workspace_bytes(int64_t n);
+
+/* ---------------------------------------------------------------- triplets (edge_graph.py:12-30)
+ * For each bond e=(i->j) in order, for each bond f=(j->k), k ascending, k != i:
+ *   triplets_index[0,t]=f, [1,t]=e, edge_j[t]=j, edge_i[t]=i, edge_k[t]=k.          (int64)
+ * count: builds the per-atom out-bond CSR in `ws`, writes rowptr[E+1] (int32, by target bond;
+ *        T = rowptr[E]) and flags[0]=1 if edge_index was lexicographically sorted,
+ *        flags[1]=number of out-of-range atom ids.
+ * fill : needs the same `ws` contents. */
+size_t x2_triplets_workspace_bytes(int64_t E, int64_t N);
+int x2_triplets_count(const int64_t* edge_index, int64_t E, int64_t N, int32_t* rowptr,
+                      int32_t* flags, void* ws, size_t ws_bytes, void* stream);
+int x2_triplets_fill(const int64_t* edge_index, int64_t E, int64_t N, const int32_t* rowptr,
+                     int64_t T, int64_t* triplets_index, int64_t* edge_j, int64_t* edge_i,
+                     int64_t* edge_k, const void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- line-graph CSR metadata
+ * edge_index[2,T] int64 (row 0 = source line-node, row 1 = target line-node), E line-nodes.
+ * Outputs (int32): src[T], tgt[T]; rowptr_tgt[E+1] + order_tgt[T] (triplet ids grouped by target,
+ * ascending inside a group; identity when edge_index[1] is already sorted); rowptr_src[E+1] +
+ * order_src[T] (grouped by source, ascending).  flags[0]=1 if target-sorted, flags[1]=number of
+ * out-of-range ids. */
+size_t x2_meta_workspace_bytes(int64_t T, int64_t E);
+int x2_meta_build(const int64_t* edge_index, int64_t T, int64_t E, int32_t* src, int32_t* tgt,
+                  int32_t* rowptr_tgt, int32_t* order_tgt, int32_t* rowptr_src,
+                  int32_t* order_src, int32_t* flags, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- basis expansions
+ * envelop.py:16-21: out = 1/x + a x^(p-1) + b x^p + c x^(p+1), x = d * inv_cutoff. */
+int x2_envelope_fwd(const float* d, int64_t n, float inv_cutoff, int32_t p, float a, float b,
+                    float c, float* out, void* stream);
+/* radial_basis_layer.py:36-40: out[e,r] = sin(freq[r] * d[e] * inv_cutoff) * (env ? env[e] : 1).
+ * (`env` fuses xgnn.py:69; pass NULL for the plain module.) */
+int x2_radial_fwd(const float* d, const float* freq, const float* env, int64_t n, int32_t R,
+                  float inv_cutoff, float* out, void* stream);
+/* grad_freq[R] (+ optional grad_d[n]) of the above given grad_out[n,R].  Deterministic two-stage
+ * reduction; ws >= x2_radial_bwd_workspace_bytes(n, R). */
+size_t x2_radial_bwd_workspace_bytes(int64_t n, int32_t R);
+int x2_radial_bwd(const float* d, const float* freq, const float* env, const float* grad_out,
+                  int64_t n, int32_t R, float inv_cutoff, float* grad_freq, float* grad_d,
+                  void* ws, size_t ws_bytes, void* stream);
+/* angular_basis_layer.py:81-86: table[e, l*R+n] = env(d_e) * norm[l,n] * j_l(zeros[l,n]*d_e/cutoff)
+ * with env = poly envelope (cutoff env_cutoff, exponent p-1).  j_l evaluated in fp64 (series /
+ * upward recurrence), rounded once to fp32.  zeros/norm: fp32 [L,R] (basis_func.py:14-29,55-60). */
+int x2_sbf_table(const float* d, int64_t n, int32_t L, int32_t R, const float* zeros,
+                 const float* norm, float cutoff, float env_cutoff, int32_t p, float a, float b,
+                 float c, float* table, void* stream);
+/* angular_basis_layer.py:87-93: out[t, l*R+n] = table[idx[t], l*R+n] * Y_l0(angles[t]). */
+int x2_sbf_fwd(const float* table, const float* angles, const int64_t* idx, int64_t T, int64_t E,
+               int32_t L, int32_t R, float* out, void* stream);
+/* angular_basis_layer.py:28-32: out[t,l] = Y_l0(angles[t]). */
+int x2_angular_fwd(const float* angles, int64_t T, int32_t L, float* out, void* stream);
+
+/* ---------------------------------------------------------------- SBFTransformerConv
+ * Shapes: x[E,D] rbf[E,R] sbf[T,S] edge_attr[T,A] (A=0 => no lin_edge); D = H*C.
+ * Weights use the torch.nn.Linear layout [out,in] of the reference state_dict. */
+typedef struct {
+  int64_t E, T;
+  int32_t D, H, C, S, R, A;
+  int32_t fuse_skip;   /* 1: out = attn + lin_skip(x) (concat, root_weight, no beta) */
+  int32_t mode;        /* X2_MODE_* */
+  float dropout_p;     /* attention dropout (training); 0 disables */
+  uint64_t seed;       /* dropout RNG seed */
+  /* inputs */
+  const float *x, *rbf, *sbf, *edge_attr;
+  /* line-graph metadata (x2_meta_build) */
+  const int32_t *src, *tgt, *rowptr_tgt, *order_tgt, *rowptr_src, *order_src;
+  /* parameters */
+  const float *w_rbf;              /* [D,R] */
+  const float *w_q, *b_q;          /* [D,D], [D] */
+  const float *w_k, *b_k;
+  const float *w_v, *b_v;
+  const float *w_edge;             /* [D,A] or NULL */
+  const float *w_sbf, *b_sbf;      /* [D,S], [D] */
+  const float *w_skip, *b_skip;    /* [D,D], [D] (b_skip may be NULL); used iff fuse_skip */
+} x2_conv_desc;
+
+#define X2_MODE_FP32 0   /* fp32 SIMT arithmetic everywhere (1e-5 parity mode) */
+
+/* Tensors written by fwd and consumed by bwd (caller-owned, kept alive by autograd). */
+typedef struct {
+  float* qkvs;   /* [E, 4D]  Q | K | V | skip */
+  float* attn;   /* [E, D]   attention output before the skip add */
+  float* lse;    /* [E, H]   log-sum-exp of the logits per (target, head) */
+  float* ea;     /* [T, D]   lin_edge(edge_attr)  (NULL if A == 0) */
+  float* sg;     /* [T, D]   lin_sbf(sbf) */
+} x2_conv_saved;
+
+typedef struct {
+  float *dx, *drbf;            /* [E,D], [E,R] */
+  float *dsbf;                 /* [T,S] or NULL (not needed by the reference graph) */
+  float *dedge_attr;           /* [T,A] or NULL */
+  float *dw_rbf, *dw_q, *db_q, *dw_k, *db_k, *dw_v, *db_v, *dw_edge, *dw_sbf, *db_sbf;
+  float *dw_skip, *db_skip;    /* used iff fuse_skip (db_skip may be NULL) */
+} x2_conv_grads;
+
+size_t x2_sbfconv_fwd_workspace_bytes(const x2_conv_desc* d);
+size_t x2_sbfconv_bwd_workspace_bytes(const x2_conv_desc* d);
+/* out[E,D]; alpha[T,H] optional (return_attention_weights), NULL otherwise. */
+int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* saved, float* out, float* alpha,
+                   void* ws, size_t ws_bytes, void* stream);
+int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* saved, const float* grad_out,
+                   const x2_conv_grads* g, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* X2GNN_H_ */

@@ -1,0 +1,251 @@
+"""GPU parity: SBFTransformerConv forward + backward through the C-ABI against
+(1) golden vectors produced by the reference's own source in fp64 and
+(2) the CPU oracle on seeded inputs, within the north_star tolerance (1e-5 relative, fp32)."""
+import pytest
+import torch
+
+from oracle import conv as oconv
+from util import FP32_TOL, relerr
+
+pytestmark = pytest.mark.gpu
+
+INPUTS = ("x", "rbf", "sbf", "edge_attr")
+
+
+def _mine(dims, state, **kw):
+    from x2gnn_b200.sbftransformer_conv import SBFTransformerConv
+    D, H, S, R, A = dims
+    c = SBFTransformerConv(D, D // H, heads=H, sbf_dim=S, rbf_dim=R, dropout=kw.pop("dropout", 0),
+                           edge_dim=A, **kw)
+    if state is not None:
+        c.load_state_dict(state)          # reference state_dict loads unchanged
+    return c.cuda()
+
+
+def _run(conv, rec, dev, dtype, want_alpha=False, sbf_grad=True):
+    xs = {k: rec[k].to(device=dev, dtype=dtype).requires_grad_(k != "sbf" or sbf_grad) for k in INPUTS}
+    ei = rec["edge_index"].to(dev)
+    r = conv(xs["sbf"], xs["rbf"], x=xs["x"], edge_index=ei, edge_attr=xs["edge_attr"],
+             return_attention_weights=True if want_alpha else None)
+    out, alpha = (r[0], r[1][1]) if want_alpha else (r, None)
+    out.backward(rec["grad_out"].to(device=dev, dtype=dtype))
+    return out, alpha, xs
+
+
+@pytest.mark.parametrize("tag", ["cfg", "small", "c16"])
+def test_golden_fwd_bwd(golden, tag):
+    rec = golden("conv")[tag]
+    conv = _mine(rec["dims"], rec["state_dict"])
+    assert list(conv.state_dict().keys()) == list(rec["state_dict"].keys())
+    out, alpha, xs = _run(conv, rec, "cuda", torch.float32, want_alpha=True)
+    assert relerr(out, rec["out_f64"]) < FP32_TOL
+    if "alpha_f64" in rec:
+        assert relerr(alpha, rec["alpha_f64"]) < FP32_TOL
+    for k in INPUTS:
+        assert relerr(xs[k].grad, rec[f"grad_{k}_f64"]) < FP32_TOL, k
+    for k, p in conv.named_parameters():
+        ref = rec[f"gradp_{k}_f64"]
+        if k == "lin_key.bias":           # App. A identity: exactly zero in exact arithmetic
+            assert float(p.grad.abs().max()) < 1e-5 * float(rec["gradp_lin_value.bias_f64"].abs().max())
+            continue
+        assert relerr(p.grad, ref) < FP32_TOL, k
+
+
+def _oracle_pair(dims, seed=0, **kw):
+    D, H, S, R, A = dims
+    torch.manual_seed(seed)
+    ref = oconv.OracleSBFTransformerConv(D, D // H, heads=H, sbf_dim=S, rbf_dim=R, edge_dim=A, **kw)
+    with torch.no_grad():                   # non-trivial biases everywhere
+        for p in ref.parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.2, 0.2)
+    mine = _mine(dims, ref.state_dict(), **kw)
+    return ref.double(), mine
+
+
+def _graph_inputs(nmol, dims, seed):
+    from x2gnn_b200 import synth
+    D, H, S, R, A = dims
+    b = synth.qm9_batch(nmol, seed=seed)
+    tri = synth.triplets_host(b["edge_index"], len(b["x"]))[0]
+    E = b["edge_index"].shape[1]
+    ci = synth.conv_inputs(E, tri, D, S, R, max(A or 1, 1), seed=seed)
+    rec = {k: torch.from_numpy(v) for k, v in ci.items()}
+    rec["grad_out"] = torch.randn(E, D, generator=torch.Generator().manual_seed(seed + 1))
+    return rec
+
+
+def _compare(ref, mine, rec, tol=FP32_TOL, check_alpha=True):
+    o_ref, a_ref, x_ref = _run(ref, rec, "cpu", torch.float64, want_alpha=True)
+    o, a, x = _run(mine, rec, "cuda", torch.float32, want_alpha=True)
+    assert relerr(o, o_ref) < tol
+    if check_alpha:
+        assert relerr(a, a_ref) < tol
+    for k in INPUTS:
+        if x_ref[k].grad is None:
+            continue
+        assert relerr(x[k].grad, x_ref[k].grad) < tol, k
+    pm = dict(mine.named_parameters())
+    for k, p in ref.named_parameters():
+        if k == "lin_key.bias":
+            continue
+        assert relerr(pm[k].grad, p.grad) < tol, k
+
+
+@pytest.mark.parametrize("dims", [(128, 16, 42, 6, 128), (256, 16, 112, 16, 128), (64, 8, 10, 3, 20),
+                                  (32, 1, 5, 2, 7), (128, 4, 42, 6, 128)])
+def test_vs_oracle_qm9_batch(dims):
+    """config.json dims, class-default dims (xgnn.py:16) and odd shapes on a 6-molecule batch."""
+    ref, mine = _oracle_pair(dims)
+    _compare(ref, mine, _graph_inputs(6, dims, seed=2))
+
+
+@pytest.mark.parametrize("kw", [dict(concat=False), dict(beta=True), dict(root_weight=False),
+                                dict(bias=False), dict(concat=False, beta=True)])
+def test_variants(kw):
+    dims = (64, 8, 10, 3, 20)
+    ref, mine = _oracle_pair(dims, seed=3, **kw)
+    _compare(ref, mine, _graph_inputs(3, dims, seed=4))
+
+
+def test_no_edge_dim():
+    from x2gnn_b200.sbftransformer_conv import SBFTransformerConv
+    torch.manual_seed(0)
+    ref = oconv.OracleSBFTransformerConv(64, 8, heads=8, sbf_dim=10, rbf_dim=3, edge_dim=None)
+    mine = SBFTransformerConv(64, 8, heads=8, sbf_dim=10, rbf_dim=3, edge_dim=None)
+    assert "lin_edge.weight" not in mine.state_dict()
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.cuda()
+    rec = _graph_inputs(3, (64, 8, 10, 3, 1), seed=5)
+    x = {k: rec[k] for k in ("x", "rbf", "sbf")}
+    o_ref = ref.double()(x["sbf"].double(), x["rbf"].double(), x=x["x"].double(), edge_index=rec["edge_index"])
+    o = mine(x["sbf"].cuda(), x["rbf"].cuda(), x=x["x"].cuda(), edge_index=rec["edge_index"].cuda())
+    assert relerr(o, o_ref) < FP32_TOL
+
+
+def test_empty_segments_and_no_triplets():
+    """Diatomics: every segment is empty => out = lin_skip(x) (App. A); T = 0 must work."""
+    dims = (64, 8, 10, 3, 20)
+    ref, mine = _oracle_pair(dims, seed=6)
+    E = 6
+    rec = dict(x=torch.randn(E, 64), rbf=torch.rand(E, 3), sbf=torch.zeros(0, 10), edge_attr=torch.zeros(0, 20),
+               edge_index=torch.zeros(2, 0, dtype=torch.int64), grad_out=torch.randn(E, 64))
+    o, _, xs = _run(mine, rec, "cuda", torch.float32)
+    want = torch.nn.functional.linear(rec["x"].double(), ref.lin_skip.weight, ref.lin_skip.bias)
+    assert relerr(o, want) < FP32_TOL
+    assert torch.isfinite(xs["x"].grad).all()
+    # a mix: some targets have no incoming triplet
+    rec = _graph_inputs(2, dims, seed=7)
+    keep = rec["edge_index"][1] % 3 != 0
+    for k in ("sbf", "edge_attr"):
+        rec[k] = rec[k][keep]
+    rec["edge_index"] = rec["edge_index"][:, keep]
+    _compare(ref, mine, rec)
+
+
+def test_unsorted_edge_index_and_permutation_invariance():
+    dims = (128, 16, 42, 6, 128)
+    ref, mine = _oracle_pair(dims, seed=8)
+    rec = _graph_inputs(3, dims, seed=9)
+    o_sorted, _, _ = _run(mine, rec, "cuda", torch.float32)
+    T = rec["edge_index"].size(1)
+    perm = torch.randperm(T, generator=torch.Generator().manual_seed(0))
+    rec_p = dict(rec)
+    rec_p["edge_index"] = rec["edge_index"][:, perm].contiguous()
+    rec_p["sbf"], rec_p["edge_attr"] = rec["sbf"][perm], rec["edge_attr"][perm]
+    _compare(ref, mine, rec_p)
+    o_perm, _, _ = _run(mine, rec_p, "cuda", torch.float32)
+    assert relerr(o_perm, o_sorted) < 1e-6     # only the in-segment summation order differs
+
+
+def test_deterministic_bitwise():
+    dims = (128, 16, 42, 6, 128)
+    _, mine = _oracle_pair(dims, seed=10)
+    rec = _graph_inputs(8, dims, seed=11)
+    runs = []
+    for _ in range(2):
+        mine.zero_grad()
+        o, _, xs = _run(mine, rec, "cuda", torch.float32)
+        runs.append([o.detach().clone()] + [xs[k].grad.clone() for k in INPUTS] +
+                    [p.grad.clone() for p in mine.parameters()])
+    for a, b in zip(*runs):
+        assert torch.equal(a, b)            # atomic-free => run-to-run identical
+
+
+def test_batching_independence():
+    """Block-diagonal graphs: a molecule's rows do not depend on what else is in the batch."""
+    from x2gnn_b200 import synth
+    dims = (128, 16, 42, 6, 128)
+    _, mine = _oracle_pair(dims, seed=12)
+    rec = _graph_inputs(4, dims, seed=13)
+    with torch.no_grad():
+        full = mine(rec["sbf"].cuda(), rec["rbf"].cuda(), x=rec["x"].cuda(),
+                    edge_index=rec["edge_index"].cuda(), edge_attr=rec["edge_attr"].cuda())
+    b = synth.qm9_batch(4, seed=13)
+    E0 = int(b["edge_num"][0])
+    m = rec["edge_index"][1] < E0
+    with torch.no_grad():
+        first = mine(rec["sbf"][m].cuda(), rec["rbf"][:E0].cuda(), x=rec["x"][:E0].cuda(),
+                     edge_index=rec["edge_index"][:, m].cuda(), edge_attr=rec["edge_attr"][m].cuda())
+    assert torch.equal(first, full[:E0])
+
+
+def test_sbf_without_grad_and_frozen_inputs():
+    dims = (64, 8, 10, 3, 20)
+    ref, mine = _oracle_pair(dims, seed=14)
+    rec = _graph_inputs(2, dims, seed=15)
+    o, _, xs = _run(mine, rec, "cuda", torch.float32, sbf_grad=False)   # the reference graph: sbf has no grad
+    assert xs["sbf"].grad is None
+    o_ref, _, x_ref = _run(ref, rec, "cpu", torch.float64)
+    assert relerr(xs["x"].grad, x_ref["x"].grad) < FP32_TOL
+
+
+def test_dropout_training_directional_derivative():
+    dims = (64, 8, 10, 3, 20)
+    _, mine = _oracle_pair(dims, seed=16, dropout=0.3)
+    rec = _graph_inputs(2, dims, seed=17)
+    dev = "cuda"
+    args = {k: rec[k].to(dev) for k in INPUTS}
+    ei = rec["edge_index"].to(dev)
+    mine.eval()
+    with torch.no_grad():
+        o_eval = mine(args["sbf"], args["rbf"], x=args["x"], edge_index=ei, edge_attr=args["edge_attr"])
+    mine.train()
+    torch.manual_seed(0)
+    x = args["x"].clone().requires_grad_(True)
+    o1 = mine(args["sbf"], args["rbf"], x=x, edge_index=ei, edge_attr=args["edge_attr"])
+    assert relerr(o1, o_eval) > 1e-3            # the mask is applied in training ...
+    g = rec["grad_out"].to(dev)
+    o1.backward(g)
+    v = torch.randn_like(x)
+    eps = 1e-2
+    outs = []
+    for sgn in (+1, -1):
+        torch.manual_seed(0)                      # same dropout seed => same mask
+        with torch.no_grad():
+            outs.append(mine(args["sbf"], args["rbf"], x=args["x"] + sgn * eps * v, edge_index=ei,
+                             edge_attr=args["edge_attr"]))
+    fd = float(((outs[0] - outs[1]).double() * g.double()).sum() / (2 * eps))
+    an = float((x.grad.double() * v.double()).sum())
+    assert abs(fd - an) < 2e-2 * max(abs(an), 1.0)
+    mine.eval()
+    with torch.no_grad():                          # ... and never in eval
+        assert torch.equal(mine(args["sbf"], args["rbf"], x=args["x"], edge_index=ei,
+                                edge_attr=args["edge_attr"]), o_eval)
+
+
+def test_loud_failures():
+    from x2gnn_b200 import _lib
+    from x2gnn_b200.sbftransformer_conv import SBFTransformerConv
+    c = SBFTransformerConv(64, 8, heads=8, sbf_dim=10, rbf_dim=3, edge_dim=20)
+    rec = _graph_inputs(1, (64, 8, 10, 3, 20), seed=1)
+    with pytest.raises(_lib.X2Error):       # CPU tensors: no fallback
+        c(rec["sbf"], rec["rbf"], x=rec["x"], edge_index=rec["edge_index"], edge_attr=rec["edge_attr"])
+    c = c.cuda()
+    with pytest.raises(TypeError):          # fp64 is not silently down-cast
+        c(rec["sbf"].cuda().double(), rec["rbf"].cuda().double(), x=rec["x"].cuda().double(),
+          edge_index=rec["edge_index"].cuda(), edge_attr=rec["edge_attr"].cuda().double())
+    bad = SBFTransformerConv(96, 12, heads=8, sbf_dim=10, rbf_dim=3, edge_dim=20).cuda()   # D=96 unsupported
+    with pytest.raises(_lib.X2Error):
+        bad(rec["sbf"].cuda(), rec["rbf"].cuda(), x=torch.randn(rec["x"].size(0), 96, device="cuda"),
+            edge_index=rec["edge_index"].cuda(), edge_attr=rec["edge_attr"].cuda())

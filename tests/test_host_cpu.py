@@ -1,0 +1,144 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the header declares,
+the host modules keep the reference's constructor / state_dict contract, and the product path
+fails loudly (no CPU fallback, no oracle import)."""
+import ast
+import copy
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "x2-gnn_b200")
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "x2gnn.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(x2_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    from x2gnn_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build with: python x2-gnn_b200/build.py"
+    h = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(h, s), f"{s} declared in include/x2gnn.h but not exported"
+    assert sorted(_lib.SIGNATURES) == syms          # ctypes table mirrors the header one to one
+    assert _lib.lib().x2_version() >= 100
+
+
+def test_workspace_queries_need_no_gpu():
+    from x2gnn_b200 import _lib
+    L = _lib.lib()
+    assert L.x2_scan_workspace_bytes(1000) > 0
+    assert L.x2_triplets_workspace_bytes(1000, 100) > 4 * 1000 * 4
+    assert L.x2_meta_workspace_bytes(5000, 1000) > 4 * 1000 * 4
+    d = _lib.ConvDesc()
+    d.E, d.T, d.D, d.H, d.C, d.S, d.R, d.A = 100, 2000, 128, 16, 8, 42, 6, 128
+    fwd = L.x2_sbfconv_fwd_workspace_bytes(ctypes.byref(d))
+    bwd = L.x2_sbfconv_bwd_workspace_bytes(ctypes.byref(d))
+    assert fwd >= 100 * 128 * 4 and bwd >= 2 * 2000 * 128 * 4
+
+
+def test_conv_constructor_contract():
+    from x2gnn_b200.sbftransformer_conv import SBFTransformerConv
+    c = SBFTransformerConv(128, 8, heads=16, sbf_dim=42, rbf_dim=6, dropout=0, edge_dim=128)
+    sd = c.state_dict()
+    want = [("lin_key.weight", (128, 128)), ("lin_key.bias", (128,)), ("lin_query.weight", (128, 128)),
+            ("lin_query.bias", (128,)), ("lin_value.weight", (128, 128)), ("lin_value.bias", (128,)),
+            ("lin_edge.weight", (128, 128)), ("lin_skip.weight", (128, 128)), ("lin_skip.bias", (128,)),
+            ("lin_sbf.weight", (128, 42)), ("lin_sbf.bias", (128,)), ("lin_rbf.weight", (128, 6))]
+    assert [(k, tuple(v.shape)) for k, v in sd.items()] == want
+    assert sum(v.numel() for v in sd.values()) == 88704
+    assert float(c.lin_sbf.bias.abs().max()) == 0.0
+    assert repr(c) == "SBFTransformerConv(128, 8, heads=16)"
+    c2 = copy.deepcopy(c)                                                   # EMA deep-copies the model
+    assert all(torch.equal(a, b) for a, b in zip(c.state_dict().values(), c2.state_dict().values()))
+    c.reset_parameters()
+    for kw, absent in ((dict(edge_dim=None), "lin_edge.weight"), (dict(edge_dim=4, bias=False), "lin_skip.bias")):
+        assert absent not in SBFTransformerConv(32, 8, heads=4, sbf_dim=6, rbf_dim=4, **kw).state_dict()
+    b = SBFTransformerConv(32, 8, heads=4, sbf_dim=6, rbf_dim=4, edge_dim=4, beta=True, concat=False)
+    assert tuple(b.state_dict()["lin_beta.weight"].shape) == (1, 24)
+    assert tuple(b.state_dict()["lin_skip.weight"].shape) == (8, 32)
+
+
+def test_conv_state_dict_matches_oracle_and_golden(golden):
+    from oracle.conv import OracleSBFTransformerConv
+    from x2gnn_b200.sbftransformer_conv import SBFTransformerConv
+    rec = golden("conv")["cfg"]
+    D, H, S, R, A = rec["dims"]
+    mine = SBFTransformerConv(D, D // H, heads=H, sbf_dim=S, rbf_dim=R, edge_dim=A)
+    mine.load_state_dict(rec["state_dict"], strict=True)     # a reference checkpoint loads unchanged
+    ref = OracleSBFTransformerConv(D, D // H, heads=H, sbf_dim=S, rbf_dim=R, edge_dim=A)
+    assert list(ref.state_dict()) == list(mine.state_dict())
+
+
+def test_basis_modules_contract():
+    from x2gnn_b200 import angular_basis_layer, basis_func, envelop, radial_basis_layer
+    from oracle import bases as ob
+    assert list(radial_basis_layer.RadialBasis(6, 5.0).state_dict()) == ["frequencies"]
+    assert not list(radial_basis_layer.RadialBasis(6, 5.0, Trainable=False).state_dict())
+    assert not list(angular_basis_layer.F_B_2D(7, 6, 5.0, 5).state_dict())
+    e = envelop.poly_envelop(5.0, 5)
+    assert (e.p, e.a, e.b, e.c) == (6, -28.0, 48, -21.0)
+    z, n = basis_func.bessel_tables(7, 6)
+    zo, no = ob.bessel_tables(7, 6)
+    assert (z == zo).all() and (n == no.astype("float32")).all()
+    assert abs(float(z[6, 5]) - 27.507868) < 1e-5 and abs(float(n[0, 0]) - 4.442883) < 1e-5   # App. B
+    assert abs(basis_func.sph_harm_prefactor(2, 0) - 0.63078313) < 1e-7
+    with pytest.raises(AssertionError):
+        angular_basis_layer.F_B_2D(7, 65, 5.0)
+
+
+def test_no_cpu_fallback():
+    from x2gnn_b200 import _lib, edge_graph, envelop
+    from x2gnn_b200.sbftransformer_conv import SBFTransformerConv
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only behaviour")
+    with pytest.raises(_lib.X2Error):
+        edge_graph.vertex_to_edge_2(torch.zeros(2, 3, dtype=torch.long), 3)
+    with pytest.raises(_lib.X2Error):
+        envelop.poly_envelop(5.0, 5)(torch.ones(4))
+    c = SBFTransformerConv(32, 8, heads=4, sbf_dim=6, rbf_dim=4, edge_dim=4)
+    with pytest.raises(_lib.X2Error):
+        c(torch.zeros(2, 6), torch.zeros(3, 4), x=torch.zeros(3, 32),
+          edge_index=torch.zeros(2, 2, dtype=torch.long), edge_attr=torch.zeros(2, 4))
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under the package (or the drop-in modules) may
+    import it, nor read /root/reference."""
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            src = open(os.path.join(dirpath, f)).read()
+            assert "/root/reference" not in src, f
+            for node in ast.walk(ast.parse(src)):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                assert not any(n == "oracle" or n.startswith("oracle.") for n in names), f
+
+
+def test_dropin_install():
+    import importlib
+    import sys
+    import x2gnn_b200
+    x2gnn_b200.install()
+    for m in x2gnn_b200.DROPIN_MODULES:
+        mod = importlib.import_module(m)
+        assert mod.__file__.startswith(x2gnn_b200.DROPIN_DIR)
+    import sbftransformer_conv
+    from x2gnn_b200.sbftransformer_conv import SBFTransformerConv
+    assert sbftransformer_conv.SBFTransformerConv is SBFTransformerConv
+    sys.path.remove(x2gnn_b200.DROPIN_DIR)
+    for m in x2gnn_b200.DROPIN_MODULES:
+        sys.modules.pop(m, None)

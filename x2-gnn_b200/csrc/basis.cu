@@ -1,0 +1,276 @@
+// basis.cu -- fused envelope / radial / spherical-Bessel x spherical-harmonic basis kernels.
+// Replaces envelop.py:16-21, radial_basis_layer.py:36-40 and angular_basis_layer.py:80-93 (~150
+// elementwise launches of sympy-lambdified closures in the reference) with one E-scale table
+// kernel and one T-scale streaming kernel.
+//
+// Numerics: the reference evaluates closed-form j_l polynomials in 1/x in fp32, which cancel
+// catastrophically for l >= 4.  Here everything that is E-scale (envelope,
+// j_l) or O(L) per triplet (Legendre recurrence) runs in fp64 and is rounded to fp32 once, so
+// results track the fp64 evaluation of the reference formulas to ~1 ulp.  The T-scale part is a
+// pure HBM stream: read theta[T], idx[T] and an L2-resident table row, write sbf[T, L*R].
+#include "common.cuh"
+
+namespace x2 {
+
+constexpr int kMaxL = 32;
+
+__device__ __forceinline__ double envelope_d(double d, double inv_cutoff, int p, double a,
+                                             double b, double c) {
+  const double x = d * inv_cutoff;
+  double xp = 1.0;  // x^(p-1)
+  for (int i = 0; i < p - 1; ++i) xp *= x;
+  return 1.0 / x + xp * (a + x * (b + x * c));
+}
+
+__global__ void k_envelope(const float* __restrict__ d, int64_t n, float inv_cutoff, int p, float a,
+                           float b, float c, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // the reference forms x = d * (1/cutoff) in fp32 (envelop.py:17); keep that product, then
+  // evaluate the polynomial in fp64
+  const float xs = d[i] * inv_cutoff;
+  out[i] = (float)envelope_d((double)xs, 1.0, p, (double)a, (double)b, (double)c);
+}
+
+__global__ void k_radial_fwd(const float* __restrict__ d, const float* __restrict__ freq,
+                             const float* __restrict__ env, int64_t n, int R, float inv_cutoff,
+                             float* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * R) return;
+  const int64_t e = idx / R;
+  const int r = (int)(idx - e * R);
+  const float ds = d[e] * inv_cutoff;              // radial_basis_layer.py:37
+  float v = sinf(freq[r] * ds);                    // :40
+  if (env) v *= env[e];
+  out[idx] = v;
+}
+
+// Stage 1 of the frequency gradient: each warp owns a fixed, contiguous row range and keeps one
+// running sum per basis index (lane r, r+32, ...); also writes grad_d if requested.
+__global__ void k_radial_bwd_partial(const float* __restrict__ d, const float* __restrict__ freq,
+                                     const float* __restrict__ env, const float* __restrict__ go,
+                                     int64_t n, int R, float inv_cutoff, int64_t rows_per_warp,
+                                     int64_t nwarps, float* __restrict__ partial,
+                                     float* __restrict__ grad_d) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nwarps) return;
+  const int64_t r0 = w * rows_per_warp;
+  const int64_t r1 = min(n, r0 + rows_per_warp);
+  float acc0 = 0.f, acc1 = 0.f;  // R <= 64
+  const float f0 = lane < R ? freq[lane] : 0.f;
+  const float f1 = lane + 32 < R ? freq[lane + 32] : 0.f;
+  for (int64_t e = r0; e < r1; ++e) {
+    const float ds = d[e] * inv_cutoff;
+    const float ev = env ? env[e] : 1.f;
+    float gd = 0.f;
+    if (lane < R) {
+      const float g = go[e * R + lane] * ev * cosf(f0 * ds);
+      acc0 += g * ds;
+      gd += g * f0;
+    }
+    if (lane + 32 < R) {
+      const float g = go[e * R + lane + 32] * ev * cosf(f1 * ds);
+      acc1 += g * ds;
+      gd += g * f1;
+    }
+    if (grad_d) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) gd += __shfl_xor_sync(0xffffffffu, gd, o);
+      if (lane == 0) grad_d[e] = gd * inv_cutoff;
+    }
+  }
+  if (lane < R) partial[w * R + lane] = acc0;
+  if (lane + 32 < R) partial[w * R + lane + 32] = acc1;
+}
+
+__global__ void k_radial_bwd_final(const float* __restrict__ partial, int64_t nwarps, int R,
+                                   float* __restrict__ grad_freq) {
+  const int r = threadIdx.x;
+  if (r >= R) return;
+  float s = 0.f;
+  for (int64_t w = 0; w < nwarps; ++w) s += partial[w * R + r];  // fixed order => deterministic
+  grad_freq[r] = s;
+}
+
+// spherical Bessel j_l(x), fp64.  Power series where upward recurrence is unstable (x < ~l).
+__device__ double sph_jl(int l, double x) {
+  const double thr = fmax(1.0, 0.75 * (double)l);
+  if (x < thr) {
+    // j_l(x) = x^l/(2l+1)!! * sum_k (-x^2/2)^k / (k! (2l+3)(2l+5)...(2l+2k+1))
+    double pref = 1.0;
+    for (int i = 1; i <= l; ++i) pref *= x / (double)(2 * i + 1);
+    const double q = -0.5 * x * x;
+    double term = 1.0, sum = 1.0;
+    for (int k = 1; k < 80; ++k) {
+      term *= q / ((double)k * (double)(2 * l + 2 * k + 1));
+      sum += term;
+      if (fabs(term) < 1e-18 * fabs(sum)) break;
+    }
+    return pref * sum;
+  }
+  double s, c;
+  sincos(x, &s, &c);
+  const double inv = 1.0 / x;
+  double jm = s * inv;                    // j_0
+  if (l == 0) return jm;
+  double j = (s * inv - c) * inv;         // j_1
+  for (int n = 1; n < l; ++n) {
+    const double jn = (double)(2 * n + 1) * inv * j - jm;
+    jm = j;
+    j = jn;
+  }
+  return j;
+}
+
+__global__ void k_sbf_table(const float* __restrict__ d, int64_t n, int L, int R,
+                            const float* __restrict__ zeros, const float* __restrict__ norm,
+                            float cutoff, float env_cutoff, int p, float a, float b, float c,
+                            float* __restrict__ table) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int S = L * R;
+  if (idx >= n * S) return;
+  const int64_t e = idx / S;
+  const int col = (int)(idx - e * S);
+  const int l = col / R;
+  const double dd = (double)d[e];
+  const double x = (double)zeros[col] * (dd / (double)cutoff);   // angular_basis_layer.py:81
+  const double env = envelope_d(dd, 1.0 / (double)env_cutoff, p, (double)a, (double)b, (double)c);
+  table[idx] = (float)(env * (double)norm[col] * sph_jl(l, x));
+}
+
+// Y_l0(theta) = sqrt((2l+1)/(4 pi)) P_l(cos theta), l < L, three-term Legendre recurrence
+// (basis_func.py:94-96), fp64.
+__device__ __forceinline__ void y_l0(double theta, int L, float* out, int stride) {
+  const double c = cos(theta);
+  double p0 = 1.0, p1 = c;
+  const double inv4pi = 0.07957747154594767;
+  out[0] = (float)sqrt(inv4pi);
+  if (L > 1) out[stride] = (float)(sqrt(3.0 * inv4pi) * c);
+  for (int j = 2; j < L; ++j) {
+    const double pj = ((double)(2 * j - 1) * c * p1 - (double)(j - 1) * p0) / (double)j;
+    p0 = p1;
+    p1 = pj;
+    out[j * stride] = (float)(sqrt((double)(2 * j + 1) * inv4pi) * pj);
+  }
+}
+
+constexpr int kSbfTile = 64;  // triplets per block
+
+__global__ void __launch_bounds__(256)
+k_sbf_fwd(const float* __restrict__ table, const float* __restrict__ angles,
+          const int64_t* __restrict__ idx, int64_t T, int64_t E, int L, int R,
+          float* __restrict__ out) {
+  __shared__ float ys[kSbfTile * kMaxL];
+  __shared__ int64_t rows[kSbfTile];
+  const int S = L * R;
+  const int64_t t0 = (int64_t)blockIdx.x * kSbfTile;
+  const int nt = (int)min((int64_t)kSbfTile, T - t0);
+  if (threadIdx.x < nt) {
+    y_l0((double)angles[t0 + threadIdx.x], L, ys + threadIdx.x * L, 1);
+    int64_t r = idx[t0 + threadIdx.x];
+    rows[threadIdx.x] = (r < 0 || r >= E) ? 0 : r;  // bounds are validated by the caller
+  }
+  __syncthreads();
+  const int total = nt * S;
+  float* o = out + t0 * S;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int tb = i / S;
+    const int col = i - tb * S;
+    o[i] = __ldg(table + rows[tb] * S + col) * ys[tb * L + col / R];
+  }
+}
+
+__global__ void k_angular_fwd(const float* __restrict__ angles, int64_t T, int L,
+                              float* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  y_l0((double)angles[t], L, out + t * L, 1);
+}
+
+}  // namespace x2
+
+using namespace x2;
+
+extern "C" {
+
+int x2_envelope_fwd(const float* d, int64_t n, float inv_cutoff, int32_t p, float a, float b,
+                    float c, float* out, void* stream) {
+  X2_CHECK_ARG(n >= 0 && p >= 1, "x2_envelope_fwd: bad arguments");
+  if (n == 0) return X2_OK;
+  k_envelope<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(d, n, inv_cutoff, p, a, b, c, out);
+  X2_LAUNCH_OK();
+  return X2_OK;
+}
+
+int x2_radial_fwd(const float* d, const float* freq, const float* env, int64_t n, int32_t R,
+                  float inv_cutoff, float* out, void* stream) {
+  X2_CHECK_ARG(n >= 0 && R >= 1, "x2_radial_fwd: bad arguments");
+  if (n == 0) return X2_OK;
+  k_radial_fwd<<<(unsigned)cdiv(n * R, 256), 256, 0, (cudaStream_t)stream>>>(d, freq, env, n, R, inv_cutoff, out);
+  X2_LAUNCH_OK();
+  return X2_OK;
+}
+
+static int64_t radial_bwd_warps(int64_t n) {
+  int64_t w = cdiv(n, 64);                 // >= 64 rows per warp
+  const int64_t cap = (int64_t)kNumSM * 32;  // 148 SMs x 32 warps
+  if (w > cap) w = cap;
+  if (w < 1) w = 1;
+  return w;
+}
+
+size_t x2_radial_bwd_workspace_bytes(int64_t n, int32_t R) {
+  return align_up((size_t)radial_bwd_warps(n) * (size_t)R * sizeof(float), 256) + 256;
+}
+
+int x2_radial_bwd(const float* d, const float* freq, const float* env, const float* grad_out,
+                  int64_t n, int32_t R, float inv_cutoff, float* grad_freq, float* grad_d,
+                  void* ws, size_t ws_bytes, void* stream) {
+  X2_CHECK_ARG(n >= 0 && R >= 1 && R <= 64, "x2_radial_bwd: need 1 <= R <= 64 (got %d)", R);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ws_bytes < x2_radial_bwd_workspace_bytes(n, R)) { set_error("x2_radial_bwd: workspace too small"); return X2_EWORKSPACE; }
+  if (n == 0) {
+    X2_CUDA_OK(cudaMemsetAsync(grad_freq, 0, R * sizeof(float), st));
+    return X2_OK;
+  }
+  const int64_t nw = radial_bwd_warps(n);
+  const int64_t rpw = cdiv(n, nw);
+  float* partial = static_cast<float*>(ws);
+  k_radial_bwd_partial<<<(unsigned)cdiv(nw * 32, 128), 128, 0, st>>>(d, freq, env, grad_out, n, R, inv_cutoff,
+                                                                   rpw, nw, partial, grad_d);
+  X2_LAUNCH_OK();
+  k_radial_bwd_final<<<1, 64, 0, st>>>(partial, nw, R, grad_freq);
+  X2_LAUNCH_OK();
+  return X2_OK;
+}
+
+int x2_sbf_table(const float* d, int64_t n, int32_t L, int32_t R, const float* zeros,
+                 const float* norm, float cutoff, float env_cutoff, int32_t p, float a, float b,
+                 float c, float* table, void* stream) {
+  X2_CHECK_ARG(n >= 0 && L >= 1 && L <= kMaxL && R >= 1 && R <= 64, "x2_sbf_table: need 1<=L<=%d, 1<=R<=64", kMaxL);
+  if (n == 0) return X2_OK;
+  k_sbf_table<<<(unsigned)cdiv(n * L * R, 128), 128, 0, (cudaStream_t)stream>>>(d, n, L, R, zeros, norm, cutoff,
+                                                                            env_cutoff, p, a, b, c, table);
+  X2_LAUNCH_OK();
+  return X2_OK;
+}
+
+int x2_sbf_fwd(const float* table, const float* angles, const int64_t* idx, int64_t T, int64_t E,
+               int32_t L, int32_t R, float* out, void* stream) {
+  X2_CHECK_ARG(T >= 0 && L >= 1 && L <= kMaxL && R >= 1 && R <= 64, "x2_sbf_fwd: need 1<=L<=%d, 1<=R<=64", kMaxL);
+  if (T == 0) return X2_OK;
+  k_sbf_fwd<<<(unsigned)cdiv(T, kSbfTile), 256, 0, (cudaStream_t)stream>>>(table, angles, idx, T, E, L, R, out);
+  X2_LAUNCH_OK();
+  return X2_OK;
+}
+
+int x2_angular_fwd(const float* angles, int64_t T, int32_t L, float* out, void* stream) {
+  X2_CHECK_ARG(T >= 0 && L >= 1 && L <= kMaxL, "x2_angular_fwd: need 1<=L<=%d", kMaxL);
+  if (T == 0) return X2_OK;
+  k_angular_fwd<<<(unsigned)cdiv(T, 256), 256, 0, (cudaStream_t)stream>>>(angles, T, L, out);
+  X2_LAUNCH_OK();
+  return X2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,550 @@
+// conv.cu -- SBFTransformerConv forward / backward (sbftransformer_conv.py:93-162 + the PyG
+// propagate / softmax / sum-aggregate it drives), X2_MODE_FP32 path.
+//
+// Forward:   rbf filter -> one batched node GEMM (Q | K | V | skip) -> T-row projections
+//            (lin_edge, lin_sbf) -> ONE segmented attention kernel, warp per target line-node,
+//            that gathers K/V rows, forms logits, runs an online segment softmax, modulates the
+//            values by the sbf gate and aggregates -- deterministic and atomic-free (replaces 3
+//            index_selects, ~8 scatter-softmax launches, 3 elementwise passes and an atomicAdd
+//            scatter in the reference).
+// Backward:  pass 1 (warp per target) recomputes the attention weights from the saved
+//            log-sum-exp and emits dQ, d(lin_edge out), d(lin_sbf out); pass 2 (warp per SOURCE
+//            line-node, using the source-sorted permutation) accumulates dK/dV without atomics;
+//            the Linear gradients are dgrad / split-K wgrad GEMMs with fixed-order reductions.
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+namespace x2 {
+
+// ------------------------------------------------------------------ small vector helpers
+template <int VEC>
+__device__ __forceinline__ void ldv(const float* __restrict__ p, float (&r)[VEC]) {
+  if constexpr (VEC == 8) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+  } else if constexpr (VEC == 4) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+  } else if constexpr (VEC == 2) {
+    const float2 a = *reinterpret_cast<const float2*>(p);
+    r[0] = a.x; r[1] = a.y;
+  } else {
+    r[0] = p[0];
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void stv(float* __restrict__ p, const float (&r)[VEC]) {
+  if constexpr (VEC == 8) {
+    *reinterpret_cast<float4*>(p) = make_float4(r[0], r[1], r[2], r[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(r[4], r[5], r[6], r[7]);
+  } else if constexpr (VEC == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(r[0], r[1], r[2], r[3]);
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(r[0], r[1]);
+  } else {
+    p[0] = r[0];
+  }
+}
+
+// sum over the `lph` (power of two) adjacent lanes that share a head
+__device__ __forceinline__ float head_sum(float v, int lph) {
+  for (int o = 1; o < lph; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Attention-dropout keep factor for (triplet, head): 0 or 1/(1-p); counter-based so forward and
+// backward regenerate the same mask.
+__device__ __forceinline__ float keep_scale(uint64_t seed, int64_t t, int h, int H, float p) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(t * H + h + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
+  return u < p ? 0.f : 1.0f / (1.0f - p);
+}
+
+// ------------------------------------------------------------------ rbf filter
+// xs[e,:] = x[e,:] * (rbf[e,:] . W_r^T)   (sbftransformer_conv.py:99-100); optionally also F.
+__global__ void k_rbf_filter(const float* __restrict__ x, const float* __restrict__ rbf,
+                             const float* __restrict__ w_rbf, int64_t E, int D, int R,
+                             float* __restrict__ xs, float* __restrict__ F) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= E * D) return;
+  const int64_t e = idx / D;
+  const int d = (int)(idx - e * D);
+  float f = 0.f;
+  for (int r = 0; r < R; ++r) f = fmaf(rbf[e * R + r], __ldg(w_rbf + d * R + r), f);
+  xs[idx] = x[idx] * f;
+  if (F) F[idx] = f;
+}
+
+// dx += dxs * F ; dF = dxs * x (written over dxs)       (App. A last line)
+__global__ void k_filter_bwd(const float* __restrict__ x, const float* __restrict__ F,
+                             float* __restrict__ dxs, float* __restrict__ dx, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float g = dxs[i];
+  dx[i] += g * F[i];
+  dxs[i] = g * x[i];
+}
+
+// ------------------------------------------------------------------ segmented attention fwd
+template <int VEC>
+__global__ void __launch_bounds__(128)
+k_attn_fwd(const float* __restrict__ qkvs, int ldq, const float* __restrict__ ea,
+           const float* __restrict__ sg, const int32_t* __restrict__ src,
+           const int32_t* __restrict__ rowptr, const int32_t* __restrict__ order, int64_t E, int H,
+           int C, float scale, int fuse_skip, float dropout_p, uint64_t seed,
+           float* __restrict__ attn, float* __restrict__ out, float* __restrict__ lse,
+           float* __restrict__ alpha) {
+  constexpr int D = 32 * VEC;
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (e >= E) return;
+  const int lane = threadIdx.x & 31;
+  const int ch = lane * VEC;
+  const int head = ch / C;
+  const int lph = C / VEC;
+  const bool leader = (ch % C) == 0;
+
+  float q[VEC];
+  ldv<VEC>(qkvs + e * ldq + ch, q);
+  const int beg = rowptr[e], end = rowptr[e + 1];
+
+  float m = -INFINITY, z = 0.f;
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+
+  for (int base = beg; base < end; base += 32) {
+    const int my = base + lane;
+    int t_l = 0, s_l = 0;
+    if (my < end) {
+      t_l = order[my];
+      s_l = src[t_l];
+    }
+    const int cnt = min(32, end - base);
+#pragma unroll 2
+    for (int i = 0; i < cnt; ++i) {
+      const int t = __shfl_sync(0xffffffffu, t_l, i);
+      const int s = __shfl_sync(0xffffffffu, s_l, i);
+      float k[VEC], v[VEC], g[VEC], a_[VEC];
+      ldv<VEC>(qkvs + (int64_t)s * ldq + D + ch, k);
+      ldv<VEC>(qkvs + (int64_t)s * ldq + 2 * D + ch, v);
+      ldv<VEC>(sg + (int64_t)t * D + ch, g);
+      if (ea) ldv<VEC>(ea + (int64_t)t * D + ch, a_);
+      else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) a_[j] = 0.f;
+      }
+      float dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) dot = fmaf(q[j], k[j] + a_[j], dot);
+      const float a = head_sum(dot, lph) * scale;           // :150
+      if (alpha && leader) alpha[(int64_t)t * H + head] = a;  // raw logit, normalised below
+      const float mn = fmaxf(m, a);
+      const float corr = expf(m - mn);                    // exp(-inf) = 0 on the first triplet
+      const float p = expf(a - mn);
+      z = z * corr + p;
+      float pk = p;
+      if (dropout_p > 0.f) pk *= keep_scale(seed, t, head, H, dropout_p);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc[j] = acc[j] * corr + pk * (v[j] + a_[j]) * g[j];  // :155-160
+      m = mn;
+    }
+  }
+  const float inv = 1.0f / (z + 1e-16f);                    // PyG softmax: out / (sum + 1e-16)
+  float o[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) o[i] = acc[i] * inv;
+  stv<VEC>(attn + e * D + ch, o);
+  if (fuse_skip) {
+    float sk[VEC];
+    ldv<VEC>(qkvs + e * ldq + 3 * D + ch, sk);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o[i] += sk[i];            // :127
+  }
+  stv<VEC>(out + e * D + ch, o);
+  const float l = (end > beg) ? m + logf(z) : 0.f;
+  if (leader) lse[e * H + head] = l;
+  if (alpha) {
+    __syncwarp();
+    for (int idx = beg; idx < end; ++idx) {
+      const int t = order[idx];
+      if (leader) {
+        const float a = alpha[(int64_t)t * H + head];
+        alpha[(int64_t)t * H + head] = expf(a - m) * inv;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward pass 1 (by target)
+template <int VEC>
+__global__ void __launch_bounds__(128)
+k_attn_bwd_tgt(const float* __restrict__ qkvs, int ldq, const float* __restrict__ ea,
+               const float* __restrict__ sg, const float* __restrict__ attn,
+               const float* __restrict__ lse, const float* __restrict__ gout,
+               const int32_t* __restrict__ src, const int32_t* __restrict__ rowptr,
+               const int32_t* __restrict__ order, int64_t E, int H, int C, float scale,
+               float dropout_p, uint64_t seed, float* __restrict__ dqkv, int ldg,
+               float* __restrict__ dea, float* __restrict__ dsg, float* __restrict__ al,
+               float* __restrict__ da_out) {
+  constexpr int D = 32 * VEC;
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (e >= E) return;
+  const int lane = threadIdx.x & 31;
+  const int ch = lane * VEC;
+  const int head = ch / C;
+  const int lph = C / VEC;
+  const bool leader = (ch % C) == 0;
+
+  float q[VEC], g[VEC], o[VEC], dq[VEC];
+  ldv<VEC>(qkvs + e * ldq + ch, q);
+  ldv<VEC>(gout + e * D + ch, g);
+  ldv<VEC>(attn + e * D + ch, o);
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    r = fmaf(g[i], o[i], r);
+    dq[i] = 0.f;
+  }
+  r = head_sum(r, lph);                       // r_eh = sum_t alpha dalpha = <G, O>  (App. A)
+  const float l = lse[e * H + head];
+  const int beg = rowptr[e], end = rowptr[e + 1];
+
+  for (int base = beg; base < end; base += 32) {
+    const int my = base + lane;
+    int t_l = 0, s_l = 0;
+    if (my < end) {
+      t_l = order[my];
+      s_l = src[t_l];
+    }
+    const int cnt = min(32, end - base);
+#pragma unroll 2
+    for (int i = 0; i < cnt; ++i) {
+      const int t = __shfl_sync(0xffffffffu, t_l, i);
+      const int s = __shfl_sync(0xffffffffu, s_l, i);
+      float k[VEC], v[VEC], sgv[VEC], a_[VEC];
+      ldv<VEC>(qkvs + (int64_t)s * ldq + D + ch, k);
+      ldv<VEC>(qkvs + (int64_t)s * ldq + 2 * D + ch, v);
+      ldv<VEC>(sg + (int64_t)t * D + ch, sgv);
+      if (ea) ldv<VEC>(ea + (int64_t)t * D + ch, a_);
+      else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) a_[j] = 0.f;
+      }
+      float dot = 0.f, dal = 0.f;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        k[j] += a_[j];                         // kk
+        v[j] += a_[j];                         // vv
+        dot = fmaf(q[j], k[j], dot);
+        dal = fmaf(g[j] * v[j], sgv[j], dal);
+      }
+      // both reductions share the shuffle steps
+      for (int off = 1; off < lph; off <<= 1) {
+        dot += __shfl_xor_sync(0xffffffffu, dot, off);
+        dal += __shfl_xor_sync(0xffffffffu, dal, off);
+      }
+      const float alpha = expf(dot * scale - l);
+      float keep = 1.f;
+      if (dropout_p > 0.f) keep = keep_scale(seed, t, head, H, dropout_p);
+      const float alpha_d = alpha * keep;      // weight actually applied to the value
+      const float da = alpha * (dal * keep - r);
+      const float sda = scale * da;
+      float o_ea[VEC], o_sg[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        dq[j] = fmaf(sda, k[j], dq[j]);
+        const float dkk = sda * q[j];
+        const float dvv = g[j] * sgv[j] * alpha_d;
+        o_ea[j] = dkk + dvv;
+        o_sg[j] = g[j] * v[j] * alpha_d;
+      }
+      if (dea) stv<VEC>(dea + (int64_t)t * D + ch, o_ea);
+      stv<VEC>(dsg + (int64_t)t * D + ch, o_sg);
+      if (leader) {
+        al[(int64_t)t * H + head] = alpha_d;
+        da_out[(int64_t)t * H + head] = da;
+      }
+    }
+  }
+  stv<VEC>(dqkv + e * ldg + ch, dq);
+}
+
+// ------------------------------------------------------------------ backward pass 2 (by source)
+template <int VEC>
+__global__ void __launch_bounds__(128)
+k_attn_bwd_src(const float* __restrict__ qkvs, int ldq, const float* __restrict__ sg,
+               const float* __restrict__ gout, const float* __restrict__ al,
+               const float* __restrict__ da_in, const int32_t* __restrict__ tgt,
+               const int32_t* __restrict__ rowptr_src, const int32_t* __restrict__ order_src,
+               int64_t E, int H, int C, float scale, float* __restrict__ dqkv, int ldg) {
+  constexpr int D = 32 * VEC;
+  const int64_t f = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (f >= E) return;
+  const int lane = threadIdx.x & 31;
+  const int ch = lane * VEC;
+  const int head = ch / C;
+  float dk[VEC], dv[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) dk[i] = dv[i] = 0.f;
+  const int beg = rowptr_src[f], end = rowptr_src[f + 1];
+  for (int base = beg; base < end; base += 32) {
+    const int my = base + lane;
+    int t_l = 0, e_l = 0;
+    if (my < end) {
+      t_l = order_src[my];
+      e_l = tgt[t_l];
+    }
+    const int cnt = min(32, end - base);
+#pragma unroll 2
+    for (int i = 0; i < cnt; ++i) {
+      const int t = __shfl_sync(0xffffffffu, t_l, i);
+      const int e = __shfl_sync(0xffffffffu, e_l, i);
+      float q[VEC], g[VEC], sgv[VEC];
+      ldv<VEC>(qkvs + (int64_t)e * ldq + ch, q);
+      ldv<VEC>(gout + (int64_t)e * D + ch, g);
+      ldv<VEC>(sg + (int64_t)t * D + ch, sgv);
+      const float a = al[(int64_t)t * H + head];
+      const float sda = scale * da_in[(int64_t)t * H + head];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        dv[j] = fmaf(g[j] * sgv[j], a, dv[j]);   // dV[s] += G . Sg . alpha
+        dk[j] = fmaf(sda, q[j], dk[j]);          // dK[s] += sigma da Q[e]
+      }
+    }
+  }
+  stv<VEC>(dqkv + f * ldg + D + ch, dk);
+  stv<VEC>(dqkv + f * ldg + 2 * D + ch, dv);
+}
+
+// ------------------------------------------------------------------ host side
+static int check_desc(const x2_conv_desc* d) {
+  X2_CHECK_ARG(d != nullptr, "conv: null descriptor");
+  X2_CHECK_ARG(d->E >= 0 && d->T >= 0 && d->E < 2147483647LL && d->T < 2147483647LL, "conv: bad E/T");
+  X2_CHECK_ARG(d->mode == X2_MODE_FP32, "conv: unknown mode %d", d->mode);
+  X2_CHECK_ARG(d->D == d->H * d->C && d->H >= 1 && d->C >= 1, "conv: D=%d != H*C=%d*%d", d->D, d->H, d->C);
+  X2_CHECK_ARG(d->D == 32 || d->D == 64 || d->D == 128 || d->D == 256,
+               "conv: heads*out_channels must be 32, 64, 128 or 256 (got %d)", d->D);
+  const int vec = d->D / 32;
+  X2_CHECK_ARG(d->C % vec == 0 && ((d->C / vec) & (d->C / vec - 1)) == 0 && d->C / vec <= 32,
+               "conv: out_channels=%d unsupported for D=%d (need C %% (D/32) == 0 and C/(D/32) a power of two)",
+               d->C, d->D);
+  X2_CHECK_ARG(d->S >= 1 && d->R >= 1 && d->A >= 0, "conv: bad S/R/A");
+  X2_CHECK_ARG(d->dropout_p >= 0.f && d->dropout_p < 1.f, "conv: dropout must be in [0,1)");
+  X2_CHECK_ARG((d->A > 0) == (d->w_edge != nullptr), "conv: w_edge must be given iff A > 0");
+  return X2_OK;
+}
+
+struct FwdWs { float* xs; };
+static size_t fwd_layout(const x2_conv_desc* d, void* ws, FwdWs* w) {
+  Arena a(ws, (size_t)-1);
+  w->xs = a.take<float>((size_t)d->E * d->D + 4);
+  return align_up(a.off, 256) + 256;
+}
+
+struct BwdWs {
+  float *dea, *dsg, *al, *da, *dqkv, *xs, *F, *dxs, *wg;
+  size_t wg_floats;
+};
+static size_t bwd_layout(const x2_conv_desc* d, void* ws, BwdWs* w) {
+  Arena a(ws, (size_t)-1);
+  const size_t ED = (size_t)d->E * d->D, TD = (size_t)d->T * d->D, TH = (size_t)d->T * d->H;
+  w->dea = d->A > 0 ? a.take<float>(TD + 4) : nullptr;
+  w->dsg = a.take<float>(TD + 4);
+  w->al = a.take<float>(TH + 4);
+  w->da = a.take<float>(TH + 4);
+  w->dqkv = a.take<float>(3 * ED + 4);
+  w->xs = a.take<float>(ED + 4);
+  w->F = a.take<float>(ED + 4);
+  w->dxs = a.take<float>(ED + 4);
+  size_t wg = wgrad_workspace_floats(d->T, d->D, d->A > 0 ? d->A : 1);
+  size_t t2 = wgrad_workspace_floats(d->T, d->D, d->S);
+  if (t2 > wg) wg = t2;
+  t2 = wgrad_workspace_floats(d->E, d->D, d->D);
+  if (t2 > wg) wg = t2;
+  t2 = wgrad_workspace_floats(d->E, d->D, d->R);
+  if (t2 > wg) wg = t2;
+  w->wg_floats = wg;
+  w->wg = a.take<float>(wg);
+  return align_up(a.off, 256) + 256;
+}
+
+template <int VEC>
+static int launch_attn_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, float* alpha,
+                           cudaStream_t st) {
+  const float scale = 1.0f / sqrtf((float)d->C);
+  k_attn_fwd<VEC><<<(unsigned)cdiv(d->E * 32, 128), 128, 0, st>>>(
+      s->qkvs, 4 * d->D, d->A > 0 ? s->ea : nullptr, s->sg, d->src, d->rowptr_tgt, d->order_tgt, d->E,
+      d->H, d->C, scale, d->fuse_skip, d->dropout_p, d->seed, s->attn, out, s->lse, alpha);
+  X2_LAUNCH_OK();
+  return X2_OK;
+}
+
+template <int VEC>
+static int launch_attn_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* gout,
+                           const BwdWs& w, cudaStream_t st) {
+  const float scale = 1.0f / sqrtf((float)d->C);
+  const unsigned grid = (unsigned)cdiv(d->E * 32, 128);
+  phase_begin(st);
+  k_attn_bwd_tgt<VEC><<<grid, 128, 0, st>>>(s->qkvs, 4 * d->D, d->A > 0 ? s->ea : nullptr, s->sg, s->attn,
+                                            s->lse, gout, d->src, d->rowptr_tgt, d->order_tgt, d->E, d->H,
+                                            d->C, scale, d->dropout_p, d->seed, w.dqkv, 3 * d->D, w.dea,
+                                            w.dsg, w.al, w.da);
+  X2_LAUNCH_OK();
+  phase_end(X2_PHASE_ATTN_BWD_TGT, st);
+  k_attn_bwd_src<VEC><<<grid, 128, 0, st>>>(s->qkvs, 4 * d->D, s->sg, gout, w.al, w.da, d->tgt,
+                                            d->rowptr_src, d->order_src, d->E, d->H, d->C, scale, w.dqkv,
+                                            3 * d->D);
+  X2_LAUNCH_OK();
+  phase_end(X2_PHASE_ATTN_BWD_SRC, st);
+  return X2_OK;
+}
+
+}  // namespace x2
+
+using namespace x2;
+
+#define X2_TRY(expr)            \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != X2_OK) return _rc; \
+  } while (0)
+
+extern "C" {
+
+size_t x2_sbfconv_fwd_workspace_bytes(const x2_conv_desc* d) {
+  if (!d) return 0;
+  FwdWs w;
+  return fwd_layout(d, nullptr, &w);
+}
+
+size_t x2_sbfconv_bwd_workspace_bytes(const x2_conv_desc* d) {
+  if (!d) return 0;
+  BwdWs w;
+  return bwd_layout(d, nullptr, &w);
+}
+
+int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, float* alpha,
+                   void* ws, size_t ws_bytes, void* stream) {
+  X2_TRY(check_desc(d));
+  X2_CHECK_ARG(s && s->qkvs && s->attn && s->lse && s->sg && out, "conv fwd: null output buffer");
+  X2_CHECK_ARG(d->A == 0 || s->ea, "conv fwd: saved.ea required when A > 0");
+  X2_CHECK_ARG(!d->fuse_skip || d->w_skip, "conv fwd: fuse_skip needs w_skip");
+  cudaStream_t st = (cudaStream_t)stream;
+  FwdWs w;
+  const size_t need = fwd_layout(d, ws, &w);
+  if (ws_bytes < need) { set_error("conv fwd: workspace %zu < %zu", ws_bytes, need); return X2_EWORKSPACE; }
+  const int64_t E = d->E, T = d->T;
+  const int D = d->D;
+  if (E == 0) return X2_OK;
+
+  phase_begin(st);
+  // (1) x_src = x * lin_rbf(rbf)                                             :99-100
+  k_rbf_filter<<<(unsigned)cdiv(E * D, 256), 256, 0, st>>>(d->x, d->rbf, d->w_rbf, E, D, d->R, w.xs, nullptr);
+  X2_LAUNCH_OK();
+  // (2) Q | K | V | skip in one batched launch                               :105-107, :121
+  {
+    GemmBatch p{};
+    p.A[0] = d->x;  p.B[0] = d->w_q; p.bias[0] = d->b_q; p.C[0] = s->qkvs;
+    p.A[1] = w.xs;  p.B[1] = d->w_k; p.bias[1] = d->b_k; p.C[1] = s->qkvs + D;
+    p.A[2] = w.xs;  p.B[2] = d->w_v; p.bias[2] = d->b_v; p.C[2] = s->qkvs + 2 * D;
+    int nb = 3;
+    if (d->fuse_skip) {
+      p.A[3] = d->x; p.B[3] = d->w_skip; p.bias[3] = d->b_skip; p.C[3] = s->qkvs + 3 * D;
+      nb = 4;
+    }
+    X2_TRY((launch_gemm<true, true>(p, nb, E, D, D, D, D, 4 * D, 0, st)));
+  }
+  phase_end(X2_PHASE_NODE_PROJ, st);
+  // (3) T-row projections                                                    :144, :148
+  if (T > 0) {
+    if (d->A > 0) X2_TRY(gemm_nt(d->edge_attr, d->A, d->w_edge, d->A, nullptr, s->ea, D, T, D, d->A, st));
+    X2_TRY(gemm_nt(d->sbf, d->S, d->w_sbf, d->S, d->b_sbf, s->sg, D, T, D, d->S, st));
+  }
+  phase_end(X2_PHASE_TROW_PROJ, st);
+  // (4) fused gather + logits + segment softmax + gate + aggregate (+ skip)  :150-160, aggregate, :127
+  int rc;
+  switch (D / 32) {
+    case 1: rc = launch_attn_fwd<1>(d, s, out, alpha, st); break;
+    case 2: rc = launch_attn_fwd<2>(d, s, out, alpha, st); break;
+    case 4: rc = launch_attn_fwd<4>(d, s, out, alpha, st); break;
+    default: rc = launch_attn_fwd<8>(d, s, out, alpha, st); break;
+  }
+  phase_end(X2_PHASE_ATTN_FWD, st);
+  return rc;
+}
+
+int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* grad_out,
+                   const x2_conv_grads* g, void* ws, size_t ws_bytes, void* stream) {
+  X2_TRY(check_desc(d));
+  X2_CHECK_ARG(s && s->qkvs && s->attn && s->lse && s->sg && grad_out && g, "conv bwd: null buffer");
+  X2_CHECK_ARG(g->dx && g->drbf && g->dw_rbf && g->dw_q && g->db_q && g->dw_k && g->db_k && g->dw_v &&
+                   g->db_v && g->dw_sbf && g->db_sbf, "conv bwd: null gradient buffer");
+  X2_CHECK_ARG(d->A == 0 || (s->ea && g->dw_edge), "conv bwd: lin_edge buffers required when A > 0");
+  X2_CHECK_ARG(!d->fuse_skip || (d->w_skip && g->dw_skip), "conv bwd: fuse_skip needs w_skip/dw_skip");
+  cudaStream_t st = (cudaStream_t)stream;
+  BwdWs w;
+  const size_t need = bwd_layout(d, ws, &w);
+  if (ws_bytes < need) { set_error("conv bwd: workspace %zu < %zu", ws_bytes, need); return X2_EWORKSPACE; }
+  const int64_t E = d->E, T = d->T;
+  const int D = d->D, A = d->A, S = d->S, R = d->R;
+  if (E == 0) {
+    // no rows: every parameter gradient is zero
+    X2_CUDA_OK(cudaMemsetAsync(g->dw_rbf, 0, sizeof(float) * D * R, st));
+    float* ws_[] = {g->dw_q, g->dw_k, g->dw_v, d->fuse_skip ? g->dw_skip : nullptr};
+    for (float* p : ws_) if (p) X2_CUDA_OK(cudaMemsetAsync(p, 0, sizeof(float) * D * D, st));
+    float* bs_[] = {g->db_q, g->db_k, g->db_v, g->db_sbf, d->fuse_skip ? g->db_skip : nullptr};
+    for (float* p : bs_) if (p) X2_CUDA_OK(cudaMemsetAsync(p, 0, sizeof(float) * D, st));
+    if (A > 0) X2_CUDA_OK(cudaMemsetAsync(g->dw_edge, 0, sizeof(float) * D * A, st));
+    X2_CUDA_OK(cudaMemsetAsync(g->dw_sbf, 0, sizeof(float) * D * S, st));
+    return X2_OK;
+  }
+
+  // (1,2) attention backward: by target, then by source
+  switch (D / 32) {
+    case 1: X2_TRY(launch_attn_bwd<1>(d, s, grad_out, w, st)); break;
+    case 2: X2_TRY(launch_attn_bwd<2>(d, s, grad_out, w, st)); break;
+    case 4: X2_TRY(launch_attn_bwd<4>(d, s, grad_out, w, st)); break;
+    default: X2_TRY(launch_attn_bwd<8>(d, s, grad_out, w, st)); break;
+  }
+  const float* dq = w.dqkv;
+  const float* dk = w.dqkv + D;
+  const float* dv = w.dqkv + 2 * D;
+
+  // (3) T-row input gradients
+  if (A > 0 && g->dedge_attr && T > 0) X2_TRY(gemm_nn(w.dea, D, d->w_edge, A, g->dedge_attr, A, T, A, D, 0, st));
+  if (g->dsbf && T > 0) X2_TRY(gemm_nn(w.dsg, D, d->w_sbf, S, g->dsbf, S, T, S, D, 0, st));
+  phase_end(X2_PHASE_TROW_DGRAD, st);
+  // (4) T-row weight gradients (split-K over triplets, fixed-order reduction)
+  if (A > 0) X2_TRY(gemm_wgrad(w.dea, D, d->edge_attr, A, g->dw_edge, A, nullptr, T, D, A, w.wg, st));
+  X2_TRY(gemm_wgrad(w.dsg, D, d->sbf, S, g->dw_sbf, S, g->db_sbf, T, D, S, w.wg, st));
+
+  phase_end(X2_PHASE_TROW_WGRAD, st);
+  // (5) recompute the filtered sources
+  k_rbf_filter<<<(unsigned)cdiv(E * D, 256), 256, 0, st>>>(d->x, d->rbf, d->w_rbf, E, D, R, w.xs, w.F);
+  X2_LAUNCH_OK();
+  // (6) node-level weight gradients
+  X2_TRY(gemm_wgrad(dq, 3 * D, d->x, D, g->dw_q, D, g->db_q, E, D, D, w.wg, st));
+  X2_TRY(gemm_wgrad(dk, 3 * D, w.xs, D, g->dw_k, D, g->db_k, E, D, D, w.wg, st));
+  X2_TRY(gemm_wgrad(dv, 3 * D, w.xs, D, g->dw_v, D, g->db_v, E, D, D, w.wg, st));
+  if (d->fuse_skip) X2_TRY(gemm_wgrad(grad_out, D, d->x, D, g->dw_skip, D, g->db_skip, E, D, D, w.wg, st));
+  // (7) dxs = dK W_k + dV W_v
+  X2_TRY(gemm_nn(dk, 3 * D, d->w_k, D, w.dxs, D, E, D, D, 0, st));
+  X2_TRY(gemm_nn(dv, 3 * D, d->w_v, D, w.dxs, D, E, D, D, 1, st));
+  // (8) dx = dQ W_q (+ G W_o)
+  X2_TRY(gemm_nn(dq, 3 * D, d->w_q, D, g->dx, D, E, D, D, 0, st));
+  if (d->fuse_skip) X2_TRY(gemm_nn(grad_out, D, d->w_skip, D, g->dx, D, E, D, D, 1, st));
+  // (9) dx += dxs * F ; dF = dxs * x
+  k_filter_bwd<<<(unsigned)cdiv(E * D, 256), 256, 0, st>>>(d->x, w.F, w.dxs, g->dx, E * D);
+  X2_LAUNCH_OK();
+  // (10) d rbf = dF W_r ; dW_r = dF^T rbf
+  X2_TRY(gemm_nn(w.dxs, D, d->w_rbf, R, g->drbf, R, E, R, D, 0, st));
+  X2_TRY(gemm_wgrad(w.dxs, D, d->rbf, R, g->dw_rbf, R, nullptr, E, D, R, w.wg, st));
+  phase_end(X2_PHASE_NODE_BWD, st);
+  return X2_OK;
+}
+
+}  // extern "C"

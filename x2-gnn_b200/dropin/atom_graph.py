@@ -1,0 +1,7 @@
+"""Drop-in for the reference's `atom_graph.py`: put this directory on sys.path ahead of the
+reference tree (`x2gnn_b200.install()`) and the unchanged callers (model.py, xgnn.py, ...) pick up
+the sm_100a implementation."""
+from x2gnn_b200.atom_graph import *  # noqa: F401,F403
+from x2gnn_b200 import atom_graph as _impl
+
+__all__ = [n for n in dir(_impl) if not n.startswith("_")]

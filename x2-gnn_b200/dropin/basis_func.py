@@ -1,0 +1,7 @@
+"""Drop-in for the reference's `basis_func.py`: put this directory on sys.path ahead of the
+reference tree (`x2gnn_b200.install()`) and the unchanged callers (model.py, xgnn.py, ...) pick up
+the sm_100a implementation."""
+from x2gnn_b200.basis_func import *  # noqa: F401,F403
+from x2gnn_b200 import basis_func as _impl
+
+__all__ = [n for n in dir(_impl) if not n.startswith("_")]

@@ -1,0 +1,77 @@
+"""CSR metadata of the line graph consumed by the attention kernels.
+
+PyG derives this implicitly inside propagate/softmax/scatter on every layer call
+(sbftransformer_conv.py:109,151).  Here it is built once per `edge_index` tensor by integer
+kernels (x2_meta_build) and reused by all conv layers and their backward passes.
+"""
+from __future__ import annotations
+
+import weakref
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+
+@dataclass
+class LineGraphMeta:
+    T: int
+    E: int
+    src: torch.Tensor          # [T] int32
+    tgt: torch.Tensor          # [T] int32
+    rowptr_tgt: torch.Tensor   # [E+1] int32
+    order_tgt: torch.Tensor    # [T] int32 (identity when target-sorted)
+    rowptr_src: torch.Tensor   # [E+1] int32
+    order_src: torch.Tensor    # [T] int32
+    target_sorted: bool
+
+
+def build(edge_index: torch.Tensor, num_nodes: int) -> LineGraphMeta:
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError(f"edge_index must be [2, T], got {tuple(edge_index.shape)}")
+    if edge_index.dtype != torch.int64:
+        edge_index = edge_index.long()
+    dev = _lib.require_cuda(edge_index, what="line-graph metadata")
+    ei = edge_index.contiguous()
+    T, E = int(ei.size(1)), int(num_nodes)
+    L = _lib.lib()
+    i32 = dict(dtype=torch.int32, device=dev)
+    src = torch.empty(max(T, 1), **i32)
+    tgt = torch.empty(max(T, 1), **i32)
+    rp_t = torch.empty(E + 1, **i32)
+    rp_s = torch.empty(E + 1, **i32)
+    od_t = torch.empty(max(T, 1), **i32)
+    od_s = torch.empty(max(T, 1), **i32)
+    flags = torch.zeros(2, **i32)
+    ws = _lib.workspace(L.x2_meta_workspace_bytes(T, E), dev)
+    _lib.check(L.x2_meta_build(_lib.ptr(ei), T, E, _lib.ptr(src), _lib.ptr(tgt), _lib.ptr(rp_t),
+                               _lib.ptr(od_t), _lib.ptr(rp_s), _lib.ptr(od_s), _lib.ptr(flags),
+                               _lib.ptr(ws), ws.numel(), _lib.stream()), "x2_meta_build")
+    f = flags.tolist()          # one host sync per batch; also surfaces async kernel errors
+    if f[1] != 0:
+        raise IndexError(f"edge_index has {f[1]} entries outside [0, {E})")
+    return LineGraphMeta(T, E, src, tgt, rp_t, od_t, rp_s, od_s, bool(f[0]))
+
+
+_cache: list = []   # [(weakref(edge_index), version, num_nodes, meta)], most recent first
+_CACHE_SIZE = 8
+
+
+def get(edge_index: torch.Tensor, num_nodes: int) -> LineGraphMeta:
+    """Cached `build`: the same tensor object (unchanged `_version`) is passed to every conv
+    layer of a forward pass (model.py:45), so the metadata is built once per batch."""
+    ver = edge_index._version
+    for i, (ref, v, n, meta) in enumerate(_cache):
+        if ref() is edge_index and v == ver and n == num_nodes:
+            if i:
+                _cache.insert(0, _cache.pop(i))
+            return meta
+    meta = build(edge_index, num_nodes)
+    _cache.insert(0, (weakref.ref(edge_index), ver, num_nodes, meta))
+    del _cache[_CACHE_SIZE:]
+    return meta
+
+
+def clear_cache():
+    _cache.clear()

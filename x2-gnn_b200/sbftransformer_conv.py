@@ -1,0 +1,246 @@
+"""SBFTransformerConv on sm_100a.  Drop-in for the reference's sbftransformer_conv.py:16-166:
+same constructor, sub-module names (=> state_dict keys), forward signature and return values.
+
+The reference subclasses PyG's MessagePassing and runs ~35 library kernels forward / ~70
+backward per call.  Here the layer is one C-ABI call forward and one backward
+(x2_sbfconv_fwd / x2_sbfconv_bwd): batched node GEMM, T-row projections, and a deterministic
+warp-per-target segmented attention kernel (see csrc/conv.cu).  No torch_geometric /
+torch_scatter / torch_sparse dependency, no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from . import _lib, graph_meta
+
+MODE_FP32 = 0
+
+
+def Glorot_Ortho_(tensor: Tensor, scale: float = 2.0) -> Tensor:
+    """Same initialiser as the reference's initializer.Glorot_Ortho_ (orthogonal, then rescaled
+    to Glorot variance); restated here so the hot-path module has no out-of-scope import."""
+    nn.init.orthogonal_(tensor)
+    with torch.no_grad():
+        assert tensor.dim() == 2
+        tensor.mul_(torch.sqrt(scale / ((tensor.size(0) + tensor.size(1)) * tensor.var())))
+    return tensor
+
+
+class _SBFConvFn(torch.autograd.Function):
+    """out/attn = conv(x, rbf, sbf, edge_attr; weights).  Non-tensor config rides in `cfg`."""
+
+    @staticmethod
+    def forward(ctx, cfg, meta, x, rbf, sbf, edge_attr, w_rbf, w_q, b_q, w_k, b_k, w_v, b_v, w_edge,
+                w_sbf, b_sbf, w_skip, b_skip):
+        names = ("x", "rbf", "sbf", "edge_attr", "w_rbf", "w_q", "b_q", "w_k", "b_k", "w_v", "b_v",
+                 "w_edge", "w_sbf", "b_sbf", "w_skip", "b_skip")
+        vals = [_lib.f32(t, f"SBFTransformerConv.{n}") for n, t in zip(names, (
+            x, rbf, sbf, edge_attr, w_rbf, w_q, b_q, w_k, b_k, w_v, b_v, w_edge, w_sbf, b_sbf, w_skip, b_skip))]
+        t = dict(zip(names, vals))
+        dev = _lib.require_cuda(*vals, meta.src, what="SBFTransformerConv")
+        E, D = t["x"].shape
+        T = meta.T
+        H, Cc = cfg["heads"], cfg["out_channels"]
+        S, R = t["sbf"].size(1), t["rbf"].size(1)
+        A = t["edge_attr"].size(1) if t["w_edge"] is not None else 0
+        if meta.E != E:
+            raise ValueError(f"edge_index was indexed for {meta.E} nodes but x has {E} rows")
+        if t["sbf"].size(0) != T or (A and t["edge_attr"].size(0) != T) or t["rbf"].size(0) != E:
+            raise ValueError("SBFTransformerConv: sbf/edge_attr must have one row per edge_index "
+                             "column and rbf one row per node")
+        fuse = 1 if t["w_skip"] is not None else 0
+
+        desc = _lib.ConvDesc()
+        desc.E, desc.T = E, T
+        desc.D, desc.H, desc.C, desc.S, desc.R, desc.A = D, H, Cc, S, R, A
+        desc.fuse_skip, desc.mode = fuse, cfg["mode"]
+        desc.dropout_p, desc.seed = cfg["dropout_p"], cfg["seed"]
+        for n in ("x", "rbf", "sbf", "w_rbf", "w_q", "b_q", "w_k", "b_k", "w_v", "b_v", "w_sbf", "b_sbf",
+                  "w_skip", "b_skip"):
+            setattr(desc, n, _lib.ptr(t[n]))
+        desc.edge_attr = _lib.ptr(t["edge_attr"]) if A else None
+        desc.w_edge = _lib.ptr(t["w_edge"]) if A else None
+        for n in ("src", "tgt", "rowptr_tgt", "order_tgt", "rowptr_src", "order_src"):
+            setattr(desc, n, _lib.ptr(getattr(meta, n)))
+
+        f32 = dict(dtype=torch.float32, device=dev)
+        qkvs = torch.empty((E, 4 * D), **f32)
+        attn = torch.empty((E, D), **f32)
+        lse = torch.empty((E, H), **f32)
+        ea = torch.empty((max(T, 1), D), **f32) if A else None
+        sg = torch.empty((max(T, 1), D), **f32)
+        out = torch.empty((E, D), **f32) if fuse else attn
+        alpha = torch.empty((T, H), **f32) if cfg["want_alpha"] else None
+        saved = _lib.ConvSaved(_lib.ptr(qkvs), _lib.ptr(attn), _lib.ptr(lse), _lib.ptr(ea), _lib.ptr(sg))
+        L = _lib.lib()
+        ws = _lib.workspace(L.x2_sbfconv_fwd_workspace_bytes(C.byref(desc)), dev)
+        _lib.check(L.x2_sbfconv_fwd(C.byref(desc), C.byref(saved), _lib.ptr(out), _lib.ptr(alpha),
+                                    _lib.ptr(ws), ws.numel(), _lib.stream()), "x2_sbfconv_fwd")
+        ctx.cfg, ctx.meta, ctx.dims = cfg, meta, (E, T, D, H, Cc, S, R, A, fuse)
+        ctx.tensors = t            # inputs + weights (kept alive; plain references, no graph)
+        ctx.saved_bufs = (qkvs, attn, lse, ea, sg)
+        if alpha is not None:
+            ctx.mark_non_differentiable(alpha)
+            return out, alpha
+        return out, None
+
+    @staticmethod
+    def backward(ctx, gout, _galpha):
+        t, meta = ctx.tensors, ctx.meta
+        E, T, D, H, Cc, S, R, A, fuse = ctx.dims
+        qkvs, attn, lse, ea, sg = ctx.saved_bufs
+        gout = _lib.f32(gout, "SBFTransformerConv.backward")
+        dev = gout.device
+        cfg = ctx.cfg
+
+        desc = _lib.ConvDesc()
+        desc.E, desc.T = E, T
+        desc.D, desc.H, desc.C, desc.S, desc.R, desc.A = D, H, Cc, S, R, A
+        desc.fuse_skip, desc.mode = fuse, cfg["mode"]
+        desc.dropout_p, desc.seed = cfg["dropout_p"], cfg["seed"]
+        for n in ("x", "rbf", "sbf", "w_rbf", "w_q", "b_q", "w_k", "b_k", "w_v", "b_v", "w_sbf", "b_sbf",
+                  "w_skip", "b_skip"):
+            setattr(desc, n, _lib.ptr(t[n]))
+        desc.edge_attr = _lib.ptr(t["edge_attr"]) if A else None
+        desc.w_edge = _lib.ptr(t["w_edge"]) if A else None
+        for n in ("src", "tgt", "rowptr_tgt", "order_tgt", "rowptr_src", "order_src"):
+            setattr(desc, n, _lib.ptr(getattr(meta, n)))
+        saved = _lib.ConvSaved(_lib.ptr(qkvs), _lib.ptr(attn), _lib.ptr(lse), _lib.ptr(ea), _lib.ptr(sg))
+
+        f32 = dict(dtype=torch.float32, device=dev)
+        need = ctx.needs_input_grad     # (cfg, meta, x, rbf, sbf, edge_attr, ...)
+        g = {
+            "dx": torch.empty((E, D), **f32), "drbf": torch.empty((E, R), **f32),
+            "dsbf": torch.empty((T, S), **f32) if need[4] else None,
+            "dedge_attr": torch.empty((T, A), **f32) if (A and need[5]) else None,
+            "dw_rbf": torch.empty((D, R), **f32),
+            "dw_q": torch.empty((D, D), **f32), "db_q": torch.empty(D, **f32),
+            "dw_k": torch.empty((D, D), **f32), "db_k": torch.empty(D, **f32),
+            "dw_v": torch.empty((D, D), **f32), "db_v": torch.empty(D, **f32),
+            "dw_edge": torch.empty((D, A), **f32) if A else None,
+            "dw_sbf": torch.empty((D, S), **f32), "db_sbf": torch.empty(D, **f32),
+            "dw_skip": torch.empty((D, D), **f32) if fuse else None,
+            "db_skip": torch.empty(D, **f32) if (fuse and t["b_skip"] is not None) else None,
+        }
+        grads = _lib.ConvGrads(*[_lib.ptr(g[n]) for n, _ in _lib.ConvGrads._fields_])
+        L = _lib.lib()
+        ws = _lib.workspace(L.x2_sbfconv_bwd_workspace_bytes(C.byref(desc)), dev)
+        _lib.check(L.x2_sbfconv_bwd(C.byref(desc), C.byref(saved), _lib.ptr(gout), C.byref(grads),
+                                    _lib.ptr(ws), ws.numel(), _lib.stream()), "x2_sbfconv_bwd")
+        return (None, None, g["dx"], g["drbf"], g["dsbf"], g["dedge_attr"], g["dw_rbf"], g["dw_q"],
+                g["db_q"], g["dw_k"], g["db_k"], g["dw_v"], g["db_v"], g["dw_edge"], g["dw_sbf"],
+                g["db_sbf"], g["dw_skip"], g["db_skip"])
+
+
+class SBFTransformerConv(nn.Module):
+    """Multi-head attention message passing on the line graph with an rbf source filter, sbf value
+    gate, additive edge features and root skip.  See the reference for the model semantics."""
+
+    def __init__(self, in_channels, out_channels: int, heads: int = 1, sbf_dim: int = 16,
+                 rbf_dim: int = 16, concat: bool = True, beta: bool = False, dropout: float = 0.,
+                 edge_dim: Optional[int] = None, bias: bool = True, root_weight: bool = True, **kwargs):
+        aggr = kwargs.pop("aggr", "add")
+        if aggr != "add":
+            raise ValueError("SBFTransformerConv: only aggr='add' is supported")
+        kwargs.pop("node_dim", None)
+        kwargs.pop("flow", None)
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.heads = heads
+        self.sbf_dim = sbf_dim
+        self.rbf_dim = rbf_dim
+        self.beta = beta and root_weight
+        self.root_weight = root_weight
+        self.concat = concat
+        self.dropout = dropout
+        self.edge_dim = edge_dim
+        self._alpha = None
+        self.precision = MODE_FP32
+
+        if isinstance(in_channels, int):
+            in_channels = (in_channels, in_channels)
+        hc = heads * out_channels
+        self.lin_key = nn.Linear(in_channels[0], hc)
+        self.lin_query = nn.Linear(in_channels[1], hc)
+        self.lin_value = nn.Linear(in_channels[0], hc)
+        if edge_dim is not None:
+            self.lin_edge = nn.Linear(edge_dim, hc, bias=False)
+        else:
+            self.lin_edge = self.register_parameter("lin_edge", None)
+        if concat:
+            self.lin_skip = nn.Linear(in_channels[1], hc, bias=bias)
+            if self.beta:
+                self.lin_beta = nn.Linear(3 * hc, 1, bias=False)
+            else:
+                self.lin_beta = self.register_parameter("lin_beta", None)
+        else:
+            self.lin_skip = nn.Linear(in_channels[1], out_channels, bias=bias)
+            if self.beta:
+                self.lin_beta = nn.Linear(3 * out_channels, 1, bias=False)
+            else:
+                self.lin_beta = self.register_parameter("lin_beta", None)
+        self.lin_sbf = nn.Linear(sbf_dim, hc, bias=True)
+        self.lin_rbf = nn.Linear(rbf_dim, in_channels[0], bias=False)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        with torch.no_grad():
+            Glorot_Ortho_(self.lin_sbf.weight)
+            Glorot_Ortho_(self.lin_rbf.weight)
+            nn.init.zeros_(self.lin_sbf.bias)     # lin_rbf has no bias
+        self.lin_key.reset_parameters()
+        self.lin_query.reset_parameters()
+        self.lin_value.reset_parameters()
+        if self.edge_dim:
+            self.lin_edge.reset_parameters()
+        self.lin_skip.reset_parameters()
+        if self.beta:
+            self.lin_beta.reset_parameters()
+
+    def forward(self, sbf, rbf, x, edge_index, edge_attr=None, return_attention_weights=None):
+        if not isinstance(x, Tensor):
+            raise TypeError("SBFTransformerConv: `x` must be a Tensor (the reference's tuple path is dead code)")
+        if not isinstance(edge_index, Tensor):
+            raise TypeError("SBFTransformerConv: edge_index must be a [2, T] LongTensor")
+        if self.lin_edge is not None and edge_attr is None:
+            raise AssertionError("edge_attr is required when edge_dim is set")
+        if self.in_channels != self.heads * self.out_channels and isinstance(self.in_channels, int):
+            raise NotImplementedError("SBFTransformerConv: in_channels must equal heads*out_channels")
+        H, Cc = self.heads, self.out_channels
+        meta = graph_meta.get(edge_index, x.size(0))
+        fuse = self.concat and self.root_weight and self.lin_beta is None
+        p_drop = float(self.dropout) if self.training else 0.0
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0 else 0
+        cfg = dict(heads=H, out_channels=Cc, mode=self.precision, dropout_p=p_drop, seed=seed,
+                   want_alpha=isinstance(return_attention_weights, bool))
+        out, alpha = _SBFConvFn.apply(
+            cfg, meta, x, rbf, sbf, edge_attr if self.lin_edge is not None else None,
+            self.lin_rbf.weight, self.lin_query.weight, self.lin_query.bias, self.lin_key.weight,
+            self.lin_key.bias, self.lin_value.weight, self.lin_value.bias,
+            self.lin_edge.weight if self.lin_edge is not None else None, self.lin_sbf.weight,
+            self.lin_sbf.bias, self.lin_skip.weight if fuse else None,
+            self.lin_skip.bias if fuse else None)
+        if not fuse:
+            # composite tail for the non-default variants (CUDA torch ops, still no CPU path)
+            out = out.view(-1, H * Cc) if self.concat else out.view(-1, H, Cc).mean(dim=1)
+            if self.root_weight:
+                x_r = self.lin_skip(x)
+                if self.lin_beta is not None:
+                    beta = self.lin_beta(torch.cat([out, x_r, out - x_r], dim=-1)).sigmoid()
+                    out = beta * x_r + (1 - beta) * out
+                else:
+                    out = out + x_r
+        if isinstance(return_attention_weights, bool):
+            assert alpha is not None
+            return out, (edge_index, alpha)
+        return out
+
+    def __repr__(self) -> str:
+        return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels}, heads={self.heads})"

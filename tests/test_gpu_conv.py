@@ -23,12 +23,13 @@ def _mine(dims, state, **kw):
 
 
 def _run(conv, rec, dev, dtype, want_alpha=False, sbf_grad=True):
+    conv.zero_grad(set_to_none=True)
     xs = {k: rec[k].to(device=dev, dtype=dtype).requires_grad_(k != "sbf" or sbf_grad) for k in INPUTS}
     ei = rec["edge_index"].to(dev)
     r = conv(xs["sbf"], xs["rbf"], x=xs["x"], edge_index=ei, edge_attr=xs["edge_attr"],
              return_attention_weights=True if want_alpha else None)
     out, alpha = (r[0], r[1][1]) if want_alpha else (r, None)
-    out.backward(rec["grad_out"].to(device=dev, dtype=dtype))
+    out.backward(rec["grad_out"][:, :out.size(1)].to(device=dev, dtype=dtype))
     return out, alpha, xs
 
 
@@ -88,6 +89,9 @@ def _compare(ref, mine, rec, tol=FP32_TOL, check_alpha=True):
     pm = dict(mine.named_parameters())
     for k, p in ref.named_parameters():
         if k == "lin_key.bias":
+            continue
+        if p.grad is None:                  # parameter unused by this variant
+            assert pm[k].grad is None, k
             continue
         assert relerr(pm[k].grad, p.grad) < tol, k
 

@@ -13,47 +13,38 @@ ELEMENT_P = np.array([0.50, 0.35, 0.06, 0.08, 0.01])
 CUTOFF = 5.0
 
 
-def _pairs_ok(pos: np.ndarray, cutoff: float, margin: float) -> bool:
-    d = np.linalg.norm(pos[:, None, :] - pos[None, :, :], axis=-1)
-    iu = np.triu_indices(len(pos), 1)
-    return bool(np.all(np.abs(d[iu] - cutoff) > margin))
+def _accept(pos: np.ndarray, cand: np.ndarray, cutoff: float, margin: float) -> bool:
+    """Candidate atom is >= 0.95 A from every existing atom and no distance falls within
+    `margin` of the cutoff (keeps edge sets stable under fp32 rounding of the Gram form)."""
+    d = np.linalg.norm(pos - cand, axis=1)
+    return bool(d.min() >= 0.95 and np.all(np.abs(d - cutoff) > margin))
 
 
-def synth_mol(n: int, rng: np.random.Generator, cutoff: float = CUTOFF,
-              margin: float = 1e-3):
-    """Random-walk molecule: n atoms, bond length U[1.00,1.55] A, >=0.95 A exclusion,
-    no pair within `margin` of the cutoff (keeps edge sets stable under fp32 rounding)."""
-    while True:
-        pos = np.zeros((1, 3))
-        while len(pos) < n:
-            a = pos[rng.integers(len(pos))]
-            v = rng.normal(size=3)
-            v /= np.linalg.norm(v)
-            cand = a + v * rng.uniform(1.00, 1.55)
-            if np.min(np.linalg.norm(pos - cand, axis=1)) >= 0.95:
-                pos = np.vstack([pos, cand])
-        if _pairs_ok(pos, cutoff, margin):
-            break
+def synth_mol(n: int, rng: np.random.Generator, cutoff: float = CUTOFF, margin: float = 1e-3):
+    """Random-walk molecule: n atoms, bond length U[1.00,1.55] A, >= 0.95 A exclusion."""
+    pos = np.zeros((1, 3))
+    while len(pos) < n:
+        a = pos[rng.integers(len(pos))]
+        v = rng.normal(size=3)
+        v /= np.linalg.norm(v)
+        cand = a + v * rng.uniform(1.00, 1.55)
+        if _accept(pos, cand, cutoff, margin):
+            pos = np.vstack([pos, cand])
     z = rng.choice(ELEMENTS, size=n, p=ELEMENT_P)
     return pos.astype(np.float32), z
 
 
-def synth_ball(n: int, rng: np.random.Generator, density: float = 0.1,
-               cutoff: float = CUTOFF, margin: float = 1e-3):
+def synth_ball(n: int, rng: np.random.Generator, density: float = 0.1, cutoff: float = CUTOFF,
+               margin: float = 1e-3):
     """n atoms uniformly in a ball at `density` atoms/A^3 with 0.95 A exclusion."""
     radius = (3.0 * n / (4.0 * np.pi * density)) ** (1.0 / 3.0)
-    while True:
-        pts = []
-        while len(pts) < n:
-            c = rng.uniform(-radius, radius, size=3)
-            if np.linalg.norm(c) > radius:
-                continue
-            if pts and np.min(np.linalg.norm(np.asarray(pts) - c, axis=1)) < 0.95:
-                continue
-            pts.append(c)
-        pos = np.asarray(pts)
-        if _pairs_ok(pos, cutoff, margin):
-            break
+    pos = np.zeros((0, 3))
+    while len(pos) < n:
+        c = rng.uniform(-radius, radius, size=3)
+        if np.linalg.norm(c) > radius:
+            continue
+        if len(pos) == 0 or _accept(pos, c, cutoff, margin):
+            pos = np.vstack([pos, c])
     z = rng.choice(ELEMENTS, size=n, p=ELEMENT_P)
     return pos.astype(np.float32), z
 

@@ -140,6 +140,22 @@ int x2_sbf_fwd(const float* table, const float* angles, const int64_t* idx, int6
 /* angular_basis_layer.py:28-32: out[t,l] = Y_l0(angles[t]). */
 int x2_angular_fwd(const float* angles, int64_t T, int32_t L, float* out, void* stream);
 
+/* ---------------------------------------------------------------- tensor-core Linear building blocks
+ * tcgen05 (kind::tf32) GEMMs in 3xTF32 split precision (fp32-accurate), used inside x2_sbfconv_* for
+ * the torch.nn.Linear layers of the reference (sbftransformer_conv.py:99,105-107,121,144,148) and
+ * exported so the parity tests can exercise them directly.
+ *   x2_tc_gemm : C[M,N] (+)= A[M,K] . B(K,N) + bias[N],  B(k,n) = W[k*sbk + n*sbn], N <= 128.
+ *                (forward y = x W^T: sbk=1, sbn=ldw;  dgrad dx = dy W: sbk=ldw, sbn=1)
+ *   x2_tc_wgrad: dW[128,N] = Y[rows,128]^T . X[rows,N],  db[128] = column sums of Y (db may be NULL),
+ *                N <= 128; deterministic split over rows. */
+size_t x2_tc_gemm_workspace_bytes(int32_t K, int32_t N);
+int x2_tc_gemm(const float* A, int64_t lda, int64_t M, int32_t K, const float* W, int64_t sbk, int64_t sbn,
+               int32_t N, const float* bias, float* C, int64_t ldc, int32_t beta, void* ws, size_t ws_bytes,
+               void* stream);
+size_t x2_tc_wgrad_workspace_bytes(int64_t rows, int32_t N);
+int x2_tc_wgrad(const float* Y, int64_t ldy, const float* X, int64_t ldx, int64_t rows, int32_t N, float* dW,
+                int64_t lddw, float* db, void* ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------- SBFTransformerConv
  * Shapes: x[E,D] rbf[E,R] sbf[T,S] edge_attr[T,A] (A=0 => no lin_edge); D = H*C.
  * Weights use the torch.nn.Linear layout [out,in] of the reference state_dict. */
@@ -164,7 +180,9 @@ typedef struct {
   const float *w_skip, *b_skip;    /* [D,D], [D] (b_skip may be NULL); used iff fuse_skip */
 } x2_conv_desc;
 
-#define X2_MODE_FP32 0   /* fp32 SIMT arithmetic everywhere (1e-5 parity mode) */
+#define X2_MODE_FP32 0    /* fp32 SIMT arithmetic everywhere (1e-5 parity) */
+#define X2_MODE_TF32X3 1  /* Linear layers on tcgen05 tensor cores in 3xTF32 split precision (fp32-accurate,
+                             1e-5 parity); needs D % 128 == 0.  Attention arithmetic stays fp32 SIMT. */
 
 /* Tensors written by fwd and consumed by bwd (caller-owned, kept alive by autograd). */
 typedef struct {

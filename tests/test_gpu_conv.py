@@ -12,11 +12,17 @@ pytestmark = pytest.mark.gpu
 INPUTS = ("x", "rbf", "sbf", "edge_attr")
 
 
-def _mine(dims, state, **kw):
+MODES = {"fp32": 0, "tf32x3": 1}     # X2_MODE_FP32 (SIMT) / X2_MODE_TF32X3 (tcgen05 Linear layers)
+
+
+def _mine(dims, state, mode=None, **kw):
     from x2gnn_b200.sbftransformer_conv import SBFTransformerConv
     D, H, S, R, A = dims
+    if mode == "tf32x3" and D % 128:
+        pytest.skip("tensor-core mode needs D % 128 == 0")
     c = SBFTransformerConv(D, D // H, heads=H, sbf_dim=S, rbf_dim=R, dropout=kw.pop("dropout", 0),
                            edge_dim=A, **kw)
+    c.precision = None if mode is None else MODES[mode]
     if state is not None:
         c.load_state_dict(state)          # reference state_dict loads unchanged
     return c.cuda()
@@ -33,10 +39,11 @@ def _run(conv, rec, dev, dtype, want_alpha=False, sbf_grad=True):
     return out, alpha, xs
 
 
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("tag", ["cfg", "small", "c16"])
-def test_golden_fwd_bwd(golden, tag):
+def test_golden_fwd_bwd(golden, tag, mode):
     rec = golden("conv")[tag]
-    conv = _mine(rec["dims"], rec["state_dict"])
+    conv = _mine(rec["dims"], rec["state_dict"], mode=mode)
     assert list(conv.state_dict().keys()) == list(rec["state_dict"].keys())
     out, alpha, xs = _run(conv, rec, "cuda", torch.float32, want_alpha=True)
     assert relerr(out, rec["out_f64"]) < FP32_TOL
@@ -52,7 +59,7 @@ def test_golden_fwd_bwd(golden, tag):
         assert relerr(p.grad, ref) < FP32_TOL, k
 
 
-def _oracle_pair(dims, seed=0, **kw):
+def _oracle_pair(dims, seed=0, mode=None, **kw):
     D, H, S, R, A = dims
     torch.manual_seed(seed)
     ref = oconv.OracleSBFTransformerConv(D, D // H, heads=H, sbf_dim=S, rbf_dim=R, edge_dim=A, **kw)
@@ -60,7 +67,7 @@ def _oracle_pair(dims, seed=0, **kw):
         for p in ref.parameters():
             if p.dim() == 1:
                 p.uniform_(-0.2, 0.2)
-    mine = _mine(dims, ref.state_dict(), **kw)
+    mine = _mine(dims, ref.state_dict(), mode=mode, **kw)
     return ref.double(), mine
 
 
@@ -98,9 +105,10 @@ def _compare(ref, mine, rec, tol=FP32_TOL, check_alpha=True):
 
 @pytest.mark.parametrize("dims", [(128, 16, 42, 6, 128), (256, 16, 112, 16, 128), (64, 8, 10, 3, 20),
                                   (32, 1, 5, 2, 7), (128, 4, 42, 6, 128)])
-def test_vs_oracle_qm9_batch(dims):
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
+def test_vs_oracle_qm9_batch(dims, mode):
     """config.json dims, class-default dims (xgnn.py:16) and odd shapes on a 6-molecule batch."""
-    ref, mine = _oracle_pair(dims)
+    ref, mine = _oracle_pair(dims, mode=mode)
     _compare(ref, mine, _graph_inputs(6, dims, seed=2))
 
 
@@ -147,9 +155,10 @@ def test_empty_segments_and_no_triplets():
     _compare(ref, mine, rec)
 
 
-def test_unsorted_edge_index_and_permutation_invariance():
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
+def test_unsorted_edge_index_and_permutation_invariance(mode):
     dims = (128, 16, 42, 6, 128)
-    ref, mine = _oracle_pair(dims, seed=8)
+    ref, mine = _oracle_pair(dims, seed=8, mode=mode)
     rec = _graph_inputs(3, dims, seed=9)
     o_sorted, _, _ = _run(mine, rec, "cuda", torch.float32)
     T = rec["edge_index"].size(1)
@@ -159,12 +168,13 @@ def test_unsorted_edge_index_and_permutation_invariance():
     rec_p["sbf"], rec_p["edge_attr"] = rec["sbf"][perm], rec["edge_attr"][perm]
     _compare(ref, mine, rec_p)
     o_perm, _, _ = _run(mine, rec_p, "cuda", torch.float32)
-    assert relerr(o_perm, o_sorted) < 1e-6     # only the in-segment summation order differs
+    assert relerr(o_perm, o_sorted) < 3e-6     # only the summation / tile order differs
 
 
-def test_deterministic_bitwise():
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
+def test_deterministic_bitwise(mode):
     dims = (128, 16, 42, 6, 128)
-    _, mine = _oracle_pair(dims, seed=10)
+    _, mine = _oracle_pair(dims, seed=10, mode=mode)
     rec = _graph_inputs(8, dims, seed=11)
     runs = []
     for _ in range(2):

@@ -13,6 +13,7 @@
 //            the Linear gradients are dgrad / split-K wgrad GEMMs with fixed-order reductions.
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "tc_gemm.cuh"
 
 namespace x2 {
 
@@ -320,11 +321,67 @@ k_attn_bwd_src(const float* __restrict__ qkvs, int ldq, const float* __restrict_
   stv<VEC>(dqkv + f * ldg + 2 * D + ch, dv);
 }
 
+// ------------------------------------------------------------------ Linear dispatch (SIMT / tensor core)
+struct Lin {
+  int mode;          // X2_MODE_FP32: SIMT fp32;  X2_MODE_TF32X3: tcgen05 3xTF32
+  void* img;         // weight-image scratch (tensor-core mode)
+  float* wg;         // wgrad partial-tile scratch
+  cudaStream_t st;
+};
+
+constexpr int kTcBlock = 128;   // the tcgen05 kernels take N <= 128 and a K block whose image fits smem
+
+// C[M,N] (+)= A[M,K] . B(K,N) + bias with B(k,n) = W[k*sbk + n*sbn], blocked over N and K
+static int tc_linear(const Lin& L, const float* A, int64_t lda, int64_t M, int K, const float* W, int64_t sbk,
+                     int64_t sbn, int N, const float* bias, float* C, int64_t ldc, int beta) {
+  for (int n0 = 0; n0 < N; n0 += kTcBlock) {
+    const int nb = N - n0 < kTcBlock ? N - n0 : kTcBlock;
+    for (int k0 = 0; k0 < K; k0 += kTcBlock) {
+      const int kb = K - k0 < kTcBlock ? K - k0 : kTcBlock;
+      int rc = tc::tc_gemm(A + k0, lda, M, kb, W + (int64_t)k0 * sbk + (int64_t)n0 * sbn, sbk, sbn, nb,
+                           (bias && k0 == 0) ? bias + n0 : nullptr, C + n0, ldc, (beta || k0 > 0) ? 1 : 0,
+                           L.img, L.st);
+      if (rc != X2_OK) return rc;
+    }
+  }
+  return X2_OK;
+}
+
+// y[M,N] = x[M,K] W[N,K]^T + bias
+static int lin_fwd(const Lin& L, const float* x, int64_t ldx, const float* W, int64_t ldw, const float* bias,
+                   float* y, int64_t ldy, int64_t M, int N, int K) {
+  if (L.mode == X2_MODE_TF32X3) return tc_linear(L, x, ldx, M, K, W, 1, ldw, N, bias, y, ldy, 0);
+  return gemm_nt(x, ldx, W, ldw, bias, y, ldy, M, N, K, L.st);
+}
+// dx[M,N] (+)= dy[M,K] W[K,N]
+static int lin_dgrad(const Lin& L, const float* dy, int64_t lddy, const float* W, int64_t ldw, float* dx,
+                     int64_t lddx, int64_t M, int N, int K, int beta) {
+  if (L.mode == X2_MODE_TF32X3) return tc_linear(L, dy, lddy, M, K, W, ldw, 1, N, nullptr, dx, lddx, beta);
+  return gemm_nn(dy, lddy, W, ldw, dx, lddx, M, N, K, beta, L.st);
+}
+// dW[Md,N] = dy[rows,Md]^T x[rows,N] ; db[Md] = colsum(dy)
+static int lin_wgrad(const Lin& L, const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dW,
+                     int64_t lddw, float* db, int64_t rows, int Md, int N) {
+  if (L.mode == X2_MODE_TF32X3 && Md % kTcBlock == 0) {
+    for (int m0 = 0; m0 < Md; m0 += kTcBlock)
+      for (int n0 = 0; n0 < N; n0 += kTcBlock) {
+        const int nb = N - n0 < kTcBlock ? N - n0 : kTcBlock;
+        int rc = tc::tc_wgrad(dy + m0, lddy, x + n0, ldx, rows, nb, dW + (int64_t)m0 * lddw + n0, lddw,
+                              (db && n0 == 0) ? db + m0 : nullptr, L.wg, L.st);
+        if (rc != X2_OK) return rc;
+      }
+    return X2_OK;
+  }
+  return gemm_wgrad(dy, lddy, x, ldx, dW, lddw, db, rows, Md, N, L.wg, L.st);
+}
+
 // ------------------------------------------------------------------ host side
 static int check_desc(const x2_conv_desc* d) {
   X2_CHECK_ARG(d != nullptr, "conv: null descriptor");
   X2_CHECK_ARG(d->E >= 0 && d->T >= 0 && d->E < 2147483647LL && d->T < 2147483647LL, "conv: bad E/T");
-  X2_CHECK_ARG(d->mode == X2_MODE_FP32, "conv: unknown mode %d", d->mode);
+  X2_CHECK_ARG(d->mode == X2_MODE_FP32 || d->mode == X2_MODE_TF32X3, "conv: unknown mode %d", d->mode);
+  X2_CHECK_ARG(d->mode != X2_MODE_TF32X3 || d->D % 128 == 0,
+               "conv: X2_MODE_TF32X3 needs heads*out_channels to be a multiple of 128 (got %d)", d->D);
   X2_CHECK_ARG(d->D == d->H * d->C && d->H >= 1 && d->C >= 1, "conv: D=%d != H*C=%d*%d", d->D, d->H, d->C);
   X2_CHECK_ARG(d->D == 32 || d->D == 64 || d->D == 128 || d->D == 256,
                "conv: heads*out_channels must be 32, 64, 128 or 256 (got %d)", d->D);
@@ -338,15 +395,17 @@ static int check_desc(const x2_conv_desc* d) {
   return X2_OK;
 }
 
-struct FwdWs { float* xs; };
+struct FwdWs { float* xs; void* img; };
 static size_t fwd_layout(const x2_conv_desc* d, void* ws, FwdWs* w) {
   Arena a(ws, (size_t)-1);
   w->xs = a.take<float>((size_t)d->E * d->D + 4);
+  w->img = a.take<char>(tc::bimage_bytes(kTcBlock, kTcBlock) + 256);
   return align_up(a.off, 256) + 256;
 }
 
 struct BwdWs {
   float *dea, *dsg, *al, *da, *dqkv, *xs, *F, *dxs, *wg;
+  void* img;
   size_t wg_floats;
 };
 static size_t bwd_layout(const x2_conv_desc* d, void* ws, BwdWs* w) {
@@ -367,8 +426,11 @@ static size_t bwd_layout(const x2_conv_desc* d, void* ws, BwdWs* w) {
   if (t2 > wg) wg = t2;
   t2 = wgrad_workspace_floats(d->E, d->D, d->R);
   if (t2 > wg) wg = t2;
+  t2 = tc::tc_wgrad_workspace_floats(d->T > d->E ? d->T : d->E, kTcBlock);
+  if (t2 > wg) wg = t2;
   w->wg_floats = wg;
   w->wg = a.take<float>(wg);
+  w->img = a.take<char>(tc::bimage_bytes(kTcBlock, kTcBlock) + 256);
   return align_up(a.off, 256) + 256;
 }
 
@@ -415,6 +477,30 @@ using namespace x2;
 
 extern "C" {
 
+// ---- tensor-core GEMM building blocks (also exercised directly by tests/test_gpu_tc_gemm.py)
+size_t x2_tc_gemm_workspace_bytes(int32_t K, int32_t N) { return tc::bimage_bytes(K, N) + 256; }
+
+int x2_tc_gemm(const float* A, int64_t lda, int64_t M, int32_t K, const float* W, int64_t sbk, int64_t sbn,
+               int32_t N, const float* bias, float* C, int64_t ldc, int32_t beta, void* ws, size_t ws_bytes,
+               void* stream) {
+  X2_CHECK_ARG(A && W && C && M >= 0, "x2_tc_gemm: null pointer");
+  X2_CHECK_ARG(tc::g1_supported(K, N), "x2_tc_gemm: unsupported K=%d N=%d (need N <= 128 and the weight image to fit smem)", K, N);
+  if (ws_bytes < x2_tc_gemm_workspace_bytes(K, N)) { set_error("x2_tc_gemm: workspace too small"); return X2_EWORKSPACE; }
+  return tc::tc_gemm(A, lda, M, K, W, sbk, sbn, N, bias, C, ldc, beta, ws, (cudaStream_t)stream);
+}
+
+size_t x2_tc_wgrad_workspace_bytes(int64_t rows, int32_t N) {
+  return tc::tc_wgrad_workspace_floats(rows, N) * sizeof(float) + 256;
+}
+
+int x2_tc_wgrad(const float* Y, int64_t ldy, const float* X, int64_t ldx, int64_t rows, int32_t N, float* dW,
+                int64_t lddw, float* db, void* ws, size_t ws_bytes, void* stream) {
+  X2_CHECK_ARG(Y && X && dW && rows >= 0, "x2_tc_wgrad: null pointer");
+  X2_CHECK_ARG(N >= 1 && N <= 128, "x2_tc_wgrad: need 1 <= N <= 128 (got %d)", N);
+  if (ws_bytes < x2_tc_wgrad_workspace_bytes(rows, N)) { set_error("x2_tc_wgrad: workspace too small"); return X2_EWORKSPACE; }
+  return tc::tc_wgrad(Y, ldy, X, ldx, rows, N, dW, lddw, db, static_cast<float*>(ws), (cudaStream_t)stream);
+}
+
 size_t x2_sbfconv_fwd_workspace_bytes(const x2_conv_desc* d) {
   if (!d) return 0;
   FwdWs w;
@@ -445,8 +531,14 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
   // (1) x_src = x * lin_rbf(rbf)                                             :99-100
   k_rbf_filter<<<(unsigned)cdiv(E * D, 256), 256, 0, st>>>(d->x, d->rbf, d->w_rbf, E, D, d->R, w.xs, nullptr);
   X2_LAUNCH_OK();
-  // (2) Q | K | V | skip in one batched launch                               :105-107, :121
-  {
+  const Lin L{d->mode, w.img, nullptr, st};
+  // (2) Q | K | V | skip                                                     :105-107, :121
+  if (d->mode == X2_MODE_TF32X3) {
+    X2_TRY(lin_fwd(L, d->x, D, d->w_q, D, d->b_q, s->qkvs, 4 * D, E, D, D));
+    X2_TRY(lin_fwd(L, w.xs, D, d->w_k, D, d->b_k, s->qkvs + D, 4 * D, E, D, D));
+    X2_TRY(lin_fwd(L, w.xs, D, d->w_v, D, d->b_v, s->qkvs + 2 * D, 4 * D, E, D, D));
+    if (d->fuse_skip) X2_TRY(lin_fwd(L, d->x, D, d->w_skip, D, d->b_skip, s->qkvs + 3 * D, 4 * D, E, D, D));
+  } else {   // one batched SIMT launch
     GemmBatch p{};
     p.A[0] = d->x;  p.B[0] = d->w_q; p.bias[0] = d->b_q; p.C[0] = s->qkvs;
     p.A[1] = w.xs;  p.B[1] = d->w_k; p.bias[1] = d->b_k; p.C[1] = s->qkvs + D;
@@ -461,8 +553,8 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
   phase_end(X2_PHASE_NODE_PROJ, st);
   // (3) T-row projections                                                    :144, :148
   if (T > 0) {
-    if (d->A > 0) X2_TRY(gemm_nt(d->edge_attr, d->A, d->w_edge, d->A, nullptr, s->ea, D, T, D, d->A, st));
-    X2_TRY(gemm_nt(d->sbf, d->S, d->w_sbf, d->S, d->b_sbf, s->sg, D, T, D, d->S, st));
+    if (d->A > 0) X2_TRY(lin_fwd(L, d->edge_attr, d->A, d->w_edge, d->A, nullptr, s->ea, D, T, D, d->A));
+    X2_TRY(lin_fwd(L, d->sbf, d->S, d->w_sbf, d->S, d->b_sbf, s->sg, D, T, D, d->S));
   }
   phase_end(X2_PHASE_TROW_PROJ, st);
   // (4) fused gather + logits + segment softmax + gate + aggregate (+ skip)  :150-160, aggregate, :127
@@ -514,35 +606,36 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
   const float* dk = w.dqkv + D;
   const float* dv = w.dqkv + 2 * D;
 
+  const Lin L{d->mode, w.img, w.wg, st};
   // (3) T-row input gradients
-  if (A > 0 && g->dedge_attr && T > 0) X2_TRY(gemm_nn(w.dea, D, d->w_edge, A, g->dedge_attr, A, T, A, D, 0, st));
-  if (g->dsbf && T > 0) X2_TRY(gemm_nn(w.dsg, D, d->w_sbf, S, g->dsbf, S, T, S, D, 0, st));
+  if (A > 0 && g->dedge_attr && T > 0) X2_TRY(lin_dgrad(L, w.dea, D, d->w_edge, A, g->dedge_attr, A, T, A, D, 0));
+  if (g->dsbf && T > 0) X2_TRY(lin_dgrad(L, w.dsg, D, d->w_sbf, S, g->dsbf, S, T, S, D, 0));
   phase_end(X2_PHASE_TROW_DGRAD, st);
   // (4) T-row weight gradients (split-K over triplets, fixed-order reduction)
-  if (A > 0) X2_TRY(gemm_wgrad(w.dea, D, d->edge_attr, A, g->dw_edge, A, nullptr, T, D, A, w.wg, st));
-  X2_TRY(gemm_wgrad(w.dsg, D, d->sbf, S, g->dw_sbf, S, g->db_sbf, T, D, S, w.wg, st));
+  if (A > 0) X2_TRY(lin_wgrad(L, w.dea, D, d->edge_attr, A, g->dw_edge, A, nullptr, T, D, A));
+  X2_TRY(lin_wgrad(L, w.dsg, D, d->sbf, S, g->dw_sbf, S, g->db_sbf, T, D, S));
 
   phase_end(X2_PHASE_TROW_WGRAD, st);
   // (5) recompute the filtered sources
   k_rbf_filter<<<(unsigned)cdiv(E * D, 256), 256, 0, st>>>(d->x, d->rbf, d->w_rbf, E, D, R, w.xs, w.F);
   X2_LAUNCH_OK();
   // (6) node-level weight gradients
-  X2_TRY(gemm_wgrad(dq, 3 * D, d->x, D, g->dw_q, D, g->db_q, E, D, D, w.wg, st));
-  X2_TRY(gemm_wgrad(dk, 3 * D, w.xs, D, g->dw_k, D, g->db_k, E, D, D, w.wg, st));
-  X2_TRY(gemm_wgrad(dv, 3 * D, w.xs, D, g->dw_v, D, g->db_v, E, D, D, w.wg, st));
-  if (d->fuse_skip) X2_TRY(gemm_wgrad(grad_out, D, d->x, D, g->dw_skip, D, g->db_skip, E, D, D, w.wg, st));
+  X2_TRY(lin_wgrad(L, dq, 3 * D, d->x, D, g->dw_q, D, g->db_q, E, D, D));
+  X2_TRY(lin_wgrad(L, dk, 3 * D, w.xs, D, g->dw_k, D, g->db_k, E, D, D));
+  X2_TRY(lin_wgrad(L, dv, 3 * D, w.xs, D, g->dw_v, D, g->db_v, E, D, D));
+  if (d->fuse_skip) X2_TRY(lin_wgrad(L, grad_out, D, d->x, D, g->dw_skip, D, g->db_skip, E, D, D));
   // (7) dxs = dK W_k + dV W_v
-  X2_TRY(gemm_nn(dk, 3 * D, d->w_k, D, w.dxs, D, E, D, D, 0, st));
-  X2_TRY(gemm_nn(dv, 3 * D, d->w_v, D, w.dxs, D, E, D, D, 1, st));
+  X2_TRY(lin_dgrad(L, dk, 3 * D, d->w_k, D, w.dxs, D, E, D, D, 0));
+  X2_TRY(lin_dgrad(L, dv, 3 * D, d->w_v, D, w.dxs, D, E, D, D, 1));
   // (8) dx = dQ W_q (+ G W_o)
-  X2_TRY(gemm_nn(dq, 3 * D, d->w_q, D, g->dx, D, E, D, D, 0, st));
-  if (d->fuse_skip) X2_TRY(gemm_nn(grad_out, D, d->w_skip, D, g->dx, D, E, D, D, 1, st));
+  X2_TRY(lin_dgrad(L, dq, 3 * D, d->w_q, D, g->dx, D, E, D, D, 0));
+  if (d->fuse_skip) X2_TRY(lin_dgrad(L, grad_out, D, d->w_skip, D, g->dx, D, E, D, D, 1));
   // (9) dx += dxs * F ; dF = dxs * x
   k_filter_bwd<<<(unsigned)cdiv(E * D, 256), 256, 0, st>>>(d->x, w.F, w.dxs, g->dx, E * D);
   X2_LAUNCH_OK();
   // (10) d rbf = dF W_r ; dW_r = dF^T rbf
-  X2_TRY(gemm_nn(w.dxs, D, d->w_rbf, R, g->drbf, R, E, R, D, 0, st));
-  X2_TRY(gemm_wgrad(w.dxs, D, d->rbf, R, g->dw_rbf, R, nullptr, E, D, R, w.wg, st));
+  X2_TRY(lin_dgrad(L, w.dxs, D, d->w_rbf, R, g->drbf, R, E, R, D, 0));
+  X2_TRY(lin_wgrad(L, w.dxs, D, d->rbf, R, g->dw_rbf, R, nullptr, E, D, R));
   phase_end(X2_PHASE_NODE_BWD, st);
   return X2_OK;
 }

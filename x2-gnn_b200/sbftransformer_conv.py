@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Optional
 
 import torch
@@ -19,7 +20,18 @@ from torch import Tensor, nn
 
 from . import _lib, graph_meta
 
-MODE_FP32 = 0
+MODE_FP32 = 0      # X2_MODE_FP32: SIMT fp32 everywhere
+MODE_TF32X3 = 1    # X2_MODE_TF32X3: Linear layers on tcgen05 tensor cores, 3xTF32 (fp32-accurate)
+
+
+def default_mode(hc: int) -> int:
+    """Tensor-core Linear layers whenever the shape allows; override with X2GNN_MODE=fp32|tf32x3."""
+    env = os.environ.get("X2GNN_MODE", "").lower()
+    if env == "fp32":
+        return MODE_FP32
+    if env == "tf32x3":
+        return MODE_TF32X3
+    return MODE_TF32X3 if hc % 128 == 0 else MODE_FP32
 
 
 def Glorot_Ortho_(tensor: Tensor, scale: float = 2.0) -> Tensor:
@@ -162,7 +174,7 @@ class SBFTransformerConv(nn.Module):
         self.dropout = dropout
         self.edge_dim = edge_dim
         self._alpha = None
-        self.precision = MODE_FP32
+        self.precision = None          # None => default_mode(heads*out_channels) at call time
 
         if isinstance(in_channels, int):
             in_channels = (in_channels, in_channels)
@@ -218,7 +230,8 @@ class SBFTransformerConv(nn.Module):
         fuse = self.concat and self.root_weight and self.lin_beta is None
         p_drop = float(self.dropout) if self.training else 0.0
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0 else 0
-        cfg = dict(heads=H, out_channels=Cc, mode=self.precision, dropout_p=p_drop, seed=seed,
+        mode = default_mode(H * Cc) if self.precision is None else self.precision
+        cfg = dict(heads=H, out_channels=Cc, mode=mode, dropout_p=p_drop, seed=seed,
                    want_alpha=isinstance(return_attention_weights, bool))
         out, alpha = _SBFConvFn.apply(
             cfg, meta, x, rbf, sbf, edge_attr if self.lin_edge is not None else None,

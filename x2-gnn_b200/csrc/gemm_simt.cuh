@@ -317,23 +317,40 @@ k_gemm(GemmBatch p, int64_t M, int N, int64_t K, int64_t lda, int64_t ldb, int64
   }
 }
 
-// out[m*ldo + n] = sum_z partial[z][m][n]  (fixed order); bias[m] = sum_z colsum[z][m]
-__global__ void k_splitk_reduce(const float* __restrict__ partial, const float* __restrict__ colsum,
-                                int splits, int64_t M, int N, float* __restrict__ out, int64_t ldo,
-                                float* __restrict__ bias) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// out[m*ldo + n] = sum_z partial[z][m][n] ; bias[m] = sum_z colsum[z][m].
+// 256 threads = 8 warps x 32 outputs: warp g sums the splits z = g, g+8, ... in order, then the 8
+// per-warp sums are combined in order g = 0..7 -- a fixed summation tree (deterministic) that is 8x
+// shorter than one serial loop over all splits.
+__global__ void __launch_bounds__(256)
+k_splitk_reduce(const float* __restrict__ partial, const float* __restrict__ colsum, int splits, int64_t M,
+                int N, float* __restrict__ out, int64_t ldo, float* __restrict__ bias) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int64_t MN = M * N;
-  if (idx < MN) {
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * MN + idx];
-    const int64_t m = idx / N;
-    out[m * ldo + (idx - m * N)] = s;
+  const int64_t nblk_out = (MN + 31) / 32;
+  const bool is_bias = (int64_t)blockIdx.x >= nblk_out;      // trailing blocks reduce the column sums
+  const int64_t idx = is_bias ? ((int64_t)blockIdx.x - nblk_out) * 32 + lane : (int64_t)blockIdx.x * 32 + lane;
+  const int64_t lim = is_bias ? M : MN;
+  const float* src = is_bias ? colsum : partial;
+  float s = 0.f;
+  if (idx < lim)
+    for (int z = g; z < splits; z += 8) s += src[(int64_t)z * lim + idx];
+  red[g][lane] = s;
+  __syncthreads();
+  if (g == 0 && idx < lim) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += red[k][lane];
+    if (is_bias) bias[idx] = t;
+    else {
+      const int64_t m = idx / N;
+      out[m * ldo + (idx - m * N)] = t;
+    }
   }
-  if (bias != nullptr && colsum != nullptr && idx < M) {
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += colsum[(int64_t)z * M + idx];
-    bias[idx] = s;
-  }
+}
+
+static inline unsigned splitk_reduce_blocks(int64_t M, int N, bool with_bias) {
+  return (unsigned)(((M * N + 31) / 32) + (with_bias ? (M + 31) / 32 : 0));
 }
 
 // ------------------------------------------------------------------------- host launchers
@@ -409,7 +426,8 @@ static inline int gemm_wgrad(const float* dy, int64_t lddy, const float* x, int6
   else k_gemm<32, false, false, 1><<<grid, block, 0, st>>>(p, M, N, rows, lddy, ldx, N, 0, kchunk, cs);
   X2_LAUNCH_OK();
   const int64_t MN = (int64_t)M * N;
-  k_splitk_reduce<<<(unsigned)cdiv(MN, 256), 256, 0, st>>>(partial, cs, splits, M, N, dW, lddw, db);
+  (void)MN;
+  k_splitk_reduce<<<splitk_reduce_blocks(M, N, db != nullptr), 256, 0, st>>>(partial, cs, splits, M, N, dW, lddw, db);
   X2_LAUNCH_OK();
   return X2_OK;
 }

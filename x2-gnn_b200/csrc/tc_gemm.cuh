@@ -4,13 +4,17 @@
 //     x = x_hi + x_lo   (x_hi = rna_tf32(x), x_lo = rna_tf32(x - x_hi))
 //     A.B ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo        (fp32 accumulation in TMEM)
 //
-// Two persistent, warp-specialised kernels (1 CTA / SM, 288 threads):
+// Two persistent, warp-specialised kernels (1 CTA / SM, 416 threads):
 //   warp 0      : TMEM allocation + single-thread tcgen05.mma issue
-//   warps 1..4  : producers -- coalesced 128-bit global loads of fp32 activations, hi/lo split in
+//   warps 1..8  : producers -- coalesced 128-bit global loads of fp32 activations, hi/lo split in
 //                 registers, 128-bit stores into the UMMA canonical SWIZZLE_128B smem layout
-//                 (the split has to touch every element anyway, so LDG->STS replaces TMA here)
-//   warps 5..8  : epilogue -- tcgen05.ld of the fp32 accumulator (one output row per thread),
-//                 bias / accumulate, 128-bit global stores
+//                 (the split has to touch every element anyway, so LDG->STS replaces TMA here).
+//                 Two producer warps per SM sub-partition and two chunks of loads in flight per
+//                 thread: with one warp per sub-partition the kernel was issue-latency bound
+//                 (ncu: 13.7 cycles per issued instruction, profiles/r1_notes.md).
+//   warps 9..12 : epilogue -- tcgen05.ld of the fp32 accumulator (one output row per thread),
+//                 transposed through a padded smem tile so that every global store instruction
+//                 writes whole 128-byte lines, bias / accumulate fused
 // synchronised with mbarriers (full/empty smem ring, full/empty double-buffered TMEM).
 //
 //   G1  C[M,N] (+)= A[M,K] . B(K,N) + bias     A streamed (K-major), B = weights, pre-split into a
@@ -24,8 +28,10 @@
 namespace x2 {
 namespace tc {
 
-constexpr int kThreads = 288;
-constexpr int kProducerThreads = 128;
+constexpr int kThreads = 416;
+constexpr int kProducerThreads = 256;
+constexpr int kEpilogueThreads = 128;
+constexpr int kStageWords = 36;      // padded row pitch (words) of the epilogue transpose tile
 constexpr int kTileM = 128;          // rows per tile (UMMA M)
 constexpr int kChunkK = 32;          // fp32 per 128-byte swizzle row
 constexpr int kChunkBytes = kTileM * kChunkK * 4;   // 16 KB: one 128 x 32 fp32 operand chunk
@@ -112,10 +118,11 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
 }
 __device__ __forceinline__ void split4(const float4& v, uint4& hi, uint4& lo) {
   hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
-  lo.x = to_tf32(v.x - __uint_as_float(hi.x));
-  lo.y = to_tf32(v.y - __uint_as_float(hi.y));
-  lo.z = to_tf32(v.z - __uint_as_float(hi.z));
-  lo.w = to_tf32(v.w - __uint_as_float(hi.w));
+  // lo is exact in fp32; the tensor core ignores its 13 low mantissa bits (~2^-22 of |x|)
+  lo.x = __float_as_uint(v.x - __uint_as_float(hi.x));
+  lo.y = __float_as_uint(v.y - __uint_as_float(hi.y));
+  lo.z = __float_as_uint(v.z - __uint_as_float(hi.z));
+  lo.w = __float_as_uint(v.w - __uint_as_float(hi.w));
 }
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
@@ -185,7 +192,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
   const uint32_t bhalf = (uint32_t)p.KC * p.N_pad * 128;          // bytes of one B image half
   uint8_t* sB = smem;                                             // [hi | lo]
   uint8_t* sA = smem + 2 * bhalf;                                 // S x [hi 16K | lo 16K]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)S * 2 * kChunkBytes);
+  float* sT = reinterpret_cast<float*>(sA + (size_t)S * 2 * kChunkBytes);   // 4 x [32][36] transpose tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sT + 4 * 32 * kStageWords);
   uint64_t* full = bars;            // [S]   producers -> MMA
   uint64_t* empty = bars + S;       // [S]   MMA -> producers
   uint64_t* tfull = bars + 2 * S;   // [2]   MMA -> epilogue
@@ -202,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kProducerThreads);   // 128 epilogue threads
+      mbar_init(&tempty[i], kEpilogueThreads);
     }
     fence_barrier_init();
   }
@@ -240,104 +248,152 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
           tc_fence_after();
           const int kvalid = min(kChunkK, p.K - kc * kChunkK);
           const int ksteps = (kvalid + 7) >> 3;
-          const uint32_t a_hi = sA_u + st * 2 * kChunkBytes, a_lo = a_hi + kChunkBytes;
-          const uint32_t b_hi = sB_u + (uint32_t)kc * p.N_pad * 128, b_lo = b_hi + bhalf;
+          const uint64_t dah = make_desc(sA_u + st * 2 * kChunkBytes, 16, 1024);
+          const uint64_t dal = make_desc(sA_u + st * 2 * kChunkBytes + kChunkBytes, 16, 1024);
+          const uint64_t dbh = make_desc(sB_u + (uint32_t)kc * p.N_pad * 128, 16, 1024);
+          const uint64_t dbl = make_desc(sB_u + (uint32_t)kc * p.N_pad * 128 + bhalf, 16, 1024);
           for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t dah = make_desc(a_hi + ks * 32, 16, 1024);
-            const uint64_t dal = make_desc(a_lo + ks * 32, 16, 1024);
-            const uint64_t dbh = make_desc(b_hi + ks * 32, 16, 1024);
-            const uint64_t dbl = make_desc(b_lo + ks * 32, 16, 1024);
-            umma_tf32(taddr, dah, dbh, idesc, (kc | ks) != 0);
-            umma_tf32(taddr, dal, dbh, idesc, 1);
-            umma_tf32(taddr, dah, dbl, idesc, 1);
+            const uint64_t adv = (uint64_t)(ks * 2);      // +32 bytes (>>4) along K inside the swizzle row
+            umma_tf32(taddr, dah + adv, dbh + adv, idesc, (kc | ks) != 0);
+            umma_tf32(taddr, dal + adv, dbh + adv, idesc, 1);
+            umma_tf32(taddr, dah + adv, dbl + adv, idesc, 1);
           }
           umma_commit(&empty[st]);          // smem slot reusable once these MMAs retire
         }
         umma_commit(&tfull[buf]);           // accumulator complete
       }
     }
-  } else if (warp <= 4) {
+  } else if (warp <= 8) {
     // =============================== producers ===============================
-    const int pt = threadIdx.x - 32;                 // 0..127
+    // 256 threads; thread (c16, r0) moves the 16-byte column chunk c16 of rows r0 + 32 i.  Two
+    // chunks of global loads are in flight per thread (register double buffering).
+    const int pt = threadIdx.x - 32;                 // 0..255
     const int c16 = pt & 7, r0 = pt >> 3;            // 8 threads cover one 128-byte row segment
     const bool vec = ((p.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
-    uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t m0 = tile * kTileM;
-      for (int kc = 0; kc < KC; ++kc, ++it) {
-        const uint32_t st = it % S, ph = (it / S) & 1;
-        const int kcol = kc * kChunkK + c16 * 4;
-        float4 v[8];
+    const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t nchunk = my_tiles * KC;
+    const uint32_t sA_u = smem_u32(sA);
+    const float* const a_thr = p.A + (int64_t)r0 * p.lda + c16 * 4;
+    const int64_t row_step = 32 * p.lda;
+    uint32_t soff[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {               // issue all global loads before waiting
-          const int64_t row = m0 + r0 + 16 * i;
+    for (int i = 0; i < 4; ++i) soff[i] = kmajor_off(r0 + 32 * i, c16);
+
+    auto issue = [&](float4 (&v)[4], int64_t it) {
+      const int64_t m0 = (blockIdx.x + (it / KC) * gridDim.x) * kTileM;
+      const int kc0 = (int)(it % KC) * kChunkK;
+      const float* src = a_thr + m0 * p.lda + kc0;
+      if (vec && m0 + kTileM <= p.M && kc0 + kChunkK <= p.K) {       // interior chunk: no guards
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(src + i * row_step));
+      } else {
+        const int kcol = kc0 + c16 * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row < p.M) {
-            const float* src = p.A + row * p.lda + kcol;
-            if (vec && kcol + 3 < p.K) v[i] = __ldg(reinterpret_cast<const float4*>(src));
+          if (m0 + r0 + 32 * i < p.M) {
+            const float* q = src + i * row_step;
+            if (vec && kcol + 3 < p.K) v[i] = __ldg(reinterpret_cast<const float4*>(q));
             else {
-              if (kcol < p.K) v[i].x = __ldg(src);
-              if (kcol + 1 < p.K) v[i].y = __ldg(src + 1);
-              if (kcol + 2 < p.K) v[i].z = __ldg(src + 2);
-              if (kcol + 3 < p.K) v[i].w = __ldg(src + 3);
+              if (kcol < p.K) v[i].x = __ldg(q);
+              if (kcol + 1 < p.K) v[i].y = __ldg(q + 1);
+              if (kcol + 2 < p.K) v[i].z = __ldg(q + 2);
+              if (kcol + 3 < p.K) v[i].w = __ldg(q + 3);
             }
           }
         }
-        mbar_wait(&empty[st], ph ^ 1);
-        const uint32_t base = smem_u32(sA) + st * 2 * kChunkBytes;
+      }
+    };
+    auto commit = [&](const float4 (&v)[4], int64_t it) {
+      const uint32_t st = (uint32_t)(it % S), ph = (uint32_t)((it / S) & 1);
+      mbar_wait(&empty[st], ph ^ 1);
+      const uint32_t base = sA_u + st * 2 * kChunkBytes;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint4 hi, lo;
-          split4(v[i], hi, lo);
-          const uint32_t off = kmajor_off(r0 + 16 * i, c16);
-          sts128(base + off, hi);
-          sts128(base + kChunkBytes + off, lo);
-        }
-        fence_proxy_async();
-        mbar_arrive(&full[st]);
+      for (int i = 0; i < 4; ++i) {
+        uint4 hi, lo;
+        split4(v[i], hi, lo);
+        sts128(base + soff[i], hi);
+        sts128(base + kChunkBytes + soff[i], lo);
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[st]);
+    };
+
+    float4 va[4], vb[4];
+    if (nchunk > 0) issue(va, 0);
+    for (int64_t it = 0; it < nchunk; it += 2) {
+      if (it + 1 < nchunk) issue(vb, it + 1);
+      commit(va, it);
+      if (it + 1 < nchunk) {
+        if (it + 2 < nchunk) issue(va, it + 2);
+        commit(vb, it + 1);
       }
     }
   } else {
     // =============================== epilogue ===============================
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    float* tile_s = sT + q * 32 * kStageWords;       // this warp's [32][36] transpose tile
+    const bool vecC = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.N & 3) == 0);
+    const int rr = lane >> 3, cc = (lane & 7) * 4;   // read-back mapping: 4 rows x 8 float4 per pass
     uint32_t tcount = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const uint32_t buf = tcount & 1;
       mbar_wait(&tfull[buf], (tcount >> 1) & 1);
       tc_fence_after();
-      const int64_t row = tile * kTileM + q * 32 + lane;
+      const int64_t row0 = tile * kTileM + q * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128;
-      for (int c0 = 0; c0 < p.N_pad; c0 += 16) {
+      for (int c0 = 0; c0 < p.N_pad; c0 += 32) {
+        // thread = accumulator row: 32 (or 16) columns -> padded smem tile
         float v[16];
         tmem_ld16(taddr + c0, v);
-        if (row < p.M) {
-          float* dst = p.C + row * p.ldc + c0;
-          if (c0 + 16 <= p.N && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (p.bias) {
-                o.x += __ldg(p.bias + c0 + j); o.y += __ldg(p.bias + c0 + j + 1);
-                o.z += __ldg(p.bias + c0 + j + 2); o.w += __ldg(p.bias + c0 + j + 3);
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(tile_s + lane * kStageWords + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (c0 + 16 < p.N_pad) {
+          tmem_ld16(taddr + c0 + 16, v);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(tile_s + lane * kStageWords + 16 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        __syncwarp();
+        if (vecC) {
+          // each store instruction writes 4 rows x 128 contiguous bytes
+          const int col = c0 + cc;
+          if (col < p.N) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll
+            for (int pass = 0; pass < 8; ++pass) {
+              const int r = pass * 4 + rr;
+              const int64_t row = row0 + r;
+              if (row < p.M) {
+                float4 o = *reinterpret_cast<const float4*>(tile_s + r * kStageWords + cc);
+                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                float* dst = p.C + row * p.ldc + col;
+                if (p.beta) {
+                  const float4 old = *reinterpret_cast<const float4*>(dst);
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *reinterpret_cast<float4*>(dst) = o;
               }
-              if (p.beta) {
-                const float4 old = *reinterpret_cast<const float4*>(dst + j);
-                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-              }
-              *reinterpret_cast<float4*>(dst + j) = o;
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (c0 + j < p.N) {
-                float o = v[j];
-                if (p.bias) o += __ldg(p.bias + c0 + j);
-                if (p.beta) o += dst[j];
-                dst[j] = o;
+          }
+        } else {
+          const int col = c0 + lane;
+          if (col < p.N) {
+            const float bv = p.bias ? __ldg(p.bias + col) : 0.f;
+            for (int r = 0; r < 32; ++r) {
+              const int64_t row = row0 + r;
+              if (row < p.M) {
+                float o = tile_s[r * kStageWords + lane] + bv;
+                float* dst = p.C + row * p.ldc + col;
+                if (p.beta) o += *dst;
+                *dst = o;
               }
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(&tempty[buf]);
@@ -387,7 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
   uint64_t* empty = bars + S;
   uint64_t* tfull = bars + 2 * S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
-  float* cs_smem = reinterpret_cast<float*>(bars + 2 * S + 2);   // [4][128] column-sum staging
+  float* cs_smem = reinterpret_cast<float*>(bars + 2 * S + 2);   // [8][128] column-sum staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -420,88 +476,131 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
         const uint32_t x_hi = y_lo + kChunkBytes, x_lo = x_hi + xbytes;
         const int kvalid = (int)min((int64_t)kChunkK, rend - rbeg - c * kChunkK);
         const int ksteps = (kvalid + 7) >> 3;
+        const uint64_t dyh = make_desc(y_hi, 4096, 512, kLayoutSW128Base32);
+        const uint64_t dyl = make_desc(y_lo, 4096, 512, kLayoutSW128Base32);
+        const uint64_t dxh = make_desc(x_hi, 4096, 512, kLayoutSW128Base32);
+        const uint64_t dxl = make_desc(x_lo, 4096, 512, kLayoutSW128Base32);
         for (int ks = 0; ks < ksteps; ++ks) {
-          // one K=8 step = two 4-row k-groups = 1024 B
-          const uint64_t dyh = make_desc(y_hi + ks * 1024, 4096, 512, kLayoutSW128Base32);
-          const uint64_t dyl = make_desc(y_lo + ks * 1024, 4096, 512, kLayoutSW128Base32);
-          const uint64_t dxh = make_desc(x_hi + ks * 1024, 4096, 512, kLayoutSW128Base32);
-          const uint64_t dxl = make_desc(x_lo + ks * 1024, 4096, 512, kLayoutSW128Base32);
-          umma_tf32(tmem_base, dyh, dxh, idesc, (c | ks) != 0);
-          umma_tf32(tmem_base, dyl, dxh, idesc, 1);
-          umma_tf32(tmem_base, dyh, dxl, idesc, 1);
+          const uint64_t adv = (uint64_t)(ks * 64);       // one K=8 step = two 4-row k-groups = 1024 B (>>4)
+          umma_tf32(tmem_base, dyh + adv, dxh + adv, idesc, (c | ks) != 0);
+          umma_tf32(tmem_base, dyl + adv, dxh + adv, idesc, 1);
+          umma_tf32(tmem_base, dyh + adv, dxl + adv, idesc, 1);
         }
         umma_commit(&empty[st]);
       }
       umma_commit(tfull);
     }
-  } else if (warp <= 4) {
+  } else if (warp <= 8) {
+    // 256 producer threads.  Y chunk = 32 rows x 32 float4: thread owns float4 column yc of rows
+    // yr + 8 i.  X chunk = 32 rows x xq float4, flattened (up to 4 per thread).  Two chunks of loads
+    // in flight per thread.
     const int pt = threadIdx.x - 32;
-    // Y: 32 rows x 32 float4; thread owns float4 column yc (4 output rows m = 4*yc..) of rows yr+4i
     const int yc = pt & 31, yr = pt >> 5;
     const bool vecY = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0);
-    const bool vecX = ((p.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0);
+    const bool vecX = ((p.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) && ((p.N & 3) == 0);
     const int xq = p.N_pad / 4;                      // float4 per X row (8..32)
+    const int nx = kChunkK * xq;                     // float4 per X chunk (256..1024)
     float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
-    for (int64_t c = 0; c < nchunks; ++c) {
-      const uint32_t st = (uint32_t)(c % S), ph = (uint32_t)((c / S) & 1);
+    const uint32_t s_u = smem_u32(sS);
+    const float* const y_thr = p.Y + (int64_t)yr * p.ldy + yc * 4;
+    const int64_t y_step = 8 * p.ldy;
+    uint32_t yoff[4], xoff[4];
+    int xr[4], xcol[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      yoff[i] = mnmajor_off(yr + 8 * i, yc);
+      const int f = pt + i * kProducerThreads;
+      xr[i] = f / xq;
+      const int xc = f - xr[i] * xq;
+      xcol[i] = xc * 4;
+      xoff[i] = mnmajor_off(xr[i] & 31, xc);
+    }
+
+    auto issue = [&](float4 (&vy)[4], float4 (&vx)[4], int64_t c) {
       const int64_t row0 = rbeg + c * kChunkK;
-      float4 vy[8];
+      const bool interior = row0 + kChunkK <= rend;
+      const float* ysrc = y_thr + row0 * p.ldy;
+      if (interior && vecY) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t row = row0 + yr + 4 * i;
-        vy[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < rend) {
-          const float* src = p.Y + row * p.ldy + yc * 4;
-          if (vecY) vy[i] = __ldg(reinterpret_cast<const float4*>(src));
-          else { vy[i].x = __ldg(src); vy[i].y = __ldg(src + 1); vy[i].z = __ldg(src + 2); vy[i].w = __ldg(src + 3); }
-        }
-        cs0 += vy[i].x; cs1 += vy[i].y; cs2 += vy[i].z; cs3 += vy[i].w;   // fixed order per thread
-      }
-      mbar_wait(&empty[st], ph ^ 1);
-      const uint32_t base = smem_u32(sS) + st * stage_bytes;
+        for (int i = 0; i < 4; ++i) vy[i] = __ldg(reinterpret_cast<const float4*>(ysrc + i * y_step));
+      } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        uint4 hi, lo;
-        split4(vy[i], hi, lo);
-        const uint32_t off = mnmajor_off(yr + 4 * i, yc);
-        sts128(base + off, hi);
-        sts128(base + kChunkBytes + off, lo);
-      }
-      // X: 32 rows x xq float4
-      const uint32_t xb = base + 2 * kChunkBytes;
-      for (int f = pt; f < kChunkK * xq; f += kProducerThreads) {
-        const int r = f / xq, xc = f - r * xq;
-        const int64_t row = row0 + r;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < rend) {
-          const float* src = p.X + row * p.ldx + xc * 4;
-          const int col = xc * 4;
-          if (vecX && col + 3 < p.N) v = __ldg(reinterpret_cast<const float4*>(src));
-          else {
-            if (col < p.N) v.x = __ldg(src);
-            if (col + 1 < p.N) v.y = __ldg(src + 1);
-            if (col + 2 < p.N) v.z = __ldg(src + 2);
-            if (col + 3 < p.N) v.w = __ldg(src + 3);
+        for (int i = 0; i < 4; ++i) {
+          vy[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row0 + yr + 8 * i < rend) {
+            const float* q = ysrc + i * y_step;
+            if (vecY) vy[i] = __ldg(reinterpret_cast<const float4*>(q));
+            else { vy[i].x = __ldg(q); vy[i].y = __ldg(q + 1); vy[i].z = __ldg(q + 2); vy[i].w = __ldg(q + 3); }
           }
         }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        vx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pt + i * kProducerThreads < nx) {
+          const int64_t row = row0 + xr[i];
+          if (row < rend) {
+            const float* q = p.X + row * p.ldx + xcol[i];
+            if (vecX && xcol[i] + 3 < p.N) vx[i] = __ldg(reinterpret_cast<const float4*>(q));
+            else {
+              if (xcol[i] < p.N) vx[i].x = __ldg(q);
+              if (xcol[i] + 1 < p.N) vx[i].y = __ldg(q + 1);
+              if (xcol[i] + 2 < p.N) vx[i].z = __ldg(q + 2);
+              if (xcol[i] + 3 < p.N) vx[i].w = __ldg(q + 3);
+            }
+          }
+        }
+      }
+    };
+    auto commit = [&](const float4 (&vy)[4], const float4 (&vx)[4], int64_t c) {
+      const uint32_t st = (uint32_t)(c % S), ph = (uint32_t)((c / S) & 1);
+      mbar_wait(&empty[st], ph ^ 1);
+      const uint32_t base = s_u + st * stage_bytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        cs0 += vy[i].x; cs1 += vy[i].y; cs2 += vy[i].z; cs3 += vy[i].w;   // fixed order per thread
         uint4 hi, lo;
-        split4(v, hi, lo);
-        const uint32_t off = mnmajor_off(r, xc);
-        sts128(xb + off, hi);
-        sts128(xb + xbytes + off, lo);
+        split4(vy[i], hi, lo);
+        sts128(base + yoff[i], hi);
+        sts128(base + kChunkBytes + yoff[i], lo);
+      }
+      const uint32_t xb = base + 2 * kChunkBytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (pt + i * kProducerThreads < nx) {
+          uint4 hi, lo;
+          split4(vx[i], hi, lo);
+          sts128(xb + xoff[i], hi);
+          sts128(xb + xbytes + xoff[i], lo);
+        }
       }
       fence_proxy_async();
       mbar_arrive(&full[st]);
+    };
+
+    float4 ya[4], xa[4], yb[4], xb_[4];
+    if (nchunks > 0) issue(ya, xa, 0);
+    for (int64_t c = 0; c < nchunks; c += 2) {
+      if (c + 1 < nchunks) issue(yb, xb_, c + 1);
+      commit(ya, xa, c);
+      if (c + 1 < nchunks) {
+        if (c + 2 < nchunks) issue(ya, xa, c + 2);
+        commit(yb, xb_, c + 1);
+      }
     }
-    // column sums of Y over this CTA's rows: combine the 4 row-phase threads in fixed order
+    // column sums of Y over this CTA's rows: combine the 8 row-phase threads in fixed order
     if (p.colsum) {
       cs_smem[yr * 128 + yc * 4 + 0] = cs0;
       cs_smem[yr * 128 + yc * 4 + 1] = cs1;
       cs_smem[yr * 128 + yc * 4 + 2] = cs2;
       cs_smem[yr * 128 + yc * 4 + 3] = cs3;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const float s = (cs_smem[pt] + cs_smem[128 + pt]) + (cs_smem[256 + pt] + cs_smem[384 + pt]);
-      p.colsum[(int64_t)blockIdx.x * 128 + pt] = s;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (pt < 128) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) s += cs_smem[g * 128 + pt];
+        p.colsum[(int64_t)blockIdx.x * 128 + pt] = s;
+      }
     }
   } else {
     const int q = warp & 3;
@@ -539,11 +638,13 @@ static inline size_t bimage_bytes(int K, int N) {
   return align_up((size_t)2 * KC * N_pad * 128, 256);
 }
 
+constexpr size_t kEpiBytes = 4 * 32 * kStageWords * sizeof(float);   // epilogue transpose tiles
+
 static inline bool g1_supported(int K, int N) {
   if (K < 1 || N < 1 || N > 128) return false;
   const int KC = (K + kChunkK - 1) / kChunkK, N_pad = ceil_to(N, 16);
   const size_t b = (size_t)2 * KC * N_pad * 128;
-  return b + 2 * (size_t)2 * kChunkBytes + 2048 <= (size_t)kMaxSmem;
+  return b + 2 * (size_t)2 * kChunkBytes + kEpiBytes + 2048 <= (size_t)kMaxSmem;
 }
 
 // C[M,N] (+)= A[M,K] . B(K,N) + bias, B(k,n) = W[k*sbk + n*sbn].  img: scratch for the weight image.
@@ -556,9 +657,9 @@ static int tc_gemm(const float* A, int64_t lda, int64_t M, int K, const float* W
   k_make_bimage<<<(total + 255) / 256, 256, 0, st>>>(W, sbk, sbn, K, N, KC, N_pad, static_cast<uint32_t*>(img));
   X2_LAUNCH_OK();
   const size_t bbytes = (size_t)2 * KC * N_pad * 128;
-  int stages = (int)(((size_t)kMaxSmem - bbytes - 2048) / (2 * kChunkBytes));
+  int stages = (int)(((size_t)kMaxSmem - bbytes - kEpiBytes - 2048) / (2 * kChunkBytes));
   if (stages > 4) stages = 4;
-  const size_t smem = 1024 + bbytes + (size_t)stages * 2 * kChunkBytes + 256;
+  const size_t smem = 1024 + bbytes + (size_t)stages * 2 * kChunkBytes + kEpiBytes + 256;
   static bool attr_set = false;
   if (!attr_set) {
     X2_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -590,6 +691,7 @@ static inline size_t tc_wgrad_workspace_floats(int64_t rows, int N) {
 __global__ void k_splitk_reduce(const float* __restrict__ partial, const float* __restrict__ colsum,
                                 int splits, int64_t M, int N, float* __restrict__ out, int64_t ldo,
                                 float* __restrict__ bias);
+static inline unsigned splitk_reduce_blocks(int64_t M, int N, bool with_bias);
 
 namespace tc {
 
@@ -601,9 +703,9 @@ static int tc_wgrad(const float* Y, int64_t ldy, const float* X, int64_t ldx, in
   const int grid = wgrad_ctas(rows);
   const int64_t rpc = cdiv(cdiv(rows > 0 ? rows : 1, grid), kChunkK) * kChunkK;
   const uint32_t stage_bytes = 2 * kChunkBytes + 2 * (uint32_t)(N_pad / 32) * 4096;
-  int stages = (int)(((size_t)kMaxSmem - 4096 - 2048) / stage_bytes);
+  int stages = (int)(((size_t)kMaxSmem - 8192 - 2048) / stage_bytes);
   if (stages > 4) stages = 4;
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + 256 + 4 * 128 * sizeof(float);
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + 256 + 8 * 128 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     X2_CUDA_OK(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -614,8 +716,7 @@ static int tc_wgrad(const float* Y, int64_t ldy, const float* X, int64_t ldx, in
   p.partial = ws; p.colsum = db ? ws + (size_t)grid * 128 * N : nullptr; p.stages = stages;
   k_tc_wgrad<<<grid, kThreads, smem, st>>>(p);
   X2_LAUNCH_OK();
-  const int64_t MN = (int64_t)128 * N;
-  k_splitk_reduce<<<(unsigned)cdiv(MN, 256), 256, 0, st>>>(ws, p.colsum, grid, 128, N, dW, lddw, db);
+  k_splitk_reduce<<<splitk_reduce_blocks(128, N, db != nullptr), 256, 0, st>>>(ws, p.colsum, grid, 128, N, dW, lddw, db);
   X2_LAUNCH_OK();
   return X2_OK;
 }

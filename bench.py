@@ -168,6 +168,83 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------- full training step
+HPARAMS = dict(conv_layers=4, sbf_dim=7, rbf_dim=6, in_channels=128, heads=16, embedding_size=128)  # config.json
+
+
+def train_step_bench(dev, world, rank, steps, warmup, with_cpu):
+    """QM9 molecules/s of a full U0 training step (BASELINE.json configs[1]/[4]): forward of the
+    xgnn_poly-equivalent harness model on a 128-molecule batch per GPU, SmoothL1 loss, backward,
+    flat-bucket gradient all-reduce (N > 1), global-norm clip, Adam, EMA -- trainer.py:37-48."""
+    import torch
+    import torch.distributed as dist
+    from x2gnn_b200 import ddp, synth
+    from x2gnn_b200.xgnn_model import XGNNPoly
+
+    torch.manual_seed(0)
+    model = XGNNPoly(**HPARAMS).to(dev)
+    ema = torch.optim.swa_utils.AveragedModel(model, multi_avg_fn=torch.optim.swa_utils.get_ema_multi_avg_fn(0.95))
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    b = synth.qm9_batch(NMOL, seed=rank)
+    data = {k: (torch.from_numpy(v).to(dev) if hasattr(v, "shape") else v) for k, v in b.items()}
+    y = torch.zeros(NMOL, device=dev)
+    bucket = ddp.FlatGradBucket(model.parameters())
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.smooth_l1_loss(model(data), y)
+        loss.backward()
+        if world > 1:
+            bucket.pack()
+            bucket.allreduce(average=True)
+            bucket.unpack()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=100.0)
+        opt.step()
+        ema.update_parameters(model)
+        return loss
+
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    res = {"molecules_per_sec": world * NMOL / (ms * 1e-3), "ms_per_step": ms, "steps": steps,
+           "molecules_per_gpu": NMOL, "loss": float(loss), "N": len(b["x"]), "E": int(b["edge_index"].shape[1])}
+    if with_cpu and rank == 0:
+        from oracle import model as omodel
+        ncores = os.cpu_count() or 1
+        torch.set_num_threads(ncores)
+        nm = 8
+        bc = synth.qm9_batch(nm, seed=0)
+        dc = {k: (torch.from_numpy(v) if hasattr(v, "shape") else v) for k, v in bc.items()}
+        torch.manual_seed(0)
+        ref = omodel.XGNNPoly(**HPARAMS)
+        ropt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+
+        def cstep():
+            ropt.zero_grad(set_to_none=True)
+            torch.nn.functional.smooth_l1_loss(ref(dc), torch.zeros(nm)).backward()
+            torch.nn.utils.clip_grad_norm_(ref.parameters(), 100.0)
+            ropt.step()
+        sec = time_cpu(cstep, 2, warmup=1)
+        res["cpu_baseline"] = {"molecules_per_sec": nm / sec, "cores": ncores, "kind": "port",
+                               "sample": f"{nm}-molecule batch, 1 warm-up + 2 timed training steps of the oracle model"}
+    return res
+
+
 # ---------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -290,6 +367,15 @@ def run_ours(args):
         e_ms = float(t[0])
     e2e_value = total_T / (e_ms / e2e_steps * 1e-3)
 
+    # ------------------------------------------------ full training step (molecules/s), all ranks
+    train = None
+    if not args.no_train_step:
+        try:
+            train = train_step_bench(dev, world, rank, max(3, min(steps, 10)), 3,
+                                     with_cpu=(world == 1 and not args.no_cpu_baseline))
+        except Exception as exc:  # keep the headline line even if the secondary metric fails
+            train = {"error": f"{type(exc).__name__}: {exc}"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -334,6 +420,7 @@ def run_ours(args):
                 "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps},
         "gpu_launches": int(launches) * steps, "gpu_launches_per_step": int(launches),
         "clocks": clocks.summary(),
+        "train_step": train,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -347,6 +434,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the secondary molecules/s measurement")
     ap.add_argument("--mode", default="tf32x3", choices=["fp32", "tf32x3"],
                     help="fp32: SIMT GEMMs; tf32x3: tcgen05 3xTF32 GEMMs (both meet the 1e-5 parity bar)")
     args = ap.parse_args()

@@ -1,0 +1,64 @@
+"""Data-parallel plumbing for multi-GPU training (new work: the reference is single-process,
+trainer.py:14,38).  Molecules are independent, so the path shards by giving each rank whole
+molecules and needs exactly one collective per step: an all-reduce of the flat fp32 gradient.
+
+    shard_graphs(costs, world)          balanced assignment of graphs to ranks (cost = triplets)
+    FlatGradBucket(params).allreduce()  one NCCL/gloo all-reduce(sum) + divide by world size
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_graphs(costs: Sequence[int], world: int) -> List[List[int]]:
+    """Longest-processing-time greedy partition of graph ids over `world` ranks, balancing the sum
+    of `costs` (per-graph triplet counts: conv cost is ~T, which varies 20x between a 9-atom and a
+    29-atom molecule).  Deterministic; every graph is assigned exactly once; ids ascend per rank."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    order = sorted(range(len(costs)), key=lambda g: (-int(costs[g]), g))
+    loads = [0] * world
+    parts: List[List[int]] = [[] for _ in range(world)]
+    for g in order:
+        r = min(range(world), key=lambda k: (loads[k], k))
+        parts[r].append(g)
+        loads[r] += int(costs[g])
+    return [sorted(p) for p in parts]
+
+
+class FlatGradBucket:
+    """All parameter gradients packed into one contiguous fp32 buffer, so that a training step
+    issues a single all-reduce (4.64 MB at config.json dims)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else "cpu"
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views = []
+        off = 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def pack(self, grads=None):
+        grads = [p.grad for p in self.params] if grads is None else grads
+        for v, g in zip(self.views, grads):
+            if g is None:
+                v.zero_()
+            else:
+                v.copy_(g)
+
+    def allreduce(self, average: bool = True):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            if average:
+                self.flat.div_(dist.get_world_size())
+        return self.flat
+
+    def unpack(self):
+        for p, v in zip(self.params, self.views):
+            p.grad = v

@@ -222,7 +222,7 @@ def train_step_bench(dev, world, rank, steps, warmup, with_cpu):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
     res = {"molecules_per_sec": world * NMOL / (ms * 1e-3), "ms_per_step": ms, "steps": steps,
-           "molecules_per_gpu": NMOL, "loss": float(loss), "N": len(b["x"]), "E": int(b["edge_index"].shape[1])}
+           "molecules_per_gpu": NMOL, "loss": float(loss.detach()), "N": len(b["x"]), "E": int(b["edge_index"].shape[1])}
     if with_cpu and rank == 0:
         from oracle import model as omodel
         ncores = os.cpu_count() or 1

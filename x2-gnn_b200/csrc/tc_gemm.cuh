@@ -4,34 +4,45 @@
 //     x = x_hi + x_lo   (x_hi = rna_tf32(x), x_lo = rna_tf32(x - x_hi))
 //     A.B ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo        (fp32 accumulation in TMEM)
 //
-// Two persistent, warp-specialised kernels (1 CTA / SM, 416 threads):
+// Two persistent, warp-specialised kernels (1 CTA / SM, 800 threads):
 //   warp 0      : TMEM allocation + single-thread tcgen05.mma issue
-//   warps 1..8  : producers -- coalesced 128-bit global loads of fp32 activations, hi/lo split in
+//   warps 1..16 : producers -- coalesced 128-bit global loads of fp32 activations, hi/lo split in
 //                 registers, 128-bit stores into the UMMA canonical SWIZZLE_128B smem layout
 //                 (the split has to touch every element anyway, so LDG->STS replaces TMA here).
 //                 Two producer warps per SM sub-partition and two chunks of loads in flight per
 //                 thread: with one warp per sub-partition the kernel was issue-latency bound
 //                 (ncu: 13.7 cycles per issued instruction, profiles/r1_notes.md).
-//   warps 9..12 : epilogue -- tcgen05.ld of the fp32 accumulator (one output row per thread),
+//   warps 17..24: epilogue -- tcgen05.ld of the fp32 accumulator (one output row per thread),
 //                 transposed through a padded smem tile so that every global store instruction
 //                 writes whole 128-byte lines, bias / accumulate fused
 // synchronised with mbarriers (full/empty smem ring, full/empty double-buffered TMEM).
 //
-//   G1  C[M,N] (+)= A[M,K] . B(K,N) + bias     A streamed (K-major), B = weights, pre-split into a
-//       resident smem image (K-major).  Used for forward (y = x W^T) and dgrad (dx = dy W).
+//   G1  C[M,N] (+)= X[M,K] . B(K,N) + bias.  The WEIGHTS are the MMA's A operand and live in TENSOR
+//       MEMORY for the whole kernel (hi and lo halves, 2 x K columns, loaded once with tcgen05.st);
+//       the streamed activations are the B operand (K-major smem ring).  The accumulator is therefore
+//       C^T (lane = output channel, column = row of the tile): no smem for weights (160 KB ring instead
+//       of a 128 KB weight image + 2 stages; keeping smem <= 192 KB also keeps a 60 KB L1, which LDG
+//       streaming needs -- tools/bw_probe.cu) and the epilogue's stores are coalesced as they come
+//       (32 lanes = 32 consecutive channels of one output row).
 //   G2  P[cta][Dm,N] = sum_{rows of this CTA} Y[row,:]^T X[row,:]   both operands streamed and
 //       MN-major; the accumulator stays in TMEM over the CTA's whole row range (split-K across
 //       CTAs, partial tiles summed in fixed order by k_splitk_reduce => deterministic wgrad).
+//
+// Split precision: the tensor core TRUNCATES fp32 operand bits to tf32 (verified with
+// tools/umma_ts_probe.cu), so the raw fp32 value is fed as the "hi" operand and lo = x - trunc(x).
 #pragma once
 #include "common.cuh"
 
 namespace x2 {
 namespace tc {
 
-constexpr int kThreads = 416;
-constexpr int kProducerThreads = 256;
-constexpr int kEpilogueThreads = 128;
-constexpr int kStageWords = 36;      // padded row pitch (words) of the epilogue transpose tile
+constexpr int kProducerWarps = 16;   // LDG bandwidth of one CTA/SM is capped by its warp count: 8 warps ->
+                                     // 3.8 TB/s, 16 -> 6.0 TB/s whatever the loads in flight (tools/bw_probe.cu)
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kEpilogueWarps = 8;    // two per TMEM lane quarter: 4 warps cap the C-tile writes at ~2 TB/s
+constexpr int kThreads = 32 + kProducerThreads + kEpilogueWarps * 32;   // MMA warp + producers + epilogue
+constexpr int kEpilogueThreads = 256;
+constexpr int kStageWords = 20;      // padded row pitch (words) of the [32][16] epilogue transpose tiles
 constexpr int kTileM = 128;          // rows per tile (UMMA M)
 constexpr int kChunkK = 32;          // fp32 per 128-byte swizzle row
 constexpr int kChunkBytes = kTileM * kChunkK * 4;   // 16 KB: one 128 x 32 fp32 operand chunk
@@ -111,18 +122,53 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// Round-to-nearest (ties away) fp32 -> tf32 as two integer ops.  cvt.rna.tf32.f32 compiles to four
+// instructions per element (add, |x|<inf compare, select, mask); inputs here are finite activations,
+// so the inf/nan guard is dropped: (bits + 2^12) & ~(2^13 - 1).
 __device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
+  return (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32f(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+// hi = the raw bits (the tensor core drops the 13 low mantissa bits itself); lo = x - trunc(x), exact in
+// fp32, of which the tensor core again keeps the top 11 bits (error ~2^-21 |x|).
+__device__ __forceinline__ float lo_part(float x) {
+  return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
 }
 __device__ __forceinline__ void split4(const float4& v, uint4& hi, uint4& lo) {
-  hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
-  // lo is exact in fp32; the tensor core ignores its 13 low mantissa bits (~2^-22 of |x|)
-  lo.x = __float_as_uint(v.x - __uint_as_float(hi.x));
-  lo.y = __float_as_uint(v.y - __uint_as_float(hi.y));
-  lo.z = __float_as_uint(v.z - __uint_as_float(hi.z));
-  lo.w = __float_as_uint(v.w - __uint_as_float(hi.w));
+  hi.x = __float_as_uint(v.x); hi.y = __float_as_uint(v.y); hi.z = __float_as_uint(v.z); hi.w = __float_as_uint(v.w);
+  lo.x = __float_as_uint(lo_part(v.x));
+  lo.y = __float_as_uint(lo_part(v.y));
+  lo.z = __float_as_uint(lo_part(v.z));
+  lo.w = __float_as_uint(lo_part(v.w));
+}
+// D[tmem] (+)= A[tmem] . B[smem desc]  (A operand in tensor memory: lane = row, 32-bit column = k)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
@@ -150,34 +196,17 @@ __host__ __device__ __forceinline__ uint32_t kmajor_off(int r, int c16) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4));
 }
 
-// ------------------------------------------------------------------ weight image
-// Builds the resident B operand of G1: B(k,n) = W[k*sbk + n*sbn] (zero padded to KC*32 x N_pad),
-// split into hi / lo and laid out exactly as the CTA keeps it in smem:
-//   img[half][kc][kmajor_off(n, kk/4)] , half 0 = hi, 1 = lo, each KC * N_pad * 128 bytes.
-__global__ void k_make_bimage(const float* __restrict__ W, int64_t sbk, int64_t sbn, int K, int N,
-                              int KC, int N_pad, uint32_t* __restrict__ img) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int total = KC * N_pad * kChunkK;
-  if (idx >= total) return;
-  const int kc = idx / (N_pad * kChunkK);
-  const int rem = idx - kc * N_pad * kChunkK;
-  const int n = rem / kChunkK, kk = rem - n * kChunkK;
-  const int k = kc * kChunkK + kk;
-  const float v = (k < K && n < N) ? W[(int64_t)k * sbk + (int64_t)n * sbn] : 0.f;
-  const uint32_t hi = to_tf32(v);
-  const uint32_t lo = to_tf32(v - __uint_as_float(hi));
-  const uint32_t off = (uint32_t)kc * N_pad * 128 + kmajor_off(n, kk >> 2) + (kk & 3) * 4;
-  img[off >> 2] = hi;
-  img[((uint32_t)KC * N_pad * 128 + off) >> 2] = lo;
-}
-
 // ------------------------------------------------------------------ G1
+constexpr int kTmemWHi = 256;        // TMEM columns [256, 384): W_hi ; [384, 512): W_lo ; [0, 256): 2 accumulators
+constexpr int kTmemWLo = 384;
+
 struct G1Params {
-  const float* A;
+  const float* A;        // streamed activations X[M, K]
   int64_t lda, M;
-  int K, KC;
-  const uint32_t* bimg;
-  int N, N_pad;
+  int K, KC;             // KC = ceil(K / 32) <= 4
+  const float* W;        // weights: B(k, n) = W[k * sbk + n * sbn]
+  int64_t sbk, sbn;
+  int N;                 // output channels <= 128
   const float* bias;
   float* C;
   int64_t ldc;
@@ -189,11 +218,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int S = p.stages;
-  const uint32_t bhalf = (uint32_t)p.KC * p.N_pad * 128;          // bytes of one B image half
-  uint8_t* sB = smem;                                             // [hi | lo]
-  uint8_t* sA = smem + 2 * bhalf;                                 // S x [hi 16K | lo 16K]
-  float* sT = reinterpret_cast<float*>(sA + (size_t)S * 2 * kChunkBytes);   // 4 x [32][36] transpose tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sT + 4 * 32 * kStageWords);
+  uint8_t* sA = smem;                                             // S x [hi 16K | lo 16K]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)S * 2 * kChunkBytes);
   uint64_t* full = bars;            // [S]   producers -> MMA
   uint64_t* empty = bars + S;       // [S]   MMA -> producers
   uint64_t* tfull = bars + 2 * S;   // [2]   MMA -> epilogue
@@ -202,7 +228,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // ---- one-time setup: barriers, TMEM, resident weight image
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) {
       mbar_init(&full[i], kProducerThreads);
@@ -214,18 +239,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
     }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(p.bimg);
-    uint4* dst = reinterpret_cast<uint4*>(sB);
-    const int n16 = (int)(2 * bhalf / 16);
-    for (int i = threadIdx.x; i < n16; i += kThreads) dst[i] = __ldg(src + i);
-  }
-  fence_proxy_async();
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // ---- weights -> tensor memory (first epilogue warp of each lane quarter): lane = output channel n
+  if (warp > kProducerWarps && warp <= kProducerWarps + 4) {
+    const int q = warp & 3;
+    const int n = q * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int k0 = 0; k0 < p.KC * kChunkK; k0 += 8) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + j;
+        const float w = (n < p.N && k < p.K) ? __ldg(p.W + (int64_t)k * p.sbk + (int64_t)n * p.sbn) : 0.f;
+        hi[j] = __float_as_uint(w);
+        lo[j] = __float_as_uint(lo_part(w));
+      }
+      tmem_st8(trow + kTmemWHi + k0, hi);
+      tmem_st8(trow + kTmemWLo + k0, lo);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   const int64_t ntiles = (p.M + kTileM - 1) / kTileM;
   const int KC = p.KC;
@@ -233,65 +274,70 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
   if (warp == 0) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.N_pad, 0, 0);
-      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-      uint32_t it = 0;       // global chunk counter (ring position)
-      uint32_t tcount = 0;   // tile counter (TMEM buffer)
+      const uint32_t idesc = make_idesc(kTileM, 0, 0);     // M = 128 channels, N = 128 rows of the tile
+      const uint32_t sA_u = smem_u32(sA);
+      uint32_t st = 0, ph = 0;   // smem ring position / phase
+      uint32_t tcount = 0;       // tile counter (TMEM accumulator buffer)
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
         const uint32_t buf = tcount & 1;
         mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + buf * 128;
-        for (int kc = 0; kc < KC; ++kc, ++it) {
-          const uint32_t st = it % S, ph = (it / S) & 1;
+        for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(&full[st], ph);
           tc_fence_after();
           const int kvalid = min(kChunkK, p.K - kc * kChunkK);
           const int ksteps = (kvalid + 7) >> 3;
-          const uint64_t dah = make_desc(sA_u + st * 2 * kChunkBytes, 16, 1024);
-          const uint64_t dal = make_desc(sA_u + st * 2 * kChunkBytes + kChunkBytes, 16, 1024);
-          const uint64_t dbh = make_desc(sB_u + (uint32_t)kc * p.N_pad * 128, 16, 1024);
-          const uint64_t dbl = make_desc(sB_u + (uint32_t)kc * p.N_pad * 128 + bhalf, 16, 1024);
+          const uint64_t dxh = make_desc(sA_u + st * 2 * kChunkBytes, 16, 1024);
+          const uint64_t dxl = make_desc(sA_u + st * 2 * kChunkBytes + kChunkBytes, 16, 1024);
+          const uint32_t w_hi = tmem_base + kTmemWHi + kc * kChunkK, w_lo = tmem_base + kTmemWLo + kc * kChunkK;
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint64_t adv = (uint64_t)(ks * 2);      // +32 bytes (>>4) along K inside the swizzle row
-            umma_tf32(taddr, dah + adv, dbh + adv, idesc, (kc | ks) != 0);
-            umma_tf32(taddr, dal + adv, dbh + adv, idesc, 1);
-            umma_tf32(taddr, dah + adv, dbl + adv, idesc, 1);
+            umma_tf32_ts(taddr, w_hi + ks * 8, dxh + adv, idesc, (kc | ks) != 0);
+            umma_tf32_ts(taddr, w_lo + ks * 8, dxh + adv, idesc, 1);
+            umma_tf32_ts(taddr, w_hi + ks * 8, dxl + adv, idesc, 1);
           }
           umma_commit(&empty[st]);          // smem slot reusable once these MMAs retire
+          if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
         }
         umma_commit(&tfull[buf]);           // accumulator complete
       }
     }
-  } else if (warp <= 8) {
+  } else if (warp <= kProducerWarps) {
     // =============================== producers ===============================
-    // 256 threads; thread (c16, r0) moves the 16-byte column chunk c16 of rows r0 + 32 i.  Two
-    // chunks of global loads are in flight per thread (register double buffering).
-    const int pt = threadIdx.x - 32;                 // 0..255
+    // 512 threads; thread (c16, r0) moves the 16-byte column chunk c16 of rows r0 + 64 i.
+    const int pt = threadIdx.x - 32;                 // 0..511
     const int c16 = pt & 7, r0 = pt >> 3;            // 8 threads cover one 128-byte row segment
     const bool vec = ((p.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
     const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t nchunk = my_tiles * KC;
     const uint32_t sA_u = smem_u32(sA);
     const float* const a_thr = p.A + (int64_t)r0 * p.lda + c16 * 4;
-    const int64_t row_step = 32 * p.lda;
-    uint32_t soff[4];
+    constexpr int NV = kTileM * 8 / kProducerThreads;   // float4 per thread per chunk (2)
+    constexpr int RS = kProducerThreads / 8;            // row stride between a thread's loads (64)
+    const int64_t row_step = (int64_t)RS * p.lda;
+    uint32_t soff[NV];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) soff[i] = kmajor_off(r0 + 32 * i, c16);
+    for (int i = 0; i < NV; ++i) soff[i] = kmajor_off(r0 + RS * i, c16);
 
-    auto issue = [&](float4 (&v)[4], int64_t it) {
-      const int64_t m0 = (blockIdx.x + (it / KC) * gridDim.x) * kTileM;
-      const int kc0 = (int)(it % KC) * kChunkK;
+    // load cursor (tile row offset, K chunk) and ring cursor advance incrementally: no div/mod
+    int64_t ld_m0 = (int64_t)blockIdx.x * kTileM;
+    int ld_kc = 0;
+    const int64_t m_step = (int64_t)gridDim.x * kTileM;
+    auto issue = [&](float4 (&v)[NV]) {
+      const int64_t m0 = ld_m0;
+      const int kc0 = ld_kc * kChunkK;
+      if (++ld_kc == KC) { ld_kc = 0; ld_m0 += m_step; }
       const float* src = a_thr + m0 * p.lda + kc0;
       if (vec && m0 + kTileM <= p.M && kc0 + kChunkK <= p.K) {       // interior chunk: no guards
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(src + i * row_step));
+        for (int i = 0; i < NV; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(src + i * row_step));
       } else {
         const int kcol = kc0 + c16 * 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NV; ++i) {
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m0 + r0 + 32 * i < p.M) {
+          if (m0 + r0 + RS * i < p.M) {
             const float* q = src + i * row_step;
             if (vec && kcol + 3 < p.K) v[i] = __ldg(reinterpret_cast<const float4*>(q));
             else {
@@ -304,12 +350,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
         }
       }
     };
-    auto commit = [&](const float4 (&v)[4], int64_t it) {
-      const uint32_t st = (uint32_t)(it % S), ph = (uint32_t)((it / S) & 1);
+    uint32_t st = 0, ph = 0;
+    auto commit = [&](const float4 (&v)[NV]) {
       mbar_wait(&empty[st], ph ^ 1);
       const uint32_t base = sA_u + st * 2 * kChunkBytes;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < NV; ++i) {
         uint4 hi, lo;
         split4(v[i], hi, lo);
         sts128(base + soff[i], hi);
@@ -317,83 +363,66 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
       }
       fence_proxy_async();
       mbar_arrive(&full[st]);
+      if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
     };
 
-    float4 va[4], vb[4];
-    if (nchunk > 0) issue(va, 0);
-    for (int64_t it = 0; it < nchunk; it += 2) {
-      if (it + 1 < nchunk) issue(vb, it + 1);
-      commit(va, it);
+    // three chunks of loads in flight per thread
+    float4 va[NV], vb[NV], vc[NV];
+    if (nchunk > 0) issue(va);
+    if (nchunk > 1) issue(vb);
+    for (int64_t it = 0; it < nchunk; it += 3) {
+      if (it + 2 < nchunk) issue(vc);
+      commit(va);
       if (it + 1 < nchunk) {
-        if (it + 2 < nchunk) issue(va, it + 2);
-        commit(vb, it + 1);
+        if (it + 3 < nchunk) issue(va);
+        commit(vb);
+      }
+      if (it + 2 < nchunk) {
+        if (it + 4 < nchunk) issue(vb);
+        commit(vc);
       }
     }
   } else {
     // =============================== epilogue ===============================
+    // The accumulator is C^T: lane = output channel n = 32 q + lane, column = row of the tile.  Warp
+    // (q, half) stores the 16-column blocks c0 = 16 half + 32 j: for each column the 32 lanes write 32
+    // consecutive floats of one output row (one 128-byte line per store instruction).
+    const int ew = warp - (1 + kProducerWarps);      // 0..7
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
-    float* tile_s = sT + q * 32 * kStageWords;       // this warp's [32][36] transpose tile
-    const bool vecC = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.N & 3) == 0);
-    const int rr = lane >> 3, cc = (lane & 7) * 4;   // read-back mapping: 4 rows x 8 float4 per pass
+    const int half = ew >> 2;
+    const int n = q * 32 + lane;
+    const bool nvalid = n < p.N;
+    const float bv = (p.bias && nvalid) ? __ldg(p.bias + n) : 0.f;
     uint32_t tcount = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const uint32_t buf = tcount & 1;
       mbar_wait(&tfull[buf], (tcount >> 1) & 1);
       tc_fence_after();
-      const int64_t row0 = tile * kTileM + q * 32;
+      const int64_t row0 = tile * kTileM;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128;
-      for (int c0 = 0; c0 < p.N_pad; c0 += 32) {
-        // thread = accumulator row: 32 (or 16) columns -> padded smem tile
+      for (int c0 = half * 16; c0 < kTileM; c0 += 32) {
         float v[16];
         tmem_ld16(taddr + c0, v);
+        if (nvalid) {
+          float* dst = p.C + (row0 + c0) * p.ldc + n;
+          if (row0 + c0 + 16 <= p.M) {
+            if (p.beta) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4*>(tile_s + lane * kStageWords + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        if (c0 + 16 < p.N_pad) {
-          tmem_ld16(taddr + c0 + 16, v);
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(tile_s + lane * kStageWords + 16 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-        __syncwarp();
-        if (vecC) {
-          // each store instruction writes 4 rows x 128 contiguous bytes
-          const int col = c0 + cc;
-          if (col < p.N) {
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-#pragma unroll
-            for (int pass = 0; pass < 8; ++pass) {
-              const int r = pass * 4 + rr;
-              const int64_t row = row0 + r;
-              if (row < p.M) {
-                float4 o = *reinterpret_cast<const float4*>(tile_s + r * kStageWords + cc);
-                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-                float* dst = p.C + row * p.ldc + col;
-                if (p.beta) {
-                  const float4 old = *reinterpret_cast<const float4*>(dst);
-                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                }
-                *reinterpret_cast<float4*>(dst) = o;
-              }
+              for (int j = 0; j < 16; ++j) v[j] += dst[(int64_t)j * p.ldc];
             }
-          }
-        } else {
-          const int col = c0 + lane;
-          if (col < p.N) {
-            const float bv = p.bias ? __ldg(p.bias + col) : 0.f;
-            for (int r = 0; r < 32; ++r) {
-              const int64_t row = row0 + r;
-              if (row < p.M) {
-                float o = tile_s[r * kStageWords + lane] + bv;
-                float* dst = p.C + row * p.ldc + col;
-                if (p.beta) o += *dst;
-                *dst = o;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dst[(int64_t)j * p.ldc] = v[j] + bv;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (row0 + c0 + j < p.M) {
+                float o = v[j] + bv;
+                if (p.beta) o += dst[(int64_t)j * p.ldc];
+                dst[(int64_t)j * p.ldc] = o;
               }
             }
           }
         }
-        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(&tempty[buf]);
@@ -404,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
   __syncthreads();
   if (warp == 0) {
     __syncwarp();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -443,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
   uint64_t* empty = bars + S;
   uint64_t* tfull = bars + 2 * S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
-  float* cs_smem = reinterpret_cast<float*>(bars + 2 * S + 2);   // [8][128] column-sum staging
+  float* cs_smem = reinterpret_cast<float*>(bars + 2 * S + 2);   // [16][128] column-sum staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -468,8 +497,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
     if (lane == 0 && nchunks > 0) {
       const uint32_t idesc = make_idesc(p.N_pad, 1, 1);
       const uint32_t s_u = smem_u32(sS);
+      uint32_t st = 0, ph = 0;
       for (int64_t c = 0; c < nchunks; ++c) {
-        const uint32_t st = (uint32_t)(c % S), ph = (uint32_t)((c / S) & 1);
         mbar_wait(&full[st], ph);
         tc_fence_after();
         const uint32_t y_hi = s_u + st * stage_bytes, y_lo = y_hi + kChunkBytes;
@@ -487,12 +516,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
           umma_tf32(tmem_base, dyh + adv, dxl + adv, idesc, 1);
         }
         umma_commit(&empty[st]);
+        if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
       }
       umma_commit(tfull);
     }
-  } else if (warp <= 8) {
-    // 256 producer threads.  Y chunk = 32 rows x 32 float4: thread owns float4 column yc of rows
-    // yr + 8 i.  X chunk = 32 rows x xq float4, flattened (up to 4 per thread).  Two chunks of loads
+  } else if (warp <= kProducerWarps) {
+    // 512 producer threads.  Y chunk = 32 rows x 32 float4: thread owns float4 column yc of rows
+    // yr + 16 i.  X chunk = 32 rows x xq float4, flattened (up to 2 per thread).  Two chunks of loads
     // in flight per thread.
     const int pt = threadIdx.x - 32;
     const int yc = pt & 31, yr = pt >> 5;
@@ -502,13 +532,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
     const int nx = kChunkK * xq;                     // float4 per X chunk (256..1024)
     float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
     const uint32_t s_u = smem_u32(sS);
+    constexpr int NV = kChunkK * 32 / kProducerThreads;   // float4 per thread per operand chunk (2)
+    constexpr int RS = kProducerThreads / 32;             // row stride between a thread's Y loads (16)
     const float* const y_thr = p.Y + (int64_t)yr * p.ldy + yc * 4;
-    const int64_t y_step = 8 * p.ldy;
-    uint32_t yoff[4], xoff[4];
-    int xr[4], xcol[4];
+    const int64_t y_step = (int64_t)RS * p.ldy;
+    uint32_t yoff[NV], xoff[NV];
+    int xr[NV], xcol[NV];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      yoff[i] = mnmajor_off(yr + 8 * i, yc);
+    for (int i = 0; i < NV; ++i) {
+      yoff[i] = mnmajor_off(yr + RS * i, yc);
       const int f = pt + i * kProducerThreads;
       xr[i] = f / xq;
       const int xc = f - xr[i] * xq;
@@ -516,18 +548,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
       xoff[i] = mnmajor_off(xr[i] & 31, xc);
     }
 
-    auto issue = [&](float4 (&vy)[4], float4 (&vx)[4], int64_t c) {
+    auto issue = [&](float4 (&vy)[NV], float4 (&vx)[NV], int64_t c) {
       const int64_t row0 = rbeg + c * kChunkK;
       const bool interior = row0 + kChunkK <= rend;
       const float* ysrc = y_thr + row0 * p.ldy;
       if (interior && vecY) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) vy[i] = __ldg(reinterpret_cast<const float4*>(ysrc + i * y_step));
+        for (int i = 0; i < NV; ++i) vy[i] = __ldg(reinterpret_cast<const float4*>(ysrc + i * y_step));
       } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NV; ++i) {
           vy[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row0 + yr + 8 * i < rend) {
+          if (row0 + yr + RS * i < rend) {
             const float* q = ysrc + i * y_step;
             if (vecY) vy[i] = __ldg(reinterpret_cast<const float4*>(q));
             else { vy[i].x = __ldg(q); vy[i].y = __ldg(q + 1); vy[i].z = __ldg(q + 2); vy[i].w = __ldg(q + 3); }
@@ -535,7 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
         }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < NV; ++i) {
         vx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (pt + i * kProducerThreads < nx) {
           const int64_t row = row0 + xr[i];
@@ -552,12 +584,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
         }
       }
     };
-    auto commit = [&](const float4 (&vy)[4], const float4 (&vx)[4], int64_t c) {
-      const uint32_t st = (uint32_t)(c % S), ph = (uint32_t)((c / S) & 1);
+    uint32_t st = 0, ph = 0;
+    auto commit = [&](const float4 (&vy)[NV], const float4 (&vx)[NV]) {
       mbar_wait(&empty[st], ph ^ 1);
       const uint32_t base = s_u + st * stage_bytes;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < NV; ++i) {
         cs0 += vy[i].x; cs1 += vy[i].y; cs2 += vy[i].z; cs3 += vy[i].w;   // fixed order per thread
         uint4 hi, lo;
         split4(vy[i], hi, lo);
@@ -566,7 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
       }
       const uint32_t xb = base + 2 * kChunkBytes;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < NV; ++i) {
         if (pt + i * kProducerThreads < nx) {
           uint4 hi, lo;
           split4(vx[i], hi, lo);
@@ -576,33 +608,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
       }
       fence_proxy_async();
       mbar_arrive(&full[st]);
+      if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
     };
 
-    float4 ya[4], xa[4], yb[4], xb_[4];
+    float4 ya[NV], xa[NV], yb[NV], xb_[NV];
     if (nchunks > 0) issue(ya, xa, 0);
     for (int64_t c = 0; c < nchunks; c += 2) {
       if (c + 1 < nchunks) issue(yb, xb_, c + 1);
-      commit(ya, xa, c);
+      commit(ya, xa);
       if (c + 1 < nchunks) {
         if (c + 2 < nchunks) issue(ya, xa, c + 2);
-        commit(yb, xb_, c + 1);
+        commit(yb, xb_);
       }
     }
-    // column sums of Y over this CTA's rows: combine the 8 row-phase threads in fixed order
+    // column sums of Y over this CTA's rows: combine the 16 row-phase threads in fixed order
     if (p.colsum) {
       cs_smem[yr * 128 + yc * 4 + 0] = cs0;
       cs_smem[yr * 128 + yc * 4 + 1] = cs1;
       cs_smem[yr * 128 + yc * 4 + 2] = cs2;
       cs_smem[yr * 128 + yc * 4 + 3] = cs3;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
       if (pt < 128) {
         float s = 0.f;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) s += cs_smem[g * 128 + pt];
+        for (int g = 0; g < RS; ++g) s += cs_smem[g * 128 + pt];
         p.colsum[(int64_t)blockIdx.x * 128 + pt] = s;
       }
     }
-  } else {
+  } else if (warp <= kProducerWarps + 4) {
     const int q = warp & 3;
     const int m = q * 32 + lane;
     float* dst = p.partial + ((int64_t)blockIdx.x * 128 + m) * p.N;
@@ -632,34 +665,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
 // ------------------------------------------------------------------ host launchers
 static inline int ceil_to(int v, int m) { return (v + m - 1) / m * m; }
 
-// bytes of workspace for one weight image (hi + lo)
-static inline size_t bimage_bytes(int K, int N) {
-  const int KC = (K + kChunkK - 1) / kChunkK, N_pad = ceil_to(N, 16);
-  return align_up((size_t)2 * KC * N_pad * 128, 256);
-}
+// kept for ABI compatibility of the workspace queries: the weights now live in tensor memory
+static inline size_t bimage_bytes(int K, int N) { (void)K; (void)N; return 256; }
 
-constexpr size_t kEpiBytes = 4 * 32 * kStageWords * sizeof(float);   // epilogue transpose tiles
+static inline bool g1_supported(int K, int N) { return K >= 1 && K <= 128 && N >= 1 && N <= 128; }
 
-static inline bool g1_supported(int K, int N) {
-  if (K < 1 || N < 1 || N > 128) return false;
-  const int KC = (K + kChunkK - 1) / kChunkK, N_pad = ceil_to(N, 16);
-  const size_t b = (size_t)2 * KC * N_pad * 128;
-  return b + 2 * (size_t)2 * kChunkBytes + kEpiBytes + 2048 <= (size_t)kMaxSmem;
-}
-
-// C[M,N] (+)= A[M,K] . B(K,N) + bias, B(k,n) = W[k*sbk + n*sbn].  img: scratch for the weight image.
+// C[M,N] (+)= A[M,K] . B(K,N) + bias, B(k,n) = W[k*sbk + n*sbn].
 static int tc_gemm(const float* A, int64_t lda, int64_t M, int K, const float* W, int64_t sbk, int64_t sbn,
                    int N, const float* bias, float* C, int64_t ldc, int beta, void* img, cudaStream_t st) {
+  (void)img;
   if (M <= 0) return X2_OK;
   if (!g1_supported(K, N)) { set_error("tc_gemm: unsupported K=%d N=%d", K, N); return X2_EINVAL; }
-  const int KC = (K + kChunkK - 1) / kChunkK, N_pad = ceil_to(N, 16);
-  const int total = KC * N_pad * kChunkK;
-  k_make_bimage<<<(total + 255) / 256, 256, 0, st>>>(W, sbk, sbn, K, N, KC, N_pad, static_cast<uint32_t*>(img));
-  X2_LAUNCH_OK();
-  const size_t bbytes = (size_t)2 * KC * N_pad * 128;
-  int stages = (int)(((size_t)kMaxSmem - bbytes - kEpiBytes - 2048) / (2 * kChunkBytes));
-  if (stages > 4) stages = 4;
-  const size_t smem = 1024 + bbytes + (size_t)stages * 2 * kChunkBytes + kEpiBytes + 256;
+  const int KC = (K + kChunkK - 1) / kChunkK;
+  const int stages = 5;                                   // 5 x 32 KB = 160 KB: stays under the 196 KB carve-out
+  const size_t smem = 1024 + (size_t)stages * 2 * kChunkBytes + 256;
   static bool attr_set = false;
   if (!attr_set) {
     X2_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -667,8 +686,8 @@ static int tc_gemm(const float* A, int64_t lda, int64_t M, int K, const float* W
   }
   G1Params p;
   p.A = A; p.lda = lda; p.M = M; p.K = K; p.KC = KC;
-  p.bimg = static_cast<const uint32_t*>(img);
-  p.N = N; p.N_pad = N_pad; p.bias = bias; p.C = C; p.ldc = ldc; p.beta = beta; p.stages = stages;
+  p.W = W; p.sbk = sbk; p.sbn = sbn;
+  p.N = N; p.bias = bias; p.C = C; p.ldc = ldc; p.beta = beta; p.stages = stages;
   const int64_t ntiles = cdiv(M, kTileM);
   const int grid = (int)(ntiles < kNumSM ? ntiles : kNumSM);
   k_tc_gemm<<<grid, kThreads, smem, st>>>(p);
@@ -703,9 +722,10 @@ static int tc_wgrad(const float* Y, int64_t ldy, const float* X, int64_t ldx, in
   const int grid = wgrad_ctas(rows);
   const int64_t rpc = cdiv(cdiv(rows > 0 ? rows : 1, grid), kChunkK) * kChunkK;
   const uint32_t stage_bytes = 2 * kChunkBytes + 2 * (uint32_t)(N_pad / 32) * 4096;
-  int stages = (int)(((size_t)kMaxSmem - 8192 - 2048) / stage_bytes);
+  int stages = (int)(((size_t)196608 - 12288 - 4096) / stage_bytes);   // <= 192 KB: keeps a 60 KB L1 for the LDG stream
   if (stages > 4) stages = 4;
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + 256 + 8 * 128 * sizeof(float);
+  if (stages < 2) stages = 2;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + 256 + (kProducerThreads / 32) * 128 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     X2_CUDA_OK(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));

@@ -165,6 +165,8 @@ typedef struct {
   int32_t fuse_skip;   /* 1: out = attn + lin_skip(x) (concat, root_weight, no beta) */
   int32_t mode;        /* X2_MODE_* */
   float dropout_p;     /* attention dropout (training); 0 disables */
+  int32_t tgt_sorted;  /* 1 iff edge_index[1] is non-decreasing (order_tgt is the identity): enables the fused
+                          forward kernel; x2_meta_build reports it in flags[0] */
   uint64_t seed;       /* dropout RNG seed */
   /* inputs */
   const float *x, *rbf, *sbf, *edge_attr;
@@ -183,6 +185,9 @@ typedef struct {
 #define X2_MODE_FP32 0    /* fp32 SIMT arithmetic everywhere (1e-5 parity) */
 #define X2_MODE_TF32X3 1  /* Linear layers on tcgen05 tensor cores in 3xTF32 split precision (fp32-accurate,
                              1e-5 parity); needs D % 128 == 0.  Attention arithmetic stays fp32 SIMT. */
+#define X2_MODE_TF32X3_FUSED 2  /* experimental: as TF32X3, with lin_edge / lin_sbf and the forward attention
+                                   fused into one tcgen05 kernel (csrc/fused_fwd.cuh) when edge_index is
+                                   target-sorted, D == 128, A <= 128, S <= 64, no dropout / alpha request */
 
 /* Tensors written by fwd and consumed by bwd (caller-owned, kept alive by autograd). */
 typedef struct {

@@ -32,7 +32,7 @@ class ConvDesc(C.Structure):
         ("D", C.c_int32), ("H", C.c_int32), ("C", C.c_int32), ("S", C.c_int32),
         ("R", C.c_int32), ("A", C.c_int32),
         ("fuse_skip", C.c_int32), ("mode", C.c_int32),
-        ("dropout_p", C.c_float), ("seed", C.c_uint64),
+        ("dropout_p", C.c_float), ("tgt_sorted", C.c_int32), ("seed", C.c_uint64),
         ("x", c_f32p), ("rbf", c_f32p), ("sbf", c_f32p), ("edge_attr", c_f32p),
         ("src", c_i32p), ("tgt", c_i32p), ("rowptr_tgt", c_i32p), ("order_tgt", c_i32p),
         ("rowptr_src", c_i32p), ("order_src", c_i32p),

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "tc_gemm.cuh"
+#include "fused_fwd.cuh"
 
 namespace x2 {
 
@@ -67,17 +68,32 @@ __device__ __forceinline__ float keep_scale(uint64_t seed, int64_t t, int h, int
 
 // ------------------------------------------------------------------ rbf filter
 // xs[e,:] = x[e,:] * (rbf[e,:] . W_r^T)   (sbftransformer_conv.py:99-100); optionally also F.
-__global__ void k_rbf_filter(const float* __restrict__ x, const float* __restrict__ rbf,
-                             const float* __restrict__ w_rbf, int64_t E, int D, int R,
-                             float* __restrict__ xs, float* __restrict__ F) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= E * D) return;
-  const int64_t e = idx / D;
-  const int d = (int)(idx - e * D);
-  float f = 0.f;
-  for (int r = 0; r < R; ++r) f = fmaf(rbf[e * R + r], __ldg(w_rbf + d * R + r), f);
-  xs[idx] = x[idx] * f;
-  if (F) F[idx] = f;
+// One warp per row e: lane r holds rbf[e,r] (broadcast by shuffle), every lane produces 4 consecutive
+// channels per step from a shared-memory copy of W_r; x / xs / F move as 128-bit accesses.
+constexpr int kFilterRows = 8;   // rows (warps) per block
+__global__ void __launch_bounds__(kFilterRows * 32)
+k_rbf_filter(const float* __restrict__ x, const float* __restrict__ rbf, const float* __restrict__ w_rbf,
+             int64_t E, int D, int R, float* __restrict__ xs, float* __restrict__ F) {
+  extern __shared__ float s_w[];                   // [D][R]
+  for (int i = threadIdx.x; i < D * R; i += blockDim.x) s_w[i] = w_rbf[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * kFilterRows + (threadIdx.x >> 5);
+  if (e >= E) return;
+  float rv[2];                                     // R <= 64: lane holds rbf[e, lane] and rbf[e, lane + 32]
+  rv[0] = lane < R ? rbf[e * R + lane] : 0.f;
+  rv[1] = lane + 32 < R ? rbf[e * R + lane + 32] : 0.f;
+  for (int d0 = lane * 4; d0 < D; d0 += 128) {
+    float f[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < R; ++r) {
+      const float b = __shfl_sync(0xffffffffu, rv[r >> 5], r & 31);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f[j] = fmaf(b, s_w[(d0 + j) * R + r], f[j]);
+    }
+    const float4 xv = *reinterpret_cast<const float4*>(x + e * D + d0);
+    *reinterpret_cast<float4*>(xs + e * D + d0) = make_float4(xv.x * f[0], xv.y * f[1], xv.z * f[2], xv.w * f[3]);
+    if (F) *reinterpret_cast<float4*>(F + e * D + d0) = make_float4(f[0], f[1], f[2], f[3]);
+  }
 }
 
 // dx += dxs * F ; dF = dxs * x (written over dxs)       (App. A last line)
@@ -322,6 +338,8 @@ k_attn_bwd_src(const float* __restrict__ qkvs, int ldq, const float* __restrict_
 }
 
 // ------------------------------------------------------------------ Linear dispatch (SIMT / tensor core)
+static inline int lin_mode(int mode) { return mode == X2_MODE_TF32X3_FUSED ? X2_MODE_TF32X3 : mode; }
+
 struct Lin {
   int mode;          // X2_MODE_FP32: SIMT fp32;  X2_MODE_TF32X3: tcgen05 3xTF32
   void* img;         // weight-image scratch (tensor-core mode)
@@ -379,8 +397,9 @@ static int lin_wgrad(const Lin& L, const float* dy, int64_t lddy, const float* x
 static int check_desc(const x2_conv_desc* d) {
   X2_CHECK_ARG(d != nullptr, "conv: null descriptor");
   X2_CHECK_ARG(d->E >= 0 && d->T >= 0 && d->E < 2147483647LL && d->T < 2147483647LL, "conv: bad E/T");
-  X2_CHECK_ARG(d->mode == X2_MODE_FP32 || d->mode == X2_MODE_TF32X3, "conv: unknown mode %d", d->mode);
-  X2_CHECK_ARG(d->mode != X2_MODE_TF32X3 || d->D % 128 == 0,
+  X2_CHECK_ARG(d->mode == X2_MODE_FP32 || d->mode == X2_MODE_TF32X3 || d->mode == X2_MODE_TF32X3_FUSED,
+               "conv: unknown mode %d", d->mode);
+  X2_CHECK_ARG(d->mode == X2_MODE_FP32 || d->D % 128 == 0,
                "conv: X2_MODE_TF32X3 needs heads*out_channels to be a multiple of 128 (got %d)", d->D);
   X2_CHECK_ARG(d->D == d->H * d->C && d->H >= 1 && d->C >= 1, "conv: D=%d != H*C=%d*%d", d->D, d->H, d->C);
   X2_CHECK_ARG(d->D == 32 || d->D == 64 || d->D == 128 || d->D == 256,
@@ -389,17 +408,18 @@ static int check_desc(const x2_conv_desc* d) {
   X2_CHECK_ARG(d->C % vec == 0 && ((d->C / vec) & (d->C / vec - 1)) == 0 && d->C / vec <= 32,
                "conv: out_channels=%d unsupported for D=%d (need C %% (D/32) == 0 and C/(D/32) a power of two)",
                d->C, d->D);
-  X2_CHECK_ARG(d->S >= 1 && d->R >= 1 && d->A >= 0, "conv: bad S/R/A");
+  X2_CHECK_ARG(d->S >= 1 && d->R >= 1 && d->R <= 64 && d->A >= 0, "conv: bad S/R/A (need 1 <= R <= 64)");
   X2_CHECK_ARG(d->dropout_p >= 0.f && d->dropout_p < 1.f, "conv: dropout must be in [0,1)");
   X2_CHECK_ARG((d->A > 0) == (d->w_edge != nullptr), "conv: w_edge must be given iff A > 0");
   return X2_OK;
 }
 
-struct FwdWs { float* xs; void* img; };
+struct FwdWs { float* xs; void* img; void* fused; };
 static size_t fwd_layout(const x2_conv_desc* d, void* ws, FwdWs* w) {
   Arena a(ws, (size_t)-1);
   w->xs = a.take<float>((size_t)d->E * d->D + 4);
   w->img = a.take<char>(tc::bimage_bytes(kTcBlock, kTcBlock) + 256);
+  w->fused = a.take<char>(tc::fused_fwd_workspace_bytes(d->T));
   return align_up(a.off, 256) + 256;
 }
 
@@ -529,11 +549,12 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
 
   phase_begin(st);
   // (1) x_src = x * lin_rbf(rbf)                                             :99-100
-  k_rbf_filter<<<(unsigned)cdiv(E * D, 256), 256, 0, st>>>(d->x, d->rbf, d->w_rbf, E, D, d->R, w.xs, nullptr);
+  k_rbf_filter<<<(unsigned)cdiv(E, kFilterRows), kFilterRows * 32, (size_t)D * d->R * sizeof(float), st>>>(
+      d->x, d->rbf, d->w_rbf, E, D, d->R, w.xs, nullptr);
   X2_LAUNCH_OK();
-  const Lin L{d->mode, w.img, nullptr, st};
+  const Lin L{lin_mode(d->mode), w.img, nullptr, st};
   // (2) Q | K | V | skip                                                     :105-107, :121
-  if (d->mode == X2_MODE_TF32X3) {
+  if (L.mode == X2_MODE_TF32X3) {
     X2_TRY(lin_fwd(L, d->x, D, d->w_q, D, d->b_q, s->qkvs, 4 * D, E, D, D));
     X2_TRY(lin_fwd(L, w.xs, D, d->w_k, D, d->b_k, s->qkvs + D, 4 * D, E, D, D));
     X2_TRY(lin_fwd(L, w.xs, D, d->w_v, D, d->b_v, s->qkvs + 2 * D, 4 * D, E, D, D));
@@ -551,6 +572,28 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
     X2_TRY((launch_gemm<true, true>(p, nb, E, D, D, D, D, 4 * D, 0, st)));
   }
   phase_end(X2_PHASE_NODE_PROJ, st);
+  // (3+4 fused) tensor-core projections + segmented attention in one kernel, when the triplet list is
+  // target-sorted (what vertex_to_edge_2 produces): edge_attr / sbf are streamed once, EA / Sg stay in
+  // tensor memory for the forward result.
+  // EXPERIMENTAL, opt-in (X2_MODE_TF32X3_FUSED): correct (same parity tests) but ~2x slower than the
+  // unfused pair today -- with lane = channel the four epilogue warps of a stream each execute the whole
+  // per-triplet instruction sequence (profiles/r1_notes.md).
+  if (d->mode == X2_MODE_TF32X3_FUSED && d->tgt_sorted && T > 0 && d->dropout_p == 0.f && alpha == nullptr &&
+      tc::fused_fwd_supported(D, d->H, d->C, d->A, d->S)) {
+    tc::F1Params f{};
+    f.ea = d->edge_attr; f.ld_ea = d->A; f.A = d->A;
+    f.sbf = d->sbf; f.ld_s = d->S; f.S = d->S;
+    f.w_edge = d->w_edge; f.b_sbf = d->b_sbf;
+    f.qkvs = s->qkvs; f.ldq = 4 * D;
+    f.src = d->src; f.tgt = d->tgt; f.rowptr = d->rowptr_tgt;
+    f.E = E; f.T = T; f.H = d->H; f.C = d->C; f.scale = 1.0f / sqrtf((float)d->C); f.fuse_skip = d->fuse_skip;
+    f.out = out; f.attn = s->attn; f.lse = s->lse;
+    f.ea_out = s->ea; f.sg_out = s->sg;        // still consumed by the backward kernels
+    phase_end(X2_PHASE_TROW_PROJ, st);
+    X2_TRY(tc::fused_fwd(f, d->w_sbf, w.fused, st));
+    phase_end(X2_PHASE_ATTN_FWD, st);
+    return X2_OK;
+  }
   // (3) T-row projections                                                    :144, :148
   if (T > 0) {
     if (d->A > 0) X2_TRY(lin_fwd(L, d->edge_attr, d->A, d->w_edge, d->A, nullptr, s->ea, D, T, D, d->A));
@@ -606,7 +649,7 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
   const float* dk = w.dqkv + D;
   const float* dv = w.dqkv + 2 * D;
 
-  const Lin L{d->mode, w.img, w.wg, st};
+  const Lin L{lin_mode(d->mode), w.img, w.wg, st};
   // (3) T-row input gradients
   if (A > 0 && g->dedge_attr && T > 0) X2_TRY(lin_dgrad(L, w.dea, D, d->w_edge, A, g->dedge_attr, A, T, A, D, 0));
   if (g->dsbf && T > 0) X2_TRY(lin_dgrad(L, w.dsg, D, d->w_sbf, S, g->dsbf, S, T, S, D, 0));
@@ -617,7 +660,8 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
 
   phase_end(X2_PHASE_TROW_WGRAD, st);
   // (5) recompute the filtered sources
-  k_rbf_filter<<<(unsigned)cdiv(E * D, 256), 256, 0, st>>>(d->x, d->rbf, d->w_rbf, E, D, R, w.xs, w.F);
+  k_rbf_filter<<<(unsigned)cdiv(E, kFilterRows), kFilterRows * 32, (size_t)D * R * sizeof(float), st>>>(
+      d->x, d->rbf, d->w_rbf, E, D, R, w.xs, w.F);
   X2_LAUNCH_OK();
   // (6) node-level weight gradients
   X2_TRY(lin_wgrad(L, dq, 3 * D, d->x, D, g->dw_q, D, g->db_q, E, D, D));

@@ -245,34 +245,46 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // ---- weights -> tensor memory (first epilogue warp of each lane quarter): lane = output channel n
+  // ---- weights -> tensor memory (first epilogue warp of each lane quarter): lane = output channel n.
+  // Loads are issued 32 at a time (a serial chain of 128 dependent loads cost ~10 us per launch); only the
+  // MMA warp waits for the weights (named barrier 2), the producers start streaming immediately.
   if (warp > kProducerWarps && warp <= kProducerWarps + 4) {
     const int q = warp & 3;
     const int n = q * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int k0 = 0; k0 < p.KC * kChunkK; k0 += 8) {
-      uint32_t hi[8], lo[8];
+    const float* __restrict__ wrow = p.W + (int64_t)n * p.sbn;
+    const bool nv = n < p.N;
+    for (int k0 = 0; k0 < p.KC * kChunkK; k0 += 32) {
+      float w[32];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 32; ++j) {
         const int k = k0 + j;
-        const float w = (n < p.N && k < p.K) ? __ldg(p.W + (int64_t)k * p.sbk + (int64_t)n * p.sbn) : 0.f;
-        hi[j] = __float_as_uint(w);
-        lo[j] = __float_as_uint(lo_part(w));
+        w[j] = (nv && k < p.K) ? __ldg(wrow + (int64_t)k * p.sbk) : 0.f;
       }
-      tmem_st8(trow + kTmemWHi + k0, hi);
-      tmem_st8(trow + kTmemWLo + k0, lo);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          hi[j] = __float_as_uint(w[g * 8 + j]);
+          lo[j] = __float_as_uint(lo_part(w[g * 8 + j]));
+        }
+        tmem_st8(trow + kTmemWHi + k0 + g * 8, hi);
+        tmem_st8(trow + kTmemWLo + k0 + g * 8, lo);
+      }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    asm volatile("bar.arrive 2, 160;" ::: "memory");
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
 
   const int64_t ntiles = (p.M + kTileM - 1) / kTileM;
   const int KC = p.KC;
 
   if (warp == 0) {
     // =============================== MMA issuer ===============================
+    asm volatile("bar.sync 2, 160;" ::: "memory");        // weights are in tensor memory
+    tc_fence_after();
     if (lane == 0) {
       const uint32_t idesc = make_idesc(kTileM, 0, 0);     // M = 128 channels, N = 128 rows of the tile
       const uint32_t sA_u = smem_u32(sA);

@@ -22,6 +22,7 @@ from . import _lib, graph_meta
 
 MODE_FP32 = 0      # X2_MODE_FP32: SIMT fp32 everywhere
 MODE_TF32X3 = 1    # X2_MODE_TF32X3: Linear layers on tcgen05 tensor cores, 3xTF32 (fp32-accurate)
+MODE_TF32X3_FUSED = 2   # experimental: + fused tcgen05 projection/attention forward kernel
 
 
 def default_mode(hc: int) -> int:
@@ -31,6 +32,8 @@ def default_mode(hc: int) -> int:
         return MODE_FP32
     if env == "tf32x3":
         return MODE_TF32X3
+    if env == "tf32x3_fused":
+        return MODE_TF32X3_FUSED if hc == 128 else MODE_TF32X3
     return MODE_TF32X3 if hc % 128 == 0 else MODE_FP32
 
 
@@ -73,6 +76,7 @@ class _SBFConvFn(torch.autograd.Function):
         desc.D, desc.H, desc.C, desc.S, desc.R, desc.A = D, H, Cc, S, R, A
         desc.fuse_skip, desc.mode = fuse, cfg["mode"]
         desc.dropout_p, desc.seed = cfg["dropout_p"], cfg["seed"]
+        desc.tgt_sorted = 1 if meta.target_sorted else 0
         for n in ("x", "rbf", "sbf", "w_rbf", "w_q", "b_q", "w_k", "b_k", "w_v", "b_v", "w_sbf", "b_sbf",
                   "w_skip", "b_skip"):
             setattr(desc, n, _lib.ptr(t[n]))
@@ -116,6 +120,7 @@ class _SBFConvFn(torch.autograd.Function):
         desc.D, desc.H, desc.C, desc.S, desc.R, desc.A = D, H, Cc, S, R, A
         desc.fuse_skip, desc.mode = fuse, cfg["mode"]
         desc.dropout_p, desc.seed = cfg["dropout_p"], cfg["seed"]
+        desc.tgt_sorted = 1 if meta.target_sorted else 0
         for n in ("x", "rbf", "sbf", "w_rbf", "w_q", "b_q", "w_k", "b_k", "w_v", "b_v", "w_sbf", "b_sbf",
                   "w_skip", "b_skip"):
             setattr(desc, n, _lib.ptr(t[n]))

@@ -95,3 +95,25 @@ def test_precision_is_fp32_level_not_tf32():
     err = relerr(C, ref)
     fp32 = relerr(A @ W.T, ref) if not torch.backends.cuda.matmul.allow_tf32 else None
     assert err < 2e-6, (err, fp32)
+
+
+@pytest.mark.parametrize("M,K,N", [(1000, 128, 128), (777, 338, 256), (512, 256, 128), (300, 128, 1), (64, 6, 128)])
+def test_tc_linear_module_fwd_bwd(M, K, N):
+    """TCLinear == nn.Linear (fp64) for output, input grad, weight grad, bias grad; state_dict-compatible."""
+    from x2gnn_b200.tc_linear import TCLinear
+    torch.manual_seed(M + N)
+    ref = torch.nn.Linear(K, N).double()
+    lin = TCLinear(K, N)
+    lin.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    lin = lin.cuda()
+    x = torch.randn(M, K)
+    g = torch.randn(M, N)
+    xr = x.double().requires_grad_(True)
+    ref(xr).backward(g.double())
+    xc = x.cuda().requires_grad_(True)
+    y = lin(xc)
+    y.backward(g.cuda())
+    assert relerr(y, ref(xr)) < 2e-6
+    assert relerr(xc.grad, xr.grad) < 2e-6
+    assert relerr(lin.weight.grad, ref.weight.grad) < 6e-6
+    assert relerr(lin.bias.grad, ref.bias.grad) < 6e-6

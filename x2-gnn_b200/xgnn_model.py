@@ -4,12 +4,14 @@ with the reference's module names so a reference checkpoint (`ckpt/U0_ckpt.pth`,
 loads with `load_state_dict` unchanged.  It exists so that U0 predictions and full training
 steps (molecules/s) can be measured on the GPU box, where the reference tree is not present.
 
-Out-of-scope layers (dense MLPs, graph LayerNorm, readout scatter) are plain CUDA PyTorch ops; the
-hot path -- radius/triplet graphs, envelope, radial + 2-D Fourier-Bessel bases, SBFTransformerConv
--- runs on the sm_100a kernels of this package.  Differences from the reference's control flow,
-none of which change results: triplets are built on the GPU (no `.to('cpu')` round trip,
-xgnn.py:52-53), and `num_graphs` is taken from the batch instead of `int(batch.max())` host syncs
-(model.py:46,53).
+The hot path -- radius/triplet graphs, envelope, radial + 2-D Fourier-Bessel bases, SBFTransformerConv
+-- runs on the sm_100a kernels of this package; the dense layers around it use `TCLinear` (the same
+tcgen05 3xTF32 GEMMs behind an nn.Linear); graph LayerNorm and the readout scatter
+are CUDA PyTorch ops.  Differences from the reference's control flow, none of which change results:
+triplets are built on the GPU (no `.to('cpu')` round trip, xgnn.py:52-53); `num_graphs` is taken from
+the batch instead of `int(batch.max())` host syncs (model.py:46,53); and `edgenn` is evaluated once per
+ATOM and gathered per triplet instead of on all T gathered rows (its input emb(Z)[atom_j] has one
+distinct row per atom -- SURVEY.md §8f row 1; row-wise MLP, so edgenn(emb[a_j]) == edgenn(emb)[a_j]).
 """
 from __future__ import annotations
 
@@ -22,10 +24,11 @@ from .edge_graph import vertex_to_edge_2
 from .envelop import poly_envelop
 from .radial_basis_layer import RadialBasis
 from .sbftransformer_conv import Glorot_Ortho_, SBFTransformerConv
+from .tc_linear import TCLinear
 
 
 def _lin(i, o):
-    l = nn.Linear(i, o)
+    l = TCLinear(i, o)      # nn.Linear parameters; tensor-core GEMMs when out_features % 128 == 0
     Glorot_Ortho_(l.weight)
     nn.init.zeros_(l.bias)
     return l
@@ -94,8 +97,13 @@ class SBFTransformer(nn.Module):
         self.dense_bf_skip = nn.ModuleList([_lin(in_channels, in_channels) for _ in range(conv_layers)])
         self.conv_layers = conv_layers
 
-    def forward(self, x, edge_index, edge_attr, batch, edge_sbf, node_rbf, edge_index_0, atom_batch, num_graphs):
+    def forward(self, x, edge_index, edge_attr, batch, edge_sbf, node_rbf, edge_index_0, atom_batch, num_graphs,
+                edge_attr_index=None):
+        """`edge_attr` is [T, A] as in the reference, or -- with `edge_attr_index` [T] -- a per-atom table
+        [N, A] whose rows are gathered AFTER edgenn."""
         edge_attr = self.edgenn(edge_attr)
+        if edge_attr_index is not None:
+            edge_attr = edge_attr[edge_attr_index]
         out = x
         n_atoms = atom_batch.size(0)
         results = self.readouts[0](out, node_rbf, n_atoms, edge_index_0)
@@ -137,10 +145,11 @@ class XGNNPoly(nn.Module):
         env = self.envelop_function(d)[:, None]
         tri, a_j, a_i, a_k = vertex_to_edge_2(ei, data["x"].size(0))
         neo_x = F.silu(self.mat_trans(data["edge_attr"] * env))
-        neo_edge_attr = self.emb_block(data["x"])[a_j]
+        atom_emb = self.emb_block(data["x"])            # [N, A]; the reference gathers [a_j] here (xgnn.py:58)
         ji, jk = pos[a_i] - pos[a_j], pos[a_k] - pos[a_j]
         ang = torch.atan2(torch.linalg.cross(ji, jk).norm(dim=1), (ji * jk).sum(1))
         edge_sbf = self.sbf_layer(d, ang, tri[0])
         node_rbf = self.rbf_layer(d) * env
         neo_x = F.silu(self.emb_trans(neo_x))
-        return self.fin_model(neo_x, tri, neo_edge_attr, batch, edge_sbf, node_rbf, ei[0], data["batch"], B)
+        return self.fin_model(neo_x, tri, atom_emb, batch, edge_sbf, node_rbf, ei[0], data["batch"], B,
+                              edge_attr_index=a_j)

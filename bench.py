@@ -391,8 +391,15 @@ def run_ours(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = (fwd_b + bwd_b) / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
     phase_ms = {k: round(v[0] / max(steps, 1), 4) for k, v in phases.items()}
+    # DRAM traffic of the same step from the committed ncu capture (only valid for the same workload / mode)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_step_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("E") == E and tj.get("T") == T and tj.get("mode") == args.mode:
+            traffic, traffic_src = tj["dram_bytes_per_step"], tj["source"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel": "all launches of x2_sbfconv_fwd + x2_sbfconv_bwd (one layer step)",
                 "algorithmic_bytes_per_step": fwd_b + bwd_b, "kernel_ms_per_step": kernel_ms,
                 "phase_ms_per_step": phase_ms}

@@ -78,8 +78,9 @@ k_rbf_filter(const float* __restrict__ x, const float* __restrict__ rbf, const f
   for (int i = threadIdx.x; i < D * R; i += blockDim.x) s_w[i] = w_rbf[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int64_t e = (int64_t)blockIdx.x * kFilterRows + (threadIdx.x >> 5);
-  if (e >= E) return;
+  // grid-stride over rows: the W_r copy above is paid once per resident block, not once per 8 rows
+  for (int64_t e = (int64_t)blockIdx.x * kFilterRows + (threadIdx.x >> 5); e < E;
+       e += (int64_t)gridDim.x * kFilterRows) {
   float rv[2];                                     // R <= 64: lane holds rbf[e, lane] and rbf[e, lane + 32]
   rv[0] = lane < R ? rbf[e * R + lane] : 0.f;
   rv[1] = lane + 32 < R ? rbf[e * R + lane + 32] : 0.f;
@@ -94,6 +95,12 @@ k_rbf_filter(const float* __restrict__ x, const float* __restrict__ rbf, const f
     *reinterpret_cast<float4*>(xs + e * D + d0) = make_float4(xv.x * f[0], xv.y * f[1], xv.z * f[2], xv.w * f[3]);
     if (F) *reinterpret_cast<float4*>(F + e * D + d0) = make_float4(f[0], f[1], f[2], f[3]);
   }
+  }
+}
+static inline unsigned filter_grid(int64_t E) {
+  const int64_t need = cdiv(E, kFilterRows);
+  const int64_t cap = (int64_t)kNumSM * 8;
+  return (unsigned)(need < cap ? (need > 0 ? need : 1) : cap);
 }
 
 // dx += dxs * F ; dF = dxs * x (written over dxs)       (App. A last line)
@@ -549,7 +556,7 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
 
   phase_begin(st);
   // (1) x_src = x * lin_rbf(rbf)                                             :99-100
-  k_rbf_filter<<<(unsigned)cdiv(E, kFilterRows), kFilterRows * 32, (size_t)D * d->R * sizeof(float), st>>>(
+  k_rbf_filter<<<filter_grid(E), kFilterRows * 32, (size_t)D * d->R * sizeof(float), st>>>(
       d->x, d->rbf, d->w_rbf, E, D, d->R, w.xs, nullptr);
   X2_LAUNCH_OK();
   const Lin L{lin_mode(d->mode), w.img, nullptr, st};
@@ -660,7 +667,7 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
 
   phase_end(X2_PHASE_TROW_WGRAD, st);
   // (5) recompute the filtered sources
-  k_rbf_filter<<<(unsigned)cdiv(E, kFilterRows), kFilterRows * 32, (size_t)D * R * sizeof(float), st>>>(
+  k_rbf_filter<<<filter_grid(E), kFilterRows * 32, (size_t)D * R * sizeof(float), st>>>(
       d->x, d->rbf, d->w_rbf, E, D, R, w.xs, w.F);
   X2_LAUNCH_OK();
   // (6) node-level weight gradients

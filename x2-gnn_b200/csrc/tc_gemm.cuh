@@ -472,19 +472,33 @@ __device__ __forceinline__ uint32_t mnmajor_off(int r, int c16) {
   return (uint32_t)((c16 >> 3) * 4096 + (r >> 2) * 512 + (r & 3) * 128 + ((c32 ^ (r & 3)) << 5) + ((c16 & 1) << 4));
 }
 
+constexpr int kG2YCol = 128;         // TMEM columns [128, 128 + 64 S): per stage Y^T hi (32 cols) | lo (32 cols)
+
+__device__ __forceinline__ void tmem_st8f(uint32_t taddr, const float (&v)[8], bool lo) {
+  uint32_t r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(lo ? lo_part(v[j]) : v[j]);
+  tmem_st8(taddr, r);
+}
+
+// The dY^T operand (M = 128 output channels x K = rows) is the MMA's A operand and lives in TENSOR
+// MEMORY: producer thread (q, g, lane) owns channel d = 32 q + lane (its TMEM lane) and the 8 rows
+// 8g..8g+7 of every 32-row chunk, loads them coalesced across lanes and writes them with tcgen05.st.
+// Only X goes through shared memory (MN-major B operand), halving the smem traffic of the first
+// version, which was bound by shared-memory bandwidth (SS-mode MMAs re-read both operands 3 times).
 __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int S = p.stages;
   const uint32_t xbytes = (uint32_t)(p.N_pad / 32) * 4096;      // one X half (hi or lo)
-  const uint32_t stage_bytes = 2 * kChunkBytes + 2 * xbytes;    // Y hi | Y lo | X hi | X lo
+  const uint32_t stage_bytes = 2 * xbytes;                      // X hi | X lo
   uint8_t* sS = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sS + (size_t)S * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + S;
   uint64_t* tfull = bars + 2 * S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
-  float* cs_smem = reinterpret_cast<float*>(bars + 2 * S + 2);   // [16][128] column-sum staging
+  float* cs_smem = reinterpret_cast<float*>(bars + 2 * S + 2);   // [4][128] column-sum staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -495,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
     mbar_init(tfull, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -507,25 +521,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
 
   if (warp == 0) {
     if (lane == 0 && nchunks > 0) {
-      const uint32_t idesc = make_idesc(p.N_pad, 1, 1);
+      const uint32_t idesc = make_idesc(p.N_pad, 0, 1);          // A from TMEM, B MN-major
       const uint32_t s_u = smem_u32(sS);
       uint32_t st = 0, ph = 0;
       for (int64_t c = 0; c < nchunks; ++c) {
         mbar_wait(&full[st], ph);
         tc_fence_after();
-        const uint32_t y_hi = s_u + st * stage_bytes, y_lo = y_hi + kChunkBytes;
-        const uint32_t x_hi = y_lo + kChunkBytes, x_lo = x_hi + xbytes;
+        const uint32_t x_hi = s_u + st * stage_bytes, x_lo = x_hi + xbytes;
+        const uint32_t y_hi = tmem_base + kG2YCol + st * 64, y_lo = y_hi + 32;
         const int kvalid = (int)min((int64_t)kChunkK, rend - rbeg - c * kChunkK);
         const int ksteps = (kvalid + 7) >> 3;
-        const uint64_t dyh = make_desc(y_hi, 4096, 512, kLayoutSW128Base32);
-        const uint64_t dyl = make_desc(y_lo, 4096, 512, kLayoutSW128Base32);
         const uint64_t dxh = make_desc(x_hi, 4096, 512, kLayoutSW128Base32);
         const uint64_t dxl = make_desc(x_lo, 4096, 512, kLayoutSW128Base32);
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint64_t adv = (uint64_t)(ks * 64);       // one K=8 step = two 4-row k-groups = 1024 B (>>4)
-          umma_tf32(tmem_base, dyh + adv, dxh + adv, idesc, (c | ks) != 0);
-          umma_tf32(tmem_base, dyl + adv, dxh + adv, idesc, 1);
-          umma_tf32(tmem_base, dyh + adv, dxl + adv, idesc, 1);
+          umma_tf32_ts(tmem_base, y_hi + ks * 8, dxh + adv, idesc, (c | ks) != 0);
+          umma_tf32_ts(tmem_base, y_lo + ks * 8, dxh + adv, idesc, 1);
+          umma_tf32_ts(tmem_base, y_hi + ks * 8, dxl + adv, idesc, 1);
         }
         umma_commit(&empty[st]);
         if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
@@ -533,50 +545,38 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
       umma_commit(tfull);
     }
   } else if (warp <= kProducerWarps) {
-    // 512 producer threads.  Y chunk = 32 rows x 32 float4: thread owns float4 column yc of rows
-    // yr + 16 i.  X chunk = 32 rows x xq float4, flattened (up to 2 per thread).  Two chunks of loads
-    // in flight per thread.
-    const int pt = threadIdx.x - 32;
-    const int yc = pt & 31, yr = pt >> 5;
-    const bool vecY = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0);
+    const int pt = threadIdx.x - 32;                 // 0..511
+    const int q = warp & 3;                          // TMEM lane quarter of this warp
+    const int g = (warp - 1) >> 2;                   // 8-row group of the chunk (0..3)
+    const int d = q * 32 + lane;                     // output channel owned by this thread
     const bool vecX = ((p.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) && ((p.N & 3) == 0);
     const int xq = p.N_pad / 4;                      // float4 per X row (8..32)
     const int nx = kChunkK * xq;                     // float4 per X chunk (256..1024)
-    float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
     const uint32_t s_u = smem_u32(sS);
-    constexpr int NV = kChunkK * 32 / kProducerThreads;   // float4 per thread per operand chunk (2)
-    constexpr int RS = kProducerThreads / 32;             // row stride between a thread's Y loads (16)
-    const float* const y_thr = p.Y + (int64_t)yr * p.ldy + yc * 4;
-    const int64_t y_step = (int64_t)RS * p.ldy;
-    uint32_t yoff[NV], xoff[NV];
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + kG2YCol + 8 * g;
+    const float* const y_thr = p.Y + (int64_t)(8 * g) * p.ldy + d;
+    constexpr int NV = kChunkK * 32 / kProducerThreads;   // X float4 per thread per chunk (2)
+    uint32_t xoff[NV];
     int xr[NV], xcol[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      yoff[i] = mnmajor_off(yr + RS * i, yc);
       const int f = pt + i * kProducerThreads;
       xr[i] = f / xq;
       const int xc = f - xr[i] * xq;
       xcol[i] = xc * 4;
       xoff[i] = mnmajor_off(xr[i] & 31, xc);
     }
+    float cs = 0.f;
 
-    auto issue = [&](float4 (&vy)[NV], float4 (&vx)[NV], int64_t c) {
+    auto issue = [&](float (&vy)[8], float4 (&vx)[NV], int64_t c) {
       const int64_t row0 = rbeg + c * kChunkK;
-      const bool interior = row0 + kChunkK <= rend;
       const float* ysrc = y_thr + row0 * p.ldy;
-      if (interior && vecY) {
+      if (row0 + kChunkK <= rend) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) vy[i] = __ldg(reinterpret_cast<const float4*>(ysrc + i * y_step));
+        for (int j = 0; j < 8; ++j) vy[j] = __ldg(ysrc + (int64_t)j * p.ldy);
       } else {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          vy[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row0 + yr + RS * i < rend) {
-            const float* q = ysrc + i * y_step;
-            if (vecY) vy[i] = __ldg(reinterpret_cast<const float4*>(q));
-            else { vy[i].x = __ldg(q); vy[i].y = __ldg(q + 1); vy[i].z = __ldg(q + 2); vy[i].w = __ldg(q + 3); }
-          }
-        }
+        for (int j = 0; j < 8; ++j) vy[j] = (row0 + 8 * g + j < rend) ? __ldg(ysrc + (int64_t)j * p.ldy) : 0.f;
       }
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
@@ -584,31 +584,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
         if (pt + i * kProducerThreads < nx) {
           const int64_t row = row0 + xr[i];
           if (row < rend) {
-            const float* q = p.X + row * p.ldx + xcol[i];
-            if (vecX && xcol[i] + 3 < p.N) vx[i] = __ldg(reinterpret_cast<const float4*>(q));
+            const float* qx = p.X + row * p.ldx + xcol[i];
+            if (vecX && xcol[i] + 3 < p.N) vx[i] = __ldg(reinterpret_cast<const float4*>(qx));
             else {
-              if (xcol[i] < p.N) vx[i].x = __ldg(q);
-              if (xcol[i] + 1 < p.N) vx[i].y = __ldg(q + 1);
-              if (xcol[i] + 2 < p.N) vx[i].z = __ldg(q + 2);
-              if (xcol[i] + 3 < p.N) vx[i].w = __ldg(q + 3);
+              if (xcol[i] < p.N) vx[i].x = __ldg(qx);
+              if (xcol[i] + 1 < p.N) vx[i].y = __ldg(qx + 1);
+              if (xcol[i] + 2 < p.N) vx[i].z = __ldg(qx + 2);
+              if (xcol[i] + 3 < p.N) vx[i].w = __ldg(qx + 3);
             }
           }
         }
       }
     };
     uint32_t st = 0, ph = 0;
-    auto commit = [&](const float4 (&vy)[NV], const float4 (&vx)[NV]) {
+    auto commit = [&](const float (&vy)[8], const float4 (&vx)[NV]) {
       mbar_wait(&empty[st], ph ^ 1);
-      const uint32_t base = s_u + st * stage_bytes;
+      tc_fence_after();
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        cs0 += vy[i].x; cs1 += vy[i].y; cs2 += vy[i].z; cs3 += vy[i].w;   // fixed order per thread
-        uint4 hi, lo;
-        split4(vy[i], hi, lo);
-        sts128(base + yoff[i], hi);
-        sts128(base + kChunkBytes + yoff[i], lo);
-      }
-      const uint32_t xb = base + 2 * kChunkBytes;
+      for (int j = 0; j < 8; ++j) cs += vy[j];                   // fixed order per thread
+      tmem_st8f(trow + st * 64, vy, false);
+      tmem_st8f(trow + st * 64 + 32, vy, true);
+      const uint32_t xb = s_u + st * stage_bytes;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         if (pt + i * kProducerThreads < nx) {
@@ -618,12 +614,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
           sts128(xb + xbytes + xoff[i], lo);
         }
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
       fence_proxy_async();
       mbar_arrive(&full[st]);
       if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
     };
 
-    float4 ya[NV], xa[NV], yb[NV], xb_[NV];
+    float ya[8], yb[8];
+    float4 xa[NV], xb_[NV];
     if (nchunks > 0) issue(ya, xa, 0);
     for (int64_t c = 0; c < nchunks; c += 2) {
       if (c + 1 < nchunks) issue(yb, xb_, c + 1);
@@ -633,19 +632,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
         commit(yb, xb_);
       }
     }
-    // column sums of Y over this CTA's rows: combine the 16 row-phase threads in fixed order
+    // column sums of Y over this CTA's rows: combine the 4 row groups in fixed order
     if (p.colsum) {
-      cs_smem[yr * 128 + yc * 4 + 0] = cs0;
-      cs_smem[yr * 128 + yc * 4 + 1] = cs1;
-      cs_smem[yr * 128 + yc * 4 + 2] = cs2;
-      cs_smem[yr * 128 + yc * 4 + 3] = cs3;
+      cs_smem[g * 128 + d] = cs;
       asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
-      if (pt < 128) {
-        float s = 0.f;
-#pragma unroll
-        for (int g = 0; g < RS; ++g) s += cs_smem[g * 128 + pt];
-        p.colsum[(int64_t)blockIdx.x * 128 + pt] = s;
-      }
+      if (g == 0) p.colsum[(int64_t)blockIdx.x * 128 + d] = (cs_smem[d] + cs_smem[128 + d]) + (cs_smem[256 + d] + cs_smem[384 + d]);
     }
   } else if (warp <= kProducerWarps + 4) {
     const int q = warp & 3;
@@ -670,7 +661,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
   __syncthreads();
   if (warp == 0) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 128);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -733,11 +724,9 @@ static int tc_wgrad(const float* Y, int64_t ldy, const float* X, int64_t ldx, in
   const int N_pad = ceil_to(N, 32);
   const int grid = wgrad_ctas(rows);
   const int64_t rpc = cdiv(cdiv(rows > 0 ? rows : 1, grid), kChunkK) * kChunkK;
-  const uint32_t stage_bytes = 2 * kChunkBytes + 2 * (uint32_t)(N_pad / 32) * 4096;
-  int stages = (int)(((size_t)196608 - 12288 - 4096) / stage_bytes);   // <= 192 KB: keeps a 60 KB L1 for the LDG stream
-  if (stages > 4) stages = 4;
-  if (stages < 2) stages = 2;
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + 256 + (kProducerThreads / 32) * 128 * sizeof(float);
+  const uint32_t stage_bytes = 2 * (uint32_t)(N_pad / 32) * 4096;      // X hi | X lo (Y^T lives in tensor memory)
+  const int stages = 4;                                                 // <= 128 KB smem, 4 x 64 TMEM columns
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + 256 + 4 * 128 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     X2_CUDA_OK(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));

@@ -561,7 +561,14 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
   X2_LAUNCH_OK();
   const Lin L{lin_mode(d->mode), w.img, nullptr, st};
   // (2) Q | K | V | skip                                                     :105-107, :121
-  if (L.mode == X2_MODE_TF32X3) {
+  if (L.mode == X2_MODE_TF32X3 && D == kTcBlock) {   // the four projections as problems of ONE launch
+    tc::G1Prob pr[4] = {
+        {d->x, D, d->w_q, d->b_q, s->qkvs, 4 * D, 0},
+        {w.xs, D, d->w_k, d->b_k, s->qkvs + D, 4 * D, 0},
+        {w.xs, D, d->w_v, d->b_v, s->qkvs + 2 * D, 4 * D, 0},
+        {d->x, D, d->w_skip, d->b_skip, s->qkvs + 3 * D, 4 * D, 0}};
+    X2_TRY(tc::tc_gemm_batch(pr, d->fuse_skip ? 4 : 3, E, D, 1, D, D, st));
+  } else if (L.mode == X2_MODE_TF32X3) {
     X2_TRY(lin_fwd(L, d->x, D, d->w_q, D, d->b_q, s->qkvs, 4 * D, E, D, D));
     X2_TRY(lin_fwd(L, w.xs, D, d->w_k, D, d->b_k, s->qkvs + D, 4 * D, E, D, D));
     X2_TRY(lin_fwd(L, w.xs, D, d->w_v, D, d->b_v, s->qkvs + 2 * D, 4 * D, E, D, D));
@@ -675,12 +682,22 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
   X2_TRY(lin_wgrad(L, dk, 3 * D, w.xs, D, g->dw_k, D, g->db_k, E, D, D));
   X2_TRY(lin_wgrad(L, dv, 3 * D, w.xs, D, g->dw_v, D, g->db_v, E, D, D));
   if (d->fuse_skip) X2_TRY(lin_wgrad(L, grad_out, D, d->x, D, g->dw_skip, D, g->db_skip, E, D, D));
+  if (L.mode == X2_MODE_TF32X3 && D == kTcBlock) {
+    // (7) dxs = dK W_k + dV W_v and (8) dx = dQ W_q (+ G W_o) as four problems of ONE launch
+    tc::G1Prob pr[4] = {
+        {dk, 3 * D, d->w_k, nullptr, w.dxs, D, 0},
+        {dv, 3 * D, d->w_v, nullptr, w.dxs, D, 1},
+        {dq, 3 * D, d->w_q, nullptr, g->dx, D, 0},
+        {grad_out, D, d->w_skip, nullptr, g->dx, D, 1}};
+    X2_TRY(tc::tc_gemm_batch(pr, d->fuse_skip ? 4 : 3, E, D, D, 1, D, st));
+  } else {
   // (7) dxs = dK W_k + dV W_v
   X2_TRY(lin_dgrad(L, dk, 3 * D, d->w_k, D, w.dxs, D, E, D, D, 0));
   X2_TRY(lin_dgrad(L, dv, 3 * D, d->w_v, D, w.dxs, D, E, D, D, 1));
   // (8) dx = dQ W_q (+ G W_o)
   X2_TRY(lin_dgrad(L, dq, 3 * D, d->w_q, D, g->dx, D, E, D, D, 0));
   if (d->fuse_skip) X2_TRY(lin_dgrad(L, grad_out, D, d->w_skip, D, g->dx, D, E, D, D, 1));
+  }
   // (9) dx += dxs * F ; dF = dxs * x
   k_filter_bwd<<<(unsigned)cdiv(E * D, 256), 256, 0, st>>>(d->x, w.F, w.dxs, g->dx, E * D);
   X2_LAUNCH_OK();

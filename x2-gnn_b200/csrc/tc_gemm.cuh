@@ -200,17 +200,26 @@ __host__ __device__ __forceinline__ uint32_t kmajor_off(int r, int c16) {
 constexpr int kTmemWHi = 256;        // TMEM columns [256, 384): W_hi ; [384, 512): W_lo ; [0, 256): 2 accumulators
 constexpr int kTmemWLo = 384;
 
-struct G1Params {
+constexpr int kMaxProb = 4;
+struct G1Prob {
   const float* A;        // streamed activations X[M, K]
-  int64_t lda, M;
-  int K, KC;             // KC = ceil(K / 32) <= 4
+  int64_t lda;
   const float* W;        // weights: B(k, n) = W[k * sbk + n * sbn]
-  int64_t sbk, sbn;
-  int N;                 // output channels <= 128
   const float* bias;
   float* C;
   int64_t ldc;
   int beta;
+};
+// Up to kMaxProb problems of identical shape run back to back inside one persistent launch (the Q / K /
+// V / skip projections, or the dgrad pairs): the ~15 us start-up of a launch (TMEM allocation, pipeline
+// fill, tail) is paid once; only the weights in tensor memory are swapped between problems.
+struct G1Params {
+  G1Prob prob[kMaxProb];
+  int nprob;
+  int64_t M;
+  int K, KC;             // KC = ceil(K / 32) <= 4
+  int64_t sbk, sbn;      // weight strides (shared by the problems)
+  int N;                 // output channels <= 128
   int stages;
 };
 
@@ -246,13 +255,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
   const uint32_t tmem_base = *tmem_slot;
 
   // ---- weights -> tensor memory (first epilogue warp of each lane quarter): lane = output channel n.
-  // Loads are issued 32 at a time (a serial chain of 128 dependent loads cost ~10 us per launch); only the
-  // MMA warp waits for the weights (named barrier 2), the producers start streaming immediately.
-  if (warp > kProducerWarps && warp <= kProducerWarps + 4) {
+  // Loads are issued 32 at a time; only the MMA warp waits for the weights (named barrier 2), the
+  // producers start streaming immediately.
+  auto load_weights = [&](const float* __restrict__ W) {
     const int q = warp & 3;
     const int n = q * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float* __restrict__ wrow = p.W + (int64_t)n * p.sbn;
+    const float* __restrict__ wrow = W + (int64_t)n * p.sbn;
     const bool nv = n < p.N;
     for (int k0 = 0; k0 < p.KC * kChunkK; k0 += 32) {
       float w[32];
@@ -276,20 +285,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     tc_fence_before();
     asm volatile("bar.arrive 2, 160;" ::: "memory");
-  }
+  };
 
   const int64_t ntiles = (p.M + kTileM - 1) / kTileM;
   const int KC = p.KC;
 
   if (warp == 0) {
     // =============================== MMA issuer ===============================
-    asm volatile("bar.sync 2, 160;" ::: "memory");        // weights are in tensor memory
+    const uint32_t idesc = make_idesc(kTileM, 0, 0);     // M = 128 channels, N = 128 rows of the tile
+    const uint32_t sA_u = smem_u32(sA);
+    uint32_t st = 0, ph = 0;   // smem ring position / phase
+    uint32_t tcount = 0;       // tile counter (TMEM accumulator buffer)
+    for (int pi = 0; pi < p.nprob; ++pi) {
+    asm volatile("bar.sync 2, 160;" ::: "memory");        // this problem's weights are in tensor memory
     tc_fence_after();
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(kTileM, 0, 0);     // M = 128 channels, N = 128 rows of the tile
-      const uint32_t sA_u = smem_u32(sA);
-      uint32_t st = 0, ph = 0;   // smem ring position / phase
-      uint32_t tcount = 0;       // tile counter (TMEM accumulator buffer)
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
         const uint32_t buf = tcount & 1;
         mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1);
@@ -315,32 +325,38 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
         umma_commit(&tfull[buf]);           // accumulator complete
       }
     }
+    __syncwarp();
+    }
   } else if (warp <= kProducerWarps) {
     // =============================== producers ===============================
     // 512 threads; thread (c16, r0) moves the 16-byte column chunk c16 of rows r0 + 64 i.
     const int pt = threadIdx.x - 32;                 // 0..511
     const int c16 = pt & 7, r0 = pt >> 3;            // 8 threads cover one 128-byte row segment
-    const bool vec = ((p.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
     const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t nchunk = my_tiles * KC;
     const uint32_t sA_u = smem_u32(sA);
-    const float* const a_thr = p.A + (int64_t)r0 * p.lda + c16 * 4;
     constexpr int NV = kTileM * 8 / kProducerThreads;   // float4 per thread per chunk (2)
     constexpr int RS = kProducerThreads / 8;            // row stride between a thread's loads (64)
-    const int64_t row_step = (int64_t)RS * p.lda;
+    uint32_t st = 0, ph = 0;
+    for (int pi = 0; pi < p.nprob; ++pi) {
+    const G1Prob& pr = p.prob[pi];
+    const int64_t lda = pr.lda;
+    const bool vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(pr.A) & 15) == 0);
+    const float* const a_thr = pr.A + (int64_t)r0 * lda + c16 * 4;
+    const int64_t row_step = (int64_t)RS * lda;
     uint32_t soff[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) soff[i] = kmajor_off(r0 + RS * i, c16);
 
     // load cursor (tile row offset, K chunk) and ring cursor advance incrementally: no div/mod
-    int64_t ld_m0 = (int64_t)blockIdx.x * kTileM;
+    int64_t ld_m0 = (int64_t)blockIdx.x * kTileM;     // restarts for every problem
     int ld_kc = 0;
     const int64_t m_step = (int64_t)gridDim.x * kTileM;
     auto issue = [&](float4 (&v)[NV]) {
       const int64_t m0 = ld_m0;
       const int kc0 = ld_kc * kChunkK;
       if (++ld_kc == KC) { ld_kc = 0; ld_m0 += m_step; }
-      const float* src = a_thr + m0 * p.lda + kc0;
+      const float* src = a_thr + m0 * lda + kc0;
       if (vec && m0 + kTileM <= p.M && kc0 + kChunkK <= p.K) {       // interior chunk: no guards
 #pragma unroll
         for (int i = 0; i < NV; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(src + i * row_step));
@@ -362,7 +378,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
         }
       }
     };
-    uint32_t st = 0, ph = 0;
     auto commit = [&](const float4 (&v)[NV]) {
       mbar_wait(&empty[st], ph ^ 1);
       const uint32_t base = sA_u + st * 2 * kChunkBytes;
@@ -394,6 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
         commit(vc);
       }
     }
+    }
   } else {
     // =============================== epilogue ===============================
     // The accumulator is C^T: lane = output channel n = 32 q + lane, column = row of the tile.  Warp
@@ -404,8 +420,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
     const int half = ew >> 2;
     const int n = q * 32 + lane;
     const bool nvalid = n < p.N;
-    const float bv = (p.bias && nvalid) ? __ldg(p.bias + n) : 0.f;
     uint32_t tcount = 0;
+    for (int pi = 0; pi < p.nprob; ++pi) {
+    const G1Prob& pr = p.prob[pi];
+    // every epilogue warp has waited for the previous problem's last accumulator, i.e. all MMAs that
+    // read the old weights have retired: the loader warps may overwrite them
+    if (ew < 4) load_weights(pr.W);
+    const float bv = (pr.bias && nvalid) ? __ldg(pr.bias + n) : 0.f;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const uint32_t buf = tcount & 1;
       mbar_wait(&tfull[buf], (tcount >> 1) & 1);
@@ -416,21 +437,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
         float v[16];
         tmem_ld16(taddr + c0, v);
         if (nvalid) {
-          float* dst = p.C + (row0 + c0) * p.ldc + n;
+          float* dst = pr.C + (row0 + c0) * pr.ldc + n;
           if (row0 + c0 + 16 <= p.M) {
-            if (p.beta) {
+            if (pr.beta) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] += dst[(int64_t)j * p.ldc];
+              for (int j = 0; j < 16; ++j) v[j] += dst[(int64_t)j * pr.ldc];
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dst[(int64_t)j * p.ldc] = v[j] + bv;
+            for (int j = 0; j < 16; ++j) dst[(int64_t)j * pr.ldc] = v[j] + bv;
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               if (row0 + c0 + j < p.M) {
                 float o = v[j] + bv;
-                if (p.beta) o += dst[(int64_t)j * p.ldc];
-                dst[(int64_t)j * p.ldc] = o;
+                if (pr.beta) o += dst[(int64_t)j * pr.ldc];
+                dst[(int64_t)j * pr.ldc] = o;
               }
             }
           }
@@ -438,6 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
       }
       tc_fence_before();
       mbar_arrive(&tempty[buf]);
+    }
     }
   }
 
@@ -673,13 +695,11 @@ static inline size_t bimage_bytes(int K, int N) { (void)K; (void)N; return 256; 
 
 static inline bool g1_supported(int K, int N) { return K >= 1 && K <= 128 && N >= 1 && N <= 128; }
 
-// C[M,N] (+)= A[M,K] . B(K,N) + bias, B(k,n) = W[k*sbk + n*sbn].
-static int tc_gemm(const float* A, int64_t lda, int64_t M, int K, const float* W, int64_t sbk, int64_t sbn,
-                   int N, const float* bias, float* C, int64_t ldc, int beta, void* img, cudaStream_t st) {
-  (void)img;
-  if (M <= 0) return X2_OK;
-  if (!g1_supported(K, N)) { set_error("tc_gemm: unsupported K=%d N=%d", K, N); return X2_EINVAL; }
-  const int KC = (K + kChunkK - 1) / kChunkK;
+// nprob problems C_i[M,N] (+)= A_i[M,K] . B_i(K,N) + bias_i, B_i(k,n) = W_i[k*sbk + n*sbn], in one launch.
+static int tc_gemm_batch(const G1Prob* probs, int nprob, int64_t M, int K, int64_t sbk, int64_t sbn, int N,
+                         cudaStream_t st) {
+  if (M <= 0 || nprob <= 0) return X2_OK;
+  if (!g1_supported(K, N) || nprob > kMaxProb) { set_error("tc_gemm: unsupported K=%d N=%d nprob=%d", K, N, nprob); return X2_EINVAL; }
   const int stages = 5;                                   // 5 x 32 KB = 160 KB: stays under the 196 KB carve-out
   const size_t smem = 1024 + (size_t)stages * 2 * kChunkBytes + 256;
   static bool attr_set = false;
@@ -687,15 +707,24 @@ static int tc_gemm(const float* A, int64_t lda, int64_t M, int K, const float* W
     X2_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     attr_set = true;
   }
-  G1Params p;
-  p.A = A; p.lda = lda; p.M = M; p.K = K; p.KC = KC;
-  p.W = W; p.sbk = sbk; p.sbn = sbn;
-  p.N = N; p.bias = bias; p.C = C; p.ldc = ldc; p.beta = beta; p.stages = stages;
+  G1Params p{};
+  for (int i = 0; i < nprob; ++i) p.prob[i] = probs[i];
+  p.nprob = nprob;
+  p.M = M; p.K = K; p.KC = (K + kChunkK - 1) / kChunkK;
+  p.sbk = sbk; p.sbn = sbn; p.N = N; p.stages = stages;
   const int64_t ntiles = cdiv(M, kTileM);
   const int grid = (int)(ntiles < kNumSM ? ntiles : kNumSM);
   k_tc_gemm<<<grid, kThreads, smem, st>>>(p);
   X2_LAUNCH_OK();
   return X2_OK;
+}
+
+// C[M,N] (+)= A[M,K] . B(K,N) + bias, B(k,n) = W[k*sbk + n*sbn].
+static int tc_gemm(const float* A, int64_t lda, int64_t M, int K, const float* W, int64_t sbk, int64_t sbn,
+                   int N, const float* bias, float* C, int64_t ldc, int beta, void* img, cudaStream_t st) {
+  (void)img;
+  G1Prob pr{A, lda, W, bias, C, ldc, beta};
+  return tc_gemm_batch(&pr, 1, M, K, sbk, sbn, N, st);
 }
 
 static inline int wgrad_ctas(int64_t rows) {

@@ -78,7 +78,7 @@ __global__ void k_make_ws_image(const float* __restrict__ W, int S, uint32_t* __
   const int k = kc * kChunkK + kk;
   const float w = k < S ? W[(int64_t)d * S + k] : 0.f;
   const uint32_t off = (uint32_t)kc * kChunkBytes + kmajor_off(d, kk >> 2) + (kk & 3) * 4;
-  img[off >> 2] = __float_as_uint(w);
+  img[off >> 2] = hi_bits(w);
   img[(kWsKC * kChunkBytes + off) >> 2] = __float_as_uint(lo_part(w));
 }
 
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_fwd(const F1Params p) {
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          hi[j] = __float_as_uint(w[g * 8 + j]);
+          hi[j] = hi_bits(w[g * 8 + j]);
           lo[j] = __float_as_uint(lo_part(w[g * 8 + j]));
         }
         tmem_st8(trow + kTmemWHi + k0 + g * 8, hi);

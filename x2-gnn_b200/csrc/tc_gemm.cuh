@@ -29,7 +29,7 @@
 //       CTAs, partial tiles summed in fixed order by k_splitk_reduce => deterministic wgrad).
 //
 // Split precision: the tensor core TRUNCATES fp32 operand bits to tf32 (verified with
-// tools/umma_ts_probe.cu), so the raw fp32 value is fed as the "hi" operand and lo = x - trunc(x).
+// tools/umma_ts_probe.cu), so hi and lo are rounded to nearest tf32 in software before they are stored.
 #pragma once
 #include "common.cuh"
 
@@ -141,13 +141,16 @@ __device__ __forceinline__ float lds32f(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
   return v;
 }
-// hi = the raw bits (the tensor core drops the 13 low mantissa bits itself); lo = x - trunc(x), exact in
-// fp32, of which the tensor core again keeps the top 11 bits (error ~2^-21 |x|).
+// 3xTF32 split.  The tensor core truncates operand bits to tf32, so both parts are rounded to NEAREST
+// tf32 here (two integer ops each): hi = rn(x), lo = rn(x - hi).  |x - hi - lo| <= 2^-23 |x| and unbiased;
+// feeding the raw bits instead leaves a one-sided 2^-21 residual (measured: 5e-6 vs 1e-6 layer error).
+__device__ __forceinline__ uint32_t hi_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ float lo_part(float x) {
-  return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  const float l = x - __uint_as_float(hi_bits(x));
+  return __uint_as_float(hi_bits(l));
 }
 __device__ __forceinline__ void split4(const float4& v, uint4& hi, uint4& lo) {
-  hi.x = __float_as_uint(v.x); hi.y = __float_as_uint(v.y); hi.z = __float_as_uint(v.z); hi.w = __float_as_uint(v.w);
+  hi.x = hi_bits(v.x); hi.y = hi_bits(v.y); hi.z = hi_bits(v.z); hi.w = hi_bits(v.w);
   lo.x = __float_as_uint(lo_part(v.x));
   lo.y = __float_as_uint(lo_part(v.y));
   lo.z = __float_as_uint(lo_part(v.z));
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          hi[j] = __float_as_uint(w[g * 8 + j]);
+          hi[j] = hi_bits(w[g * 8 + j]);
           lo[j] = __float_as_uint(lo_part(w[g * 8 + j]));
         }
         tmem_st8(trow + kTmemWHi + k0 + g * 8, hi);
@@ -499,7 +502,7 @@ constexpr int kG2YCol = 128;         // TMEM columns [128, 128 + 64 S): per stag
 __device__ __forceinline__ void tmem_st8f(uint32_t taddr, const float (&v)[8], bool lo) {
   uint32_t r[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(lo ? lo_part(v[j]) : v[j]);
+  for (int j = 0; j < 8; ++j) r[j] = lo ? __float_as_uint(lo_part(v[j])) : hi_bits(v[j]);
   tmem_st8(taddr, r);
 }
 

@@ -148,7 +148,7 @@ k_attn_fwd(const float* __restrict__ qkvs, int ldq, const float* __restrict__ ea
       s_l = src[t_l];
     }
     const int cnt = min(32, end - base);
-#pragma unroll 2
+#pragma unroll 4
     for (int i = 0; i < cnt; ++i) {
       const int t = __shfl_sync(0xffffffffu, t_l, i);
       const int s = __shfl_sync(0xffffffffu, s_l, i);
@@ -245,7 +245,7 @@ k_attn_bwd_tgt(const float* __restrict__ qkvs, int ldq, const float* __restrict_
       s_l = src[t_l];
     }
     const int cnt = min(32, end - base);
-#pragma unroll 2
+#pragma unroll 4
     for (int i = 0; i < cnt; ++i) {
       const int t = __shfl_sync(0xffffffffu, t_l, i);
       const int s = __shfl_sync(0xffffffffu, s_l, i);
@@ -323,7 +323,7 @@ k_attn_bwd_src(const float* __restrict__ qkvs, int ldq, const float* __restrict_
       e_l = tgt[t_l];
     }
     const int cnt = min(32, end - base);
-#pragma unroll 2
+#pragma unroll 4
     for (int i = 0; i < cnt; ++i) {
       const int t = __shfl_sync(0xffffffffu, t_l, i);
       const int e = __shfl_sync(0xffffffffu, e_l, i);

@@ -112,6 +112,20 @@ __global__ void k_filter_bwd(const float* __restrict__ x, const float* __restric
   dx[i] += g * F[i];
   dxs[i] = g * x[i];
 }
+// Same, with the sums the grouped dgrad launch leaves open folded in (fixed order):
+// dxs = dxs + dxs2 ; dx = (dx + dx2) + dxs * F ; dF = dxs * x.  n4 = number of float4 (dx2 may be NULL).
+__global__ void k_filter_bwd_sum(const float4* __restrict__ x, const float4* __restrict__ F,
+                                 float4* __restrict__ dxs, const float4* __restrict__ dxs2,
+                                 float4* __restrict__ dx, const float4* __restrict__ dx2, int64_t n4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 a = dxs[i], b = dxs2[i], f = F[i], xv = x[i];
+  float4 o = dx[i];
+  if (dx2) { const float4 o2 = dx2[i]; o.x += o2.x; o.y += o2.y; o.z += o2.z; o.w += o2.w; }
+  const float4 g = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  dx[i] = make_float4(o.x + g.x * f.x, o.y + g.y * f.y, o.z + g.z * f.z, o.w + g.w * f.w);
+  dxs[i] = make_float4(g.x * xv.x, g.y * xv.y, g.z * xv.z, g.w * xv.w);
+}
 
 // ------------------------------------------------------------------ segmented attention fwd
 template <int VEC>
@@ -431,7 +445,7 @@ static size_t fwd_layout(const x2_conv_desc* d, void* ws, FwdWs* w) {
 }
 
 struct BwdWs {
-  float *dea, *dsg, *al, *da, *dqkv, *xs, *F, *dxs, *wg;
+  float *dea, *dsg, *al, *da, *dqkv, *xs, *F, *dxs, *dxs2, *dx2, *wg;
   void* img;
   size_t wg_floats;
 };
@@ -446,6 +460,8 @@ static size_t bwd_layout(const x2_conv_desc* d, void* ws, BwdWs* w) {
   w->xs = a.take<float>(ED + 4);
   w->F = a.take<float>(ED + 4);
   w->dxs = a.take<float>(ED + 4);
+  w->dxs2 = a.take<float>(ED + 4);
+  w->dx2 = a.take<float>(ED + 4);
   size_t wg = wgrad_workspace_floats(d->T, d->D, d->A > 0 ? d->A : 1);
   size_t t2 = wgrad_workspace_floats(d->T, d->D, d->S);
   if (t2 > wg) wg = t2;
@@ -567,7 +583,7 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
         {w.xs, D, d->w_k, d->b_k, s->qkvs + D, 4 * D, 0},
         {w.xs, D, d->w_v, d->b_v, s->qkvs + 2 * D, 4 * D, 0},
         {d->x, D, d->w_skip, d->b_skip, s->qkvs + 3 * D, 4 * D, 0}};
-    X2_TRY(tc::tc_gemm_batch(pr, d->fuse_skip ? 4 : 3, E, D, 1, D, D, st));
+    X2_TRY(tc::tc_gemm_batch(pr, d->fuse_skip ? 4 : 3, d->fuse_skip ? 4 : 3, E, D, 1, D, D, st));   // one group each
   } else if (L.mode == X2_MODE_TF32X3) {
     X2_TRY(lin_fwd(L, d->x, D, d->w_q, D, d->b_q, s->qkvs, 4 * D, E, D, D));
     X2_TRY(lin_fwd(L, w.xs, D, d->w_k, D, d->b_k, s->qkvs + D, 4 * D, E, D, D));
@@ -678,18 +694,37 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
       d->x, d->rbf, d->w_rbf, E, D, R, w.xs, w.F);
   X2_LAUNCH_OK();
   // (6) node-level weight gradients
+  const bool batched = L.mode == X2_MODE_TF32X3 && D == kTcBlock &&
+                       ((reinterpret_cast<uintptr_t>(d->x) | reinterpret_cast<uintptr_t>(g->dx)) & 15) == 0;
+  if (batched) {          // the four weight gradients as problems of ONE launch (+ one reduction)
+    const tc::G2Job jobs[4] = {
+        {dq, 3 * D, d->x, D, g->dw_q, D, g->db_q},
+        {dk, 3 * D, w.xs, D, g->dw_k, D, g->db_k},
+        {dv, 3 * D, w.xs, D, g->dw_v, D, g->db_v},
+        {grad_out, D, d->x, D, g->dw_skip, D, g->db_skip}};
+    X2_TRY(tc::tc_wgrad_batch(jobs, d->fuse_skip ? 4 : 3, E, D, L.wg, st));
+  } else {
   X2_TRY(lin_wgrad(L, dq, 3 * D, d->x, D, g->dw_q, D, g->db_q, E, D, D));
   X2_TRY(lin_wgrad(L, dk, 3 * D, w.xs, D, g->dw_k, D, g->db_k, E, D, D));
   X2_TRY(lin_wgrad(L, dv, 3 * D, w.xs, D, g->dw_v, D, g->db_v, E, D, D));
   if (d->fuse_skip) X2_TRY(lin_wgrad(L, grad_out, D, d->x, D, g->dw_skip, D, g->db_skip, E, D, D));
-  if (L.mode == X2_MODE_TF32X3 && D == kTcBlock) {
-    // (7) dxs = dK W_k + dV W_v and (8) dx = dQ W_q (+ G W_o) as four problems of ONE launch
+  }
+  if (batched) {
+    // (7) dK W_k, dV W_v and (8) dQ W_q (, G W_o) as independent problems of ONE launch, one group
+    // each; k_filter_bwd_sum adds the pairs
     tc::G1Prob pr[4] = {
         {dk, 3 * D, d->w_k, nullptr, w.dxs, D, 0},
-        {dv, 3 * D, d->w_v, nullptr, w.dxs, D, 1},
+        {dv, 3 * D, d->w_v, nullptr, w.dxs2, D, 0},
         {dq, 3 * D, d->w_q, nullptr, g->dx, D, 0},
-        {grad_out, D, d->w_skip, nullptr, g->dx, D, 1}};
-    X2_TRY(tc::tc_gemm_batch(pr, d->fuse_skip ? 4 : 3, E, D, D, 1, D, st));
+        {grad_out, D, d->w_skip, nullptr, w.dx2, D, 0}};
+    const int np = d->fuse_skip ? 4 : 3;
+    X2_TRY(tc::tc_gemm_batch(pr, np, np, E, D, D, 1, D, st));
+    k_filter_bwd_sum<<<(unsigned)cdiv(E * D / 4, 256), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(d->x), reinterpret_cast<const float4*>(w.F),
+        reinterpret_cast<float4*>(w.dxs), reinterpret_cast<const float4*>(w.dxs2),
+        reinterpret_cast<float4*>(g->dx), d->fuse_skip ? reinterpret_cast<const float4*>(w.dx2) : nullptr,
+        E * D / 4);
+    X2_LAUNCH_OK();
   } else {
   // (7) dxs = dK W_k + dV W_v
   X2_TRY(lin_dgrad(L, dk, 3 * D, d->w_k, D, w.dxs, D, E, D, D, 0));
@@ -697,10 +732,10 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
   // (8) dx = dQ W_q (+ G W_o)
   X2_TRY(lin_dgrad(L, dq, 3 * D, d->w_q, D, g->dx, D, E, D, D, 0));
   if (d->fuse_skip) X2_TRY(lin_dgrad(L, grad_out, D, d->w_skip, D, g->dx, D, E, D, D, 1));
-  }
   // (9) dx += dxs * F ; dF = dxs * x
   k_filter_bwd<<<(unsigned)cdiv(E * D, 256), 256, 0, st>>>(d->x, w.F, w.dxs, g->dx, E * D);
   X2_LAUNCH_OK();
+  }
   // (10) d rbf = dF W_r ; dW_r = dF^T rbf
   X2_TRY(lin_dgrad(L, w.dxs, D, d->w_rbf, R, g->drbf, R, E, R, D, 0));
   X2_TRY(lin_wgrad(L, w.dxs, D, d->rbf, R, g->dw_rbf, R, nullptr, E, D, R));

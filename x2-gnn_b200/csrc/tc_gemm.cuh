@@ -216,9 +216,14 @@ struct G1Prob {
 // Up to kMaxProb problems of identical shape run back to back inside one persistent launch (the Q / K /
 // V / skip projections, or the dgrad pairs): the ~15 us start-up of a launch (TMEM allocation, pipeline
 // fill, tail) is paid once; only the weights in tensor memory are swapped between problems.
+// The problems form `ngroups` groups of `ppg` consecutive problems: CTA b works for group b % ngroups
+// only (its tiles are b / ngroups, + gridDim / ngroups, ...) and runs that group's problems back to
+// back.  Problems that write different outputs go to different groups, so a CTA loads its weights
+// once and its tile pipeline never drains; problems accumulating into one output share a group.
 struct G1Params {
   G1Prob prob[kMaxProb];
   int nprob;
+  int ngroups, ppg;      // nprob = ngroups * ppg ; gridDim.x is a multiple of ngroups
   int64_t M;
   int K, KC;             // KC = ceil(K / 32) <= 4
   int64_t sbk, sbn;      // weight strides (shared by the problems)
@@ -292,6 +297,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
 
   const int64_t ntiles = (p.M + kTileM - 1) / kTileM;
   const int KC = p.KC;
+  const int grp = (int)(blockIdx.x % (unsigned)p.ngroups);
+  const int64_t cta = blockIdx.x / (unsigned)p.ngroups, ncta = gridDim.x / (unsigned)p.ngroups;
+  const int pi_beg = grp * p.ppg, pi_end = pi_beg + p.ppg;
 
   if (warp == 0) {
     // =============================== MMA issuer ===============================
@@ -299,11 +307,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
     const uint32_t sA_u = smem_u32(sA);
     uint32_t st = 0, ph = 0;   // smem ring position / phase
     uint32_t tcount = 0;       // tile counter (TMEM accumulator buffer)
-    for (int pi = 0; pi < p.nprob; ++pi) {
+    for (int pi = pi_beg; pi < pi_end; ++pi) {
     asm volatile("bar.sync 2, 160;" ::: "memory");        // this problem's weights are in tensor memory
     tc_fence_after();
     if (lane == 0) {
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      for (int64_t tile = cta; tile < ntiles; tile += ncta, ++tcount) {
         const uint32_t buf = tcount & 1;
         mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -335,13 +343,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
     // 512 threads; thread (c16, r0) moves the 16-byte column chunk c16 of rows r0 + 64 i.
     const int pt = threadIdx.x - 32;                 // 0..511
     const int c16 = pt & 7, r0 = pt >> 3;            // 8 threads cover one 128-byte row segment
-    const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t my_tiles = cta < ntiles ? (ntiles - cta + ncta - 1) / ncta : 0;
     const int64_t nchunk = my_tiles * KC;
     const uint32_t sA_u = smem_u32(sA);
     constexpr int NV = kTileM * 8 / kProducerThreads;   // float4 per thread per chunk (2)
     constexpr int RS = kProducerThreads / 8;            // row stride between a thread's loads (64)
     uint32_t st = 0, ph = 0;
-    for (int pi = 0; pi < p.nprob; ++pi) {
+    for (int pi = pi_beg; pi < pi_end; ++pi) {
     const G1Prob& pr = p.prob[pi];
     const int64_t lda = pr.lda;
     const bool vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(pr.A) & 15) == 0);
@@ -352,9 +360,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
     for (int i = 0; i < NV; ++i) soff[i] = kmajor_off(r0 + RS * i, c16);
 
     // load cursor (tile row offset, K chunk) and ring cursor advance incrementally: no div/mod
-    int64_t ld_m0 = (int64_t)blockIdx.x * kTileM;     // restarts for every problem
+    int64_t ld_m0 = cta * kTileM;                     // restarts for every problem
     int ld_kc = 0;
-    const int64_t m_step = (int64_t)gridDim.x * kTileM;
+    const int64_t m_step = ncta * kTileM;
     auto issue = [&](float4 (&v)[NV]) {
       const int64_t m0 = ld_m0;
       const int kc0 = ld_kc * kChunkK;
@@ -424,13 +432,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
     const int n = q * 32 + lane;
     const bool nvalid = n < p.N;
     uint32_t tcount = 0;
-    for (int pi = 0; pi < p.nprob; ++pi) {
+    for (int pi = pi_beg; pi < pi_end; ++pi) {
     const G1Prob& pr = p.prob[pi];
     // every epilogue warp has waited for the previous problem's last accumulator, i.e. all MMAs that
     // read the old weights have retired: the loader warps may overwrite them
     if (ew < 4) load_weights(pr.W);
     const float bv = (pr.bias && nvalid) ? __ldg(pr.bias + n) : 0.f;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+    for (int64_t tile = cta; tile < ntiles; tile += ncta, ++tcount) {
       const uint32_t buf = tcount & 1;
       mbar_wait(&tfull[buf], (tcount >> 1) & 1);
       tc_fence_after();
@@ -475,15 +483,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
 }
 
 // ------------------------------------------------------------------ G2 (wgrad)
-struct G2Params {
+struct G2Prob {
   const float* Y;        // [rows, >=128] : the 128 columns starting at Y are the output rows (Dm)
   int64_t ldy;
   const float* X;        // [rows, N]
   int64_t ldx;
+  float* partial;        // [ctas per problem][128][N]
+  float* colsum;         // [ctas per problem][128] or NULL
+};
+// Up to kMaxProb weight gradients of identical shape (the four node-level ones: dW_q, dW_k, dW_v,
+// dW_skip) share one launch: CTA b works on problem b % nprob, row slab b / nprob.
+struct G2Params {
+  G2Prob prob[kMaxProb];
+  int nprob;
   int N, N_pad;          // N_pad multiple of 32, <= 128
   int64_t rows, rows_per_cta;   // rows_per_cta multiple of 32
-  float* partial;        // [grid][128][N]
-  float* colsum;         // [grid][128] or NULL
   int stages;
 };
 
@@ -512,6 +526,8 @@ __device__ __forceinline__ void tmem_st8f(uint32_t taddr, const float (&v)[8], b
 // Only X goes through shared memory (MN-major B operand), halving the smem traffic of the first
 // version, which was bound by shared-memory bandwidth (SS-mode MMAs re-read both operands 3 times).
 __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
+  const G2Prob& pr = p.prob[blockIdx.x % (unsigned)p.nprob];
+  const int64_t cta = blockIdx.x / (unsigned)p.nprob;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int S = p.stages;
@@ -540,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int64_t rbeg = (int64_t)blockIdx.x * p.rows_per_cta;
+  const int64_t rbeg = cta * p.rows_per_cta;
   const int64_t rend = min(p.rows, rbeg + p.rows_per_cta);
   const int64_t nchunks = rend > rbeg ? (rend - rbeg + kChunkK - 1) / kChunkK : 0;
 
@@ -574,12 +590,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
     const int q = warp & 3;                          // TMEM lane quarter of this warp
     const int g = (warp - 1) >> 2;                   // 8-row group of the chunk (0..3)
     const int d = q * 32 + lane;                     // output channel owned by this thread
-    const bool vecX = ((p.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) && ((p.N & 3) == 0);
+    const bool vecX = ((pr.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(pr.X) & 15) == 0) && ((p.N & 3) == 0);
     const int xq = p.N_pad / 4;                      // float4 per X row (8..32)
     const int nx = kChunkK * xq;                     // float4 per X chunk (256..1024)
     const uint32_t s_u = smem_u32(sS);
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + kG2YCol + 8 * g;
-    const float* const y_thr = p.Y + (int64_t)(8 * g) * p.ldy + d;
+    const float* const y_thr = pr.Y + (int64_t)(8 * g) * pr.ldy + d;
+    const int64_t ldy = pr.ldy;
     constexpr int NV = kChunkK * 32 / kProducerThreads;   // X float4 per thread per chunk (2)
     uint32_t xoff[NV];
     int xr[NV], xcol[NV];
@@ -595,13 +612,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
 
     auto issue = [&](float (&vy)[8], float4 (&vx)[NV], int64_t c) {
       const int64_t row0 = rbeg + c * kChunkK;
-      const float* ysrc = y_thr + row0 * p.ldy;
+      const float* ysrc = y_thr + row0 * ldy;
       if (row0 + kChunkK <= rend) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) vy[j] = __ldg(ysrc + (int64_t)j * p.ldy);
+        for (int j = 0; j < 8; ++j) vy[j] = __ldg(ysrc + (int64_t)j * ldy);
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) vy[j] = (row0 + 8 * g + j < rend) ? __ldg(ysrc + (int64_t)j * p.ldy) : 0.f;
+        for (int j = 0; j < 8; ++j) vy[j] = (row0 + 8 * g + j < rend) ? __ldg(ysrc + (int64_t)j * ldy) : 0.f;
       }
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
@@ -609,7 +626,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
         if (pt + i * kProducerThreads < nx) {
           const int64_t row = row0 + xr[i];
           if (row < rend) {
-            const float* qx = p.X + row * p.ldx + xcol[i];
+            const float* qx = pr.X + row * pr.ldx + xcol[i];
             if (vecX && xcol[i] + 3 < p.N) vx[i] = __ldg(reinterpret_cast<const float4*>(qx));
             else {
               if (xcol[i] < p.N) vx[i].x = __ldg(qx);
@@ -658,15 +675,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
       }
     }
     // column sums of Y over this CTA's rows: combine the 4 row groups in fixed order
-    if (p.colsum) {
+    if (pr.colsum) {
       cs_smem[g * 128 + d] = cs;
       asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
-      if (g == 0) p.colsum[(int64_t)blockIdx.x * 128 + d] = (cs_smem[d] + cs_smem[128 + d]) + (cs_smem[256 + d] + cs_smem[384 + d]);
+      if (g == 0) pr.colsum[cta * 128 + d] = (cs_smem[d] + cs_smem[128 + d]) + (cs_smem[256 + d] + cs_smem[384 + d]);
     }
   } else if (warp <= kProducerWarps + 4) {
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    float* dst = p.partial + ((int64_t)blockIdx.x * 128 + m) * p.N;
+    float* dst = pr.partial + (cta * 128 + m) * p.N;
     if (nchunks > 0) {
       mbar_wait(tfull, 0);
       tc_fence_after();
@@ -699,10 +716,14 @@ static inline size_t bimage_bytes(int K, int N) { (void)K; (void)N; return 256; 
 static inline bool g1_supported(int K, int N) { return K >= 1 && K <= 128 && N >= 1 && N <= 128; }
 
 // nprob problems C_i[M,N] (+)= A_i[M,K] . B_i(K,N) + bias_i, B_i(k,n) = W_i[k*sbk + n*sbn], in one launch.
-static int tc_gemm_batch(const G1Prob* probs, int nprob, int64_t M, int K, int64_t sbk, int64_t sbn, int N,
-                         cudaStream_t st) {
+// The problems are split into `ngroups` groups of nprob / ngroups consecutive problems (see G1Params).
+static int tc_gemm_batch(const G1Prob* probs, int nprob, int ngroups, int64_t M, int K, int64_t sbk, int64_t sbn,
+                         int N, cudaStream_t st) {
   if (M <= 0 || nprob <= 0) return X2_OK;
-  if (!g1_supported(K, N) || nprob > kMaxProb) { set_error("tc_gemm: unsupported K=%d N=%d nprob=%d", K, N, nprob); return X2_EINVAL; }
+  if (!g1_supported(K, N) || nprob > kMaxProb || ngroups < 1 || nprob % ngroups != 0) {
+    set_error("tc_gemm: unsupported K=%d N=%d nprob=%d ngroups=%d", K, N, nprob, ngroups);
+    return X2_EINVAL;
+  }
   const int stages = 5;                                   // 5 x 32 KB = 160 KB: stays under the 196 KB carve-out
   const size_t smem = 1024 + (size_t)stages * 2 * kChunkBytes + 256;
   static bool attr_set = false;
@@ -712,11 +733,12 @@ static int tc_gemm_batch(const G1Prob* probs, int nprob, int64_t M, int K, int64
   }
   G1Params p{};
   for (int i = 0; i < nprob; ++i) p.prob[i] = probs[i];
-  p.nprob = nprob;
+  p.nprob = nprob; p.ngroups = ngroups; p.ppg = nprob / ngroups;
   p.M = M; p.K = K; p.KC = (K + kChunkK - 1) / kChunkK;
   p.sbk = sbk; p.sbn = sbn; p.N = N; p.stages = stages;
   const int64_t ntiles = cdiv(M, kTileM);
-  const int grid = (int)(ntiles < kNumSM ? ntiles : kNumSM);
+  const int64_t per_group = kNumSM / ngroups;
+  const int grid = (int)(ntiles < per_group ? ntiles : per_group) * ngroups;
   k_tc_gemm<<<grid, kThreads, smem, st>>>(p);
   X2_LAUNCH_OK();
   return X2_OK;
@@ -727,35 +749,78 @@ static int tc_gemm(const float* A, int64_t lda, int64_t M, int K, const float* W
                    int N, const float* bias, float* C, int64_t ldc, int beta, void* img, cudaStream_t st) {
   (void)img;
   G1Prob pr{A, lda, W, bias, C, ldc, beta};
-  return tc_gemm_batch(&pr, 1, M, K, sbk, sbn, N, st);
+  return tc_gemm_batch(&pr, 1, 1, M, K, sbk, sbn, N, st);
 }
 
-static inline int wgrad_ctas(int64_t rows) {
+static inline int wgrad_ctas(int64_t rows, int nprob = 1) {
   int64_t c = cdiv(rows > 0 ? rows : 1, 256);     // >= 256 rows per CTA
-  if (c > kNumSM) c = kNumSM;
+  if (c > kNumSM / nprob) c = kNumSM / nprob;
   if (c < 1) c = 1;
   return (int)c;
 }
+// sized for the largest grid any batch may use (<= kNumSM CTAs in total)
 static inline size_t tc_wgrad_workspace_floats(int64_t rows, int N) {
-  return (size_t)wgrad_ctas(rows) * (128 * (size_t)N + 128) + 64;
+  (void)rows;
+  return (size_t)kNumSM * (128 * (size_t)N + 128) + 64;
 }
 
-}  // namespace tc
+struct G2Job {           // one weight gradient: dW[128,N] = Y^T X ; db[128] = colsum(Y) (db may be NULL)
+  const float* Y;
+  int64_t ldy;
+  const float* X;
+  int64_t ldx;
+  float* dW;
+  int64_t lddw;
+  float* db;
+};
 
-__global__ void k_splitk_reduce(const float* __restrict__ partial, const float* __restrict__ colsum,
-                                int splits, int64_t M, int N, float* __restrict__ out, int64_t ldo,
-                                float* __restrict__ bias);
-static inline unsigned splitk_reduce_blocks(int64_t M, int N, bool with_bias);
+struct ReduceBatch {
+  const float* partial[kMaxProb];
+  const float* colsum[kMaxProb];
+  float* out[kMaxProb];
+  float* bias[kMaxProb];
+  int64_t ldo[kMaxProb];
+};
 
-namespace tc {
+// Fixed-order reduction of the per-CTA partial tiles of up to kMaxProb weight gradients
+// (blockIdx.y = problem).  Same summation tree as k_splitk_reduce: warp g sums the splits g, g+8, ...
+// and the eight warp sums are added in order.
+__global__ void __launch_bounds__(256)
+k_splitk_reduce_batch(const ReduceBatch b, int splits, int64_t M, int N) {
+  __shared__ float red[8][33];
+  const int pi = blockIdx.y;
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int64_t MN = M * N;
+  const int64_t nblk_out = (MN + 31) / 32;
+  const bool is_bias = (int64_t)blockIdx.x >= nblk_out;      // trailing blocks reduce the column sums
+  const int64_t idx = is_bias ? ((int64_t)blockIdx.x - nblk_out) * 32 + lane : (int64_t)blockIdx.x * 32 + lane;
+  const int64_t lim = is_bias ? M : MN;
+  const float* src = is_bias ? b.colsum[pi] : b.partial[pi];
+  const bool live = idx < lim && src != nullptr;
+  float s = 0.f;
+  if (live)
+    for (int z = g; z < splits; z += 8) s += src[(int64_t)z * lim + idx];
+  red[g][lane] = s;
+  __syncthreads();
+  if (g == 0 && live) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += red[k][lane];
+    if (is_bias) b.bias[pi][idx] = t;
+    else {
+      const int64_t m = idx / N;
+      b.out[pi][m * b.ldo[pi] + (idx - m * N)] = t;
+    }
+  }
+}
 
-// dW[128,N] = Y[rows,128]^T X[rows,N] ; db[128] = colsum(Y)  (db may be NULL).  ws: tc_wgrad_workspace_floats
-static int tc_wgrad(const float* Y, int64_t ldy, const float* X, int64_t ldx, int64_t rows, int N, float* dW,
-                    int64_t lddw, float* db, float* ws, cudaStream_t st) {
-  if (N < 1 || N > 128) { set_error("tc_wgrad: unsupported N=%d", N); return X2_EINVAL; }
+// nprob weight gradients over the same `rows` and the same N in one launch + one reduction launch.
+// ws: tc_wgrad_workspace_floats
+static int tc_wgrad_batch(const G2Job* jobs, int nprob, int64_t rows, int N, float* ws, cudaStream_t st) {
+  if (N < 1 || N > 128 || nprob < 1 || nprob > kMaxProb) { set_error("tc_wgrad: unsupported N=%d nprob=%d", N, nprob); return X2_EINVAL; }
   const int N_pad = ceil_to(N, 32);
-  const int grid = wgrad_ctas(rows);
-  const int64_t rpc = cdiv(cdiv(rows > 0 ? rows : 1, grid), kChunkK) * kChunkK;
+  const int cpp = wgrad_ctas(rows, nprob);                              // CTAs per problem
+  const int64_t rpc = cdiv(cdiv(rows > 0 ? rows : 1, cpp), kChunkK) * kChunkK;
   const uint32_t stage_bytes = 2 * (uint32_t)(N_pad / 32) * 4096;      // X hi | X lo (Y^T lives in tensor memory)
   const int stages = 4;                                                 // <= 128 KB smem, 4 x 64 TMEM columns
   const size_t smem = 1024 + (size_t)stages * stage_bytes + 256 + 4 * 128 * sizeof(float);
@@ -764,14 +829,32 @@ static int tc_wgrad(const float* Y, int64_t ldy, const float* X, int64_t ldx, in
     X2_CUDA_OK(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     attr_set = true;
   }
-  G2Params p;
-  p.Y = Y; p.ldy = ldy; p.X = X; p.ldx = ldx; p.N = N; p.N_pad = N_pad; p.rows = rows; p.rows_per_cta = rpc;
-  p.partial = ws; p.colsum = db ? ws + (size_t)grid * 128 * N : nullptr; p.stages = stages;
-  k_tc_wgrad<<<grid, kThreads, smem, st>>>(p);
+  G2Params p{};
+  ReduceBatch rb{};
+  bool any_bias = false;
+  const size_t per_prob = (size_t)cpp * (128 * (size_t)N + 128);
+  for (int i = 0; i < nprob; ++i) {
+    float* base = ws + (size_t)i * per_prob;
+    p.prob[i] = G2Prob{jobs[i].Y, jobs[i].ldy, jobs[i].X, jobs[i].ldx, base,
+                       jobs[i].db ? base + (size_t)cpp * 128 * N : nullptr};
+    rb.partial[i] = p.prob[i].partial; rb.colsum[i] = p.prob[i].colsum;
+    rb.out[i] = jobs[i].dW; rb.ldo[i] = jobs[i].lddw; rb.bias[i] = jobs[i].db;
+    any_bias |= jobs[i].db != nullptr;
+  }
+  p.nprob = nprob; p.N = N; p.N_pad = N_pad; p.rows = rows; p.rows_per_cta = rpc; p.stages = stages;
+  k_tc_wgrad<<<cpp * nprob, kThreads, smem, st>>>(p);
   X2_LAUNCH_OK();
-  k_splitk_reduce<<<splitk_reduce_blocks(128, N, db != nullptr), 256, 0, st>>>(ws, p.colsum, grid, 128, N, dW, lddw, db);
+  const unsigned nblk = (unsigned)((128 * (int64_t)N + 31) / 32 + (any_bias ? 4 : 0));
+  k_splitk_reduce_batch<<<dim3(nblk, (unsigned)nprob), 256, 0, st>>>(rb, cpp, 128, N);
   X2_LAUNCH_OK();
   return X2_OK;
+}
+
+// dW[128,N] = Y[rows,128]^T X[rows,N] ; db[128] = colsum(Y)  (db may be NULL).  ws: tc_wgrad_workspace_floats
+static int tc_wgrad(const float* Y, int64_t ldy, const float* X, int64_t ldx, int64_t rows, int N, float* dW,
+                    int64_t lddw, float* db, float* ws, cudaStream_t st) {
+  const G2Job job{Y, ldy, X, ldx, dW, lddw, db};
+  return tc_wgrad_batch(&job, 1, rows, N, ws, st);
 }
 
 }  // namespace tc

@@ -180,6 +180,15 @@ typedef struct {
   const float *w_edge;             /* [D,A] or NULL */
   const float *w_sbf, *b_sbf;      /* [D,S], [D] */
   const float *w_skip, *b_skip;    /* [D,D], [D] (b_skip may be NULL); used iff fuse_skip */
+  /* Optional segment-constant edge features (opt-in fast path for callers whose edge_attr row is the
+   * same for every triplet of a target line-node, as in xgnn.py:57-58 where it is a function of the
+   * central atom only).  ea_index == NULL: edge_attr is [T,A] as in the reference.  ea_index != NULL:
+   * edge_attr is a table [ea_rows, A]; every triplet of target e uses row ea_index[e] (int32 [E]);
+   * ea_rowptr[ea_rows+1] / ea_order[E] group the targets by table row, ascending inside a group
+   * (x2_meta_build on the [2,E] index [ea_index; ea_index] with ea_rows nodes: its rowptr_src /
+   * order_src).  Then saved.ea is [ea_rows, D] and grads.dedge_attr is [ea_rows, A]. */
+  int64_t ea_rows;
+  const int32_t *ea_index, *ea_rowptr, *ea_order;
 } x2_conv_desc;
 
 #define X2_MODE_FP32 0    /* fp32 SIMT arithmetic everywhere (1e-5 parity) */

@@ -222,6 +222,64 @@ def test_sbf_without_grad_and_frozen_inputs():
     assert relerr(xs["x"].grad, x_ref["x"].grad) < FP32_TOL
 
 
+@pytest.mark.parametrize("dims,mode", [((128, 16, 42, 6, 128), "tf32x3"), ((128, 16, 42, 6, 128), "fp32"),
+                                       ((64, 8, 10, 3, 20), "fp32"), ((256, 16, 112, 16, 128), "tf32x3")])
+@pytest.mark.parametrize("rows", ["atoms", "few"])
+def test_segment_constant_edge_attr_table(dims, mode, rows):
+    """Opt-in fast path: edge_attr as a table [M, A] + edge_attr_index [E] must equal
+    the reference layer fed the expanded edge_attr[edge_attr_index[edge_index[1]]] ([T, A]), including the
+    gradient w.r.t. the table (= index_add of the per-triplet gradient) and every parameter gradient."""
+    from x2gnn_b200 import synth
+    D, H, S, R, A = dims
+    ref, mine = _oracle_pair(dims, seed=20, mode=mode)
+    b = synth.qm9_batch(5, seed=21)
+    rec = _graph_inputs(5, dims, seed=21)
+    E = rec["x"].size(0)
+    g = torch.Generator().manual_seed(22)
+    if rows == "atoms":      # xgnn.py:57-58: the row is a function of the bond's second (central) atom
+        index = torch.from_numpy(b["edge_index"][1]).long()
+        M = len(b["x"])
+    else:                    # a handful of distinct rows (one per element), some rows unused
+        M = 7
+        index = torch.randint(0, 5, (E,), generator=g)
+    table = torch.randn(M, A, generator=g)
+    tgt = rec["edge_index"][1]
+
+    tab_ref = table.double().requires_grad_(True)
+    xs_ref = {k: rec[k].double().requires_grad_(True) for k in ("x", "rbf", "sbf")}
+    o_ref = ref(xs_ref["sbf"], xs_ref["rbf"], x=xs_ref["x"], edge_index=rec["edge_index"],
+                edge_attr=tab_ref[index[tgt]])
+    o_ref.backward(rec["grad_out"].double())
+
+    mine.zero_grad(set_to_none=True)
+    tab = table.cuda().requires_grad_(True)
+    xs = {k: rec[k].cuda().requires_grad_(True) for k in ("x", "rbf", "sbf")}
+    o, (_, alpha) = mine(xs["sbf"], xs["rbf"], x=xs["x"], edge_index=rec["edge_index"].cuda(), edge_attr=tab,
+                         edge_attr_index=index.cuda(), return_attention_weights=True)
+    o.backward(rec["grad_out"].cuda())
+    assert relerr(o, o_ref) < FP32_TOL
+    assert tab.grad.shape == table.shape
+    assert relerr(tab.grad, tab_ref.grad) < FP32_TOL
+    for k in xs:
+        assert relerr(xs[k].grad, xs_ref[k].grad) < FP32_TOL, k
+    pm = dict(mine.named_parameters())
+    for k, p in ref.named_parameters():
+        if k == "lin_key.bias":
+            continue
+        assert relerr(pm[k].grad, p.grad) < FP32_TOL, k
+    # and it is the same function as the [T, A] form of this implementation
+    with torch.no_grad():
+        o_full = mine(xs["sbf"], xs["rbf"], x=xs["x"], edge_index=rec["edge_index"].cuda(),
+                      edge_attr=tab[index.cuda()[tgt.cuda()]])
+    assert relerr(o, o_full) < 2e-6
+    with pytest.raises(IndexError):
+        mine(xs["sbf"], xs["rbf"], x=xs["x"], edge_index=rec["edge_index"].cuda(), edge_attr=tab,
+             edge_attr_index=(index + M).cuda())
+    with pytest.raises(ValueError):
+        mine(xs["sbf"], xs["rbf"], x=xs["x"], edge_index=rec["edge_index"].cuda(), edge_attr=tab,
+             edge_attr_index=index[:-1].cuda())
+
+
 def test_dropout_training_directional_derivative():
     dims = (64, 8, 10, 3, 20)
     _, mine = _oracle_pair(dims, seed=16, dropout=0.3)

@@ -39,6 +39,7 @@ class ConvDesc(C.Structure):
         ("w_rbf", c_f32p), ("w_q", c_f32p), ("b_q", c_f32p), ("w_k", c_f32p), ("b_k", c_f32p),
         ("w_v", c_f32p), ("b_v", c_f32p), ("w_edge", c_f32p), ("w_sbf", c_f32p), ("b_sbf", c_f32p),
         ("w_skip", c_f32p), ("b_skip", c_f32p),
+        ("ea_rows", C.c_int64), ("ea_index", c_i32p), ("ea_rowptr", c_i32p), ("ea_order", c_i32p),
     ]
 
 

@@ -128,9 +128,12 @@ __global__ void k_filter_bwd_sum(const float4* __restrict__ x, const float4* __r
 }
 
 // ------------------------------------------------------------------ segmented attention fwd
-template <int VEC>
+// SEG: `ea` is a table and every triplet of target e uses its row ea_index[e] (segment-constant edge
+// features): the row is loaded once per segment instead of one row per triplet.
+template <int VEC, bool SEG>
 __global__ void __launch_bounds__(128)
 k_attn_fwd(const float* __restrict__ qkvs, int ldq, const float* __restrict__ ea,
+           const int32_t* __restrict__ ea_index,
            const float* __restrict__ sg, const int32_t* __restrict__ src,
            const int32_t* __restrict__ rowptr, const int32_t* __restrict__ order, int64_t E, int H,
            int C, float scale, int fuse_skip, float dropout_p, uint64_t seed,
@@ -153,6 +156,10 @@ k_attn_fwd(const float* __restrict__ qkvs, int ldq, const float* __restrict__ ea
   float acc[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  float a_[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) a_[j] = 0.f;
+  if constexpr (SEG) ldv<VEC>(ea + (int64_t)ea_index[e] * D + ch, a_);
 
   for (int base = beg; base < end; base += 32) {
     const int my = base + lane;
@@ -166,14 +173,12 @@ k_attn_fwd(const float* __restrict__ qkvs, int ldq, const float* __restrict__ ea
     for (int i = 0; i < cnt; ++i) {
       const int t = __shfl_sync(0xffffffffu, t_l, i);
       const int s = __shfl_sync(0xffffffffu, s_l, i);
-      float k[VEC], v[VEC], g[VEC], a_[VEC];
+      float k[VEC], v[VEC], g[VEC];
       ldv<VEC>(qkvs + (int64_t)s * ldq + D + ch, k);
       ldv<VEC>(qkvs + (int64_t)s * ldq + 2 * D + ch, v);
       ldv<VEC>(sg + (int64_t)t * D + ch, g);
-      if (ea) ldv<VEC>(ea + (int64_t)t * D + ch, a_);
-      else {
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) a_[j] = 0.f;
+      if constexpr (!SEG) {
+        if (ea) ldv<VEC>(ea + (int64_t)t * D + ch, a_);
       }
       float dot = 0.f;
 #pragma unroll
@@ -218,9 +223,12 @@ k_attn_fwd(const float* __restrict__ qkvs, int ldq, const float* __restrict__ ea
 }
 
 // ------------------------------------------------------------------ backward pass 1 (by target)
-template <int VEC>
+// SEG (see k_attn_fwd): d(lin_edge out) is summed over the segment in registers and written as ONE
+// row per target, dea[e, :] -- the per-triplet [T, D] stream disappears.
+template <int VEC, bool SEG>
 __global__ void __launch_bounds__(128)
 k_attn_bwd_tgt(const float* __restrict__ qkvs, int ldq, const float* __restrict__ ea,
+               const int32_t* __restrict__ ea_index,
                const float* __restrict__ sg, const float* __restrict__ attn,
                const float* __restrict__ lse, const float* __restrict__ gout,
                const int32_t* __restrict__ src, const int32_t* __restrict__ rowptr,
@@ -250,6 +258,10 @@ k_attn_bwd_tgt(const float* __restrict__ qkvs, int ldq, const float* __restrict_
   r = head_sum(r, lph);                       // r_eh = sum_t alpha dalpha = <G, O>  (App. A)
   const float l = lse[e * H + head];
   const int beg = rowptr[e], end = rowptr[e + 1];
+  float a_[VEC], dea_acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) a_[j] = dea_acc[j] = 0.f;
+  if constexpr (SEG) ldv<VEC>(ea + (int64_t)ea_index[e] * D + ch, a_);
 
   for (int base = beg; base < end; base += 32) {
     const int my = base + lane;
@@ -263,14 +275,12 @@ k_attn_bwd_tgt(const float* __restrict__ qkvs, int ldq, const float* __restrict_
     for (int i = 0; i < cnt; ++i) {
       const int t = __shfl_sync(0xffffffffu, t_l, i);
       const int s = __shfl_sync(0xffffffffu, s_l, i);
-      float k[VEC], v[VEC], sgv[VEC], a_[VEC];
+      float k[VEC], v[VEC], sgv[VEC];
       ldv<VEC>(qkvs + (int64_t)s * ldq + D + ch, k);
       ldv<VEC>(qkvs + (int64_t)s * ldq + 2 * D + ch, v);
       ldv<VEC>(sg + (int64_t)t * D + ch, sgv);
-      if (ea) ldv<VEC>(ea + (int64_t)t * D + ch, a_);
-      else {
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) a_[j] = 0.f;
+      if constexpr (!SEG) {
+        if (ea) ldv<VEC>(ea + (int64_t)t * D + ch, a_);
       }
       float dot = 0.f, dal = 0.f;
 #pragma unroll
@@ -300,7 +310,12 @@ k_attn_bwd_tgt(const float* __restrict__ qkvs, int ldq, const float* __restrict_
         o_ea[j] = dkk + dvv;
         o_sg[j] = g[j] * v[j] * alpha_d;
       }
-      if (dea) stv<VEC>(dea + (int64_t)t * D + ch, o_ea);
+      if constexpr (SEG) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) dea_acc[j] += o_ea[j];
+      } else {
+        if (dea) stv<VEC>(dea + (int64_t)t * D + ch, o_ea);
+      }
       stv<VEC>(dsg + (int64_t)t * D + ch, o_sg);
       if (leader) {
         al[(int64_t)t * H + head] = alpha_d;
@@ -309,6 +324,31 @@ k_attn_bwd_tgt(const float* __restrict__ qkvs, int ldq, const float* __restrict_
     }
   }
   stv<VEC>(dqkv + e * ldg + ch, dq);
+  if constexpr (SEG) stv<VEC>(dea + e * D + ch, dea_acc);
+}
+
+// out[m, :] = sum of in[order[i], :] over i in [rowptr[m], rowptr[m+1]) in that (ascending) order: the
+// per-target d(lin_edge out) rows summed per edge_attr table row.  Warp per output row, deterministic.
+template <int VEC>
+__global__ void __launch_bounds__(128)
+k_rows_segsum(const float* __restrict__ in, const int32_t* __restrict__ rowptr,
+              const int32_t* __restrict__ order, int64_t M, float* __restrict__ out) {
+  constexpr int D = 32 * VEC;
+  const int64_t m = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (m >= M) return;
+  const int ch = (threadIdx.x & 31) * VEC;
+  float acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+  const int beg = rowptr[m], end = rowptr[m + 1];
+#pragma unroll 4
+  for (int i = beg; i < end; ++i) {
+    float v[VEC];
+    ldv<VEC>(in + (int64_t)order[i] * D + ch, v);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] += v[j];
+  }
+  stv<VEC>(out + m * D + ch, acc);
 }
 
 // ------------------------------------------------------------------ backward pass 2 (by source)
@@ -432,6 +472,11 @@ static int check_desc(const x2_conv_desc* d) {
   X2_CHECK_ARG(d->S >= 1 && d->R >= 1 && d->R <= 64 && d->A >= 0, "conv: bad S/R/A (need 1 <= R <= 64)");
   X2_CHECK_ARG(d->dropout_p >= 0.f && d->dropout_p < 1.f, "conv: dropout must be in [0,1)");
   X2_CHECK_ARG((d->A > 0) == (d->w_edge != nullptr), "conv: w_edge must be given iff A > 0");
+  if (d->ea_index) {
+    X2_CHECK_ARG(d->A > 0, "conv: ea_index (segment-constant edge_attr) needs edge_dim > 0");
+    X2_CHECK_ARG(d->ea_rows >= 1 && d->ea_rows < 2147483647LL, "conv: bad ea_rows");
+    X2_CHECK_ARG(d->ea_rowptr && d->ea_order, "conv: ea_index needs the ea_rowptr / ea_order grouping");
+  }
   return X2_OK;
 }
 
@@ -445,14 +490,16 @@ static size_t fwd_layout(const x2_conv_desc* d, void* ws, FwdWs* w) {
 }
 
 struct BwdWs {
-  float *dea, *dsg, *al, *da, *dqkv, *xs, *F, *dxs, *dxs2, *dx2, *wg;
+  float *dea, *dea_tab, *dsg, *al, *da, *dqkv, *xs, *F, *dxs, *dxs2, *dx2, *wg;
   void* img;
   size_t wg_floats;
 };
 static size_t bwd_layout(const x2_conv_desc* d, void* ws, BwdWs* w) {
   Arena a(ws, (size_t)-1);
   const size_t ED = (size_t)d->E * d->D, TD = (size_t)d->T * d->D, TH = (size_t)d->T * d->H;
-  w->dea = d->A > 0 ? a.take<float>(TD + 4) : nullptr;
+  // segment-constant edge_attr: one d(lin_edge out) row per target + one per table row
+  w->dea = d->A > 0 ? a.take<float>((d->ea_index ? ED : TD) + 4) : nullptr;
+  w->dea_tab = d->ea_index ? a.take<float>((size_t)d->ea_rows * d->D + 4) : nullptr;
   w->dsg = a.take<float>(TD + 4);
   w->al = a.take<float>(TH + 4);
   w->da = a.take<float>(TH + 4);
@@ -481,9 +528,15 @@ template <int VEC>
 static int launch_attn_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, float* alpha,
                            cudaStream_t st) {
   const float scale = 1.0f / sqrtf((float)d->C);
-  k_attn_fwd<VEC><<<(unsigned)cdiv(d->E * 32, 128), 128, 0, st>>>(
-      s->qkvs, 4 * d->D, d->A > 0 ? s->ea : nullptr, s->sg, d->src, d->rowptr_tgt, d->order_tgt, d->E,
-      d->H, d->C, scale, d->fuse_skip, d->dropout_p, d->seed, s->attn, out, s->lse, alpha);
+  const unsigned grid = (unsigned)cdiv(d->E * 32, 128);
+  if (d->ea_index)
+    k_attn_fwd<VEC, true><<<grid, 128, 0, st>>>(
+        s->qkvs, 4 * d->D, s->ea, d->ea_index, s->sg, d->src, d->rowptr_tgt, d->order_tgt, d->E,
+        d->H, d->C, scale, d->fuse_skip, d->dropout_p, d->seed, s->attn, out, s->lse, alpha);
+  else
+    k_attn_fwd<VEC, false><<<grid, 128, 0, st>>>(
+        s->qkvs, 4 * d->D, d->A > 0 ? s->ea : nullptr, nullptr, s->sg, d->src, d->rowptr_tgt, d->order_tgt, d->E,
+        d->H, d->C, scale, d->fuse_skip, d->dropout_p, d->seed, s->attn, out, s->lse, alpha);
   X2_LAUNCH_OK();
   return X2_OK;
 }
@@ -494,11 +547,22 @@ static int launch_attn_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const 
   const float scale = 1.0f / sqrtf((float)d->C);
   const unsigned grid = (unsigned)cdiv(d->E * 32, 128);
   phase_begin(st);
-  k_attn_bwd_tgt<VEC><<<grid, 128, 0, st>>>(s->qkvs, 4 * d->D, d->A > 0 ? s->ea : nullptr, s->sg, s->attn,
-                                            s->lse, gout, d->src, d->rowptr_tgt, d->order_tgt, d->E, d->H,
-                                            d->C, scale, d->dropout_p, d->seed, w.dqkv, 3 * d->D, w.dea,
-                                            w.dsg, w.al, w.da);
+  if (d->ea_index)
+    k_attn_bwd_tgt<VEC, true><<<grid, 128, 0, st>>>(s->qkvs, 4 * d->D, s->ea, d->ea_index, s->sg, s->attn,
+                                                    s->lse, gout, d->src, d->rowptr_tgt, d->order_tgt, d->E,
+                                                    d->H, d->C, scale, d->dropout_p, d->seed, w.dqkv, 3 * d->D,
+                                                    w.dea, w.dsg, w.al, w.da);
+  else
+    k_attn_bwd_tgt<VEC, false><<<grid, 128, 0, st>>>(s->qkvs, 4 * d->D, d->A > 0 ? s->ea : nullptr, nullptr,
+                                                     s->sg, s->attn, s->lse, gout, d->src, d->rowptr_tgt,
+                                                     d->order_tgt, d->E, d->H, d->C, scale, d->dropout_p,
+                                                     d->seed, w.dqkv, 3 * d->D, w.dea, w.dsg, w.al, w.da);
   X2_LAUNCH_OK();
+  if (d->ea_index) {       // per-target rows -> per-table-row sums (fixed order)
+    k_rows_segsum<VEC><<<(unsigned)cdiv(d->ea_rows * 32, 128), 128, 0, st>>>(w.dea, d->ea_rowptr, d->ea_order,
+                                                                             d->ea_rows, w.dea_tab);
+    X2_LAUNCH_OK();
+  }
   phase_end(X2_PHASE_ATTN_BWD_TGT, st);
   k_attn_bwd_src<VEC><<<grid, 128, 0, st>>>(s->qkvs, 4 * d->D, s->sg, gout, w.al, w.da, d->tgt,
                                             d->rowptr_src, d->order_src, d->E, d->H, d->C, scale, w.dqkv,
@@ -609,6 +673,7 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
   // unfused pair today -- with lane = channel the four epilogue warps of a stream each execute the whole
   // per-triplet instruction sequence (profiles/r1_notes.md).
   if (d->mode == X2_MODE_TF32X3_FUSED && d->tgt_sorted && T > 0 && d->dropout_p == 0.f && alpha == nullptr &&
+      d->ea_index == nullptr &&
       tc::fused_fwd_supported(D, d->H, d->C, d->A, d->S)) {
     tc::F1Params f{};
     f.ea = d->edge_attr; f.ld_ea = d->A; f.A = d->A;
@@ -625,8 +690,10 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
     return X2_OK;
   }
   // (3) T-row projections                                                    :144, :148
+  // segment-constant edge_attr: lin_edge runs on the table rows only
+  if (d->ea_index) X2_TRY(lin_fwd(L, d->edge_attr, d->A, d->w_edge, d->A, nullptr, s->ea, D, d->ea_rows, D, d->A));
   if (T > 0) {
-    if (d->A > 0) X2_TRY(lin_fwd(L, d->edge_attr, d->A, d->w_edge, d->A, nullptr, s->ea, D, T, D, d->A));
+    if (d->A > 0 && !d->ea_index) X2_TRY(lin_fwd(L, d->edge_attr, d->A, d->w_edge, d->A, nullptr, s->ea, D, T, D, d->A));
     X2_TRY(lin_fwd(L, d->sbf, d->S, d->w_sbf, d->S, d->b_sbf, s->sg, D, T, D, d->S));
   }
   phase_end(X2_PHASE_TROW_PROJ, st);
@@ -665,6 +732,7 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
     for (float* p : bs_) if (p) X2_CUDA_OK(cudaMemsetAsync(p, 0, sizeof(float) * D, st));
     if (A > 0) X2_CUDA_OK(cudaMemsetAsync(g->dw_edge, 0, sizeof(float) * D * A, st));
     X2_CUDA_OK(cudaMemsetAsync(g->dw_sbf, 0, sizeof(float) * D * S, st));
+    if (d->ea_index && g->dedge_attr) X2_CUDA_OK(cudaMemsetAsync(g->dedge_attr, 0, sizeof(float) * d->ea_rows * A, st));
     return X2_OK;
   }
 
@@ -681,11 +749,13 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
 
   const Lin L{lin_mode(d->mode), w.img, w.wg, st};
   // (3) T-row input gradients
-  if (A > 0 && g->dedge_attr && T > 0) X2_TRY(lin_dgrad(L, w.dea, D, d->w_edge, A, g->dedge_attr, A, T, A, D, 0));
+  const float* dea_rows = d->ea_index ? w.dea_tab : w.dea;          // rows lin_edge was applied to
+  const int64_t n_ea = d->ea_index ? d->ea_rows : T;
+  if (A > 0 && g->dedge_attr && n_ea > 0) X2_TRY(lin_dgrad(L, dea_rows, D, d->w_edge, A, g->dedge_attr, A, n_ea, A, D, 0));
   if (g->dsbf && T > 0) X2_TRY(lin_dgrad(L, w.dsg, D, d->w_sbf, S, g->dsbf, S, T, S, D, 0));
   phase_end(X2_PHASE_TROW_DGRAD, st);
   // (4) T-row weight gradients (split-K over triplets, fixed-order reduction)
-  if (A > 0) X2_TRY(lin_wgrad(L, w.dea, D, d->edge_attr, A, g->dw_edge, A, nullptr, T, D, A));
+  if (A > 0) X2_TRY(lin_wgrad(L, dea_rows, D, d->edge_attr, A, g->dw_edge, A, nullptr, n_ea, D, A));
   X2_TRY(lin_wgrad(L, w.dsg, D, d->sbf, S, g->dw_sbf, S, g->db_sbf, T, D, S));
 
   phase_end(X2_PHASE_TROW_WGRAD, st);

@@ -204,6 +204,7 @@ constexpr int kTmemWHi = 256;        // TMEM columns [256, 384): W_hi ; [384, 51
 constexpr int kTmemWLo = 384;
 
 constexpr int kMaxProb = 4;
+constexpr int kG1Flight = 3;         // chunks of global loads in flight per producer thread
 struct G1Prob {
   const float* A;        // streamed activations X[M, K]
   int64_t lda;
@@ -404,20 +405,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
       if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
     };
 
-    // three chunks of loads in flight per thread
-    float4 va[NV], vb[NV], vc[NV];
-    if (nchunk > 0) issue(va);
-    if (nchunk > 1) issue(vb);
-    for (int64_t it = 0; it < nchunk; it += 3) {
-      if (it + 2 < nchunk) issue(vc);
-      commit(va);
-      if (it + 1 < nchunk) {
-        if (it + 3 < nchunk) issue(va);
-        commit(vb);
-      }
-      if (it + 2 < nchunk) {
-        if (it + 4 < nchunk) issue(vb);
-        commit(vc);
+    // kG1Flight chunks of loads in flight per thread (register ring, statically indexed)
+    float4 v[kG1Flight][NV];
+#pragma unroll
+    for (int u = 0; u < kG1Flight - 1; ++u)
+      if (u < nchunk) issue(v[u]);
+    for (int64_t it = 0; it < nchunk; it += kG1Flight) {
+#pragma unroll
+      for (int u = 0; u < kG1Flight; ++u) {
+        if (it + u < nchunk) {
+          if (it + u + kG1Flight - 1 < nchunk) issue(v[(u + kG1Flight - 1) % kG1Flight]);
+          commit(v[u]);
+        }
       }
     }
     }
@@ -525,7 +524,11 @@ __device__ __forceinline__ void tmem_st8f(uint32_t taddr, const float (&v)[8], b
 // 8g..8g+7 of every 32-row chunk, loads them coalesced across lanes and writes them with tcgen05.st.
 // Only X goes through shared memory (MN-major B operand), halving the smem traffic of the first
 // version, which was bound by shared-memory bandwidth (SS-mode MMAs re-read both operands 3 times).
-__global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
+// warp 0 = MMA issuer, then epilogue of lane quarter 0; warps 1..16 producers; warps 17..19 epilogue of
+// quarters 1..3.  20 warps: the register file is allocated in groups of 4 warps, so 21 would cap a
+// thread at 80 registers instead of 96 (three chunks of loads in flight need ~90).
+constexpr int kG2Threads = 32 + kProducerThreads + 3 * 32;
+__global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
   const G2Prob& pr = p.prob[blockIdx.x % (unsigned)p.nprob];
   const int64_t cta = blockIdx.x / (unsigned)p.nprob;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -585,6 +588,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
       }
       umma_commit(tfull);
     }
+    __syncwarp();
   } else if (warp <= kProducerWarps) {
     const int pt = threadIdx.x - 32;                 // 0..511
     const int q = warp & 3;                          // TMEM lane quarter of this warp
@@ -663,15 +667,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
       if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
     };
 
-    float ya[8], yb[8];
-    float4 xa[NV], xb_[NV];
+    // three chunks of loads in flight per thread
+    float ya[8], yb[8], yc[8];
+    float4 xa[NV], xb_[NV], xc[NV];
     if (nchunks > 0) issue(ya, xa, 0);
-    for (int64_t c = 0; c < nchunks; c += 2) {
-      if (c + 1 < nchunks) issue(yb, xb_, c + 1);
+    if (nchunks > 1) issue(yb, xb_, 1);
+    for (int64_t c = 0; c < nchunks; c += 3) {
+      if (c + 2 < nchunks) issue(yc, xc, c + 2);
       commit(ya, xa);
       if (c + 1 < nchunks) {
-        if (c + 2 < nchunks) issue(ya, xa, c + 2);
+        if (c + 3 < nchunks) issue(ya, xa, c + 3);
         commit(yb, xb_);
+      }
+      if (c + 2 < nchunks) {
+        if (c + 4 < nchunks) issue(yb, xb_, c + 4);
+        commit(yc, xc);
       }
     }
     // column sums of Y over this CTA's rows: combine the 4 row groups in fixed order
@@ -680,7 +690,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_wgrad(const G2Params p) {
       asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
       if (g == 0) pr.colsum[cta * 128 + d] = (cs_smem[d] + cs_smem[128 + d]) + (cs_smem[256 + d] + cs_smem[384 + d]);
     }
-  } else if (warp <= kProducerWarps + 4) {
+  }
+  if (warp == 0 || warp > kProducerWarps) {
+    // =============================== epilogue: accumulator -> this CTA's partial tile
     const int q = warp & 3;
     const int m = q * 32 + lane;
     float* dst = pr.partial + (cta * 128 + m) * p.N;
@@ -842,7 +854,7 @@ static int tc_wgrad_batch(const G2Job* jobs, int nprob, int64_t rows, int N, flo
     any_bias |= jobs[i].db != nullptr;
   }
   p.nprob = nprob; p.N = N; p.N_pad = N_pad; p.rows = rows; p.rows_per_cta = rpc; p.stages = stages;
-  k_tc_wgrad<<<cpp * nprob, kThreads, smem, st>>>(p);
+  k_tc_wgrad<<<cpp * nprob, kG2Threads, smem, st>>>(p);
   X2_LAUNCH_OK();
   const unsigned nblk = (unsigned)((128 * (int64_t)N + 31) / 32 + (any_bias ? 4 : 0));
   k_splitk_reduce_batch<<<dim3(nblk, (unsigned)nprob), 256, 0, st>>>(rb, cpp, 128, N);

@@ -73,5 +73,37 @@ def get(edge_index: torch.Tensor, num_nodes: int) -> LineGraphMeta:
     return meta
 
 
+@dataclass
+class RowGroups:
+    """Targets grouped by the `edge_attr` table row they use (segment-constant edge features)."""
+    rows: int
+    index: torch.Tensor        # [E] int32: table row of every target line-node
+    rowptr: torch.Tensor       # [rows+1] int32
+    order: torch.Tensor        # [E] int32: target ids grouped by table row, ascending inside a group
+
+
+_group_cache: list = []
+
+
+def get_groups(index: torch.Tensor, rows: int) -> RowGroups:
+    """Cached grouping of `index` [E] (values in [0, rows)) with the same integer kernels that build the
+    line-graph metadata (x2_meta_build on the [2, E] index [index; index] with `rows` nodes)."""
+    if index.dim() != 1:
+        raise ValueError(f"edge_attr_index must be one-dimensional, got {tuple(index.shape)}")
+    ver = index._version
+    for i, (ref, v, n, grp) in enumerate(_group_cache):
+        if ref() is index and v == ver and n == rows:
+            if i:
+                _group_cache.insert(0, _group_cache.pop(i))
+            return grp
+    idx = index.long()
+    meta = build(torch.stack([idx, idx]), rows)       # raises IndexError on out-of-range rows
+    grp = RowGroups(rows, meta.src, meta.rowptr_src, meta.order_src)
+    _group_cache.insert(0, (weakref.ref(index), ver, rows, grp))
+    del _group_cache[_CACHE_SIZE:]
+    return grp
+
+
 def clear_cache():
     _cache.clear()
+    _group_cache.clear()

@@ -47,6 +47,15 @@ def Glorot_Ortho_(tensor: Tensor, scale: float = 2.0) -> Tensor:
     return tensor
 
 
+def _set_groups(desc, groups):
+    if groups is None:
+        desc.ea_rows, desc.ea_index, desc.ea_rowptr, desc.ea_order = 0, None, None, None
+    else:
+        desc.ea_rows = groups.rows
+        desc.ea_index, desc.ea_rowptr, desc.ea_order = (_lib.ptr(groups.index), _lib.ptr(groups.rowptr),
+                                                         _lib.ptr(groups.order))
+
+
 class _SBFConvFn(torch.autograd.Function):
     """out/attn = conv(x, rbf, sbf, edge_attr; weights).  Non-tensor config rides in `cfg`."""
 
@@ -66,9 +75,15 @@ class _SBFConvFn(torch.autograd.Function):
         A = t["edge_attr"].size(1) if t["w_edge"] is not None else 0
         if meta.E != E:
             raise ValueError(f"edge_index was indexed for {meta.E} nodes but x has {E} rows")
-        if t["sbf"].size(0) != T or (A and t["edge_attr"].size(0) != T) or t["rbf"].size(0) != E:
+        groups = cfg.get("ea_groups") if A else None     # segment-constant edge_attr table (opt-in)
+        n_ea = groups.rows if groups is not None else T
+        if t["sbf"].size(0) != T or (A and t["edge_attr"].size(0) != n_ea) or t["rbf"].size(0) != E:
             raise ValueError("SBFTransformerConv: sbf/edge_attr must have one row per edge_index "
-                             "column and rbf one row per node")
+                             "column (edge_attr: one row per table row with edge_attr_index) and rbf one "
+                             "row per node")
+        if groups is not None and groups.index.numel() != E:
+            raise ValueError(f"edge_attr_index must have one entry per node of the line graph ({E}), "
+                             f"got {groups.index.numel()}")
         fuse = 1 if t["w_skip"] is not None else 0
 
         desc = _lib.ConvDesc()
@@ -84,12 +99,13 @@ class _SBFConvFn(torch.autograd.Function):
         desc.w_edge = _lib.ptr(t["w_edge"]) if A else None
         for n in ("src", "tgt", "rowptr_tgt", "order_tgt", "rowptr_src", "order_src"):
             setattr(desc, n, _lib.ptr(getattr(meta, n)))
+        _set_groups(desc, groups)
 
         f32 = dict(dtype=torch.float32, device=dev)
         qkvs = torch.empty((E, 4 * D), **f32)
         attn = torch.empty((E, D), **f32)
         lse = torch.empty((E, H), **f32)
-        ea = torch.empty((max(T, 1), D), **f32) if A else None
+        ea = torch.empty((max(n_ea, 1), D), **f32) if A else None
         sg = torch.empty((max(T, 1), D), **f32)
         out = torch.empty((E, D), **f32) if fuse else attn
         alpha = torch.empty((T, H), **f32) if cfg["want_alpha"] else None
@@ -99,6 +115,7 @@ class _SBFConvFn(torch.autograd.Function):
         _lib.check(L.x2_sbfconv_fwd(C.byref(desc), C.byref(saved), _lib.ptr(out), _lib.ptr(alpha),
                                     _lib.ptr(ws), ws.numel(), _lib.stream()), "x2_sbfconv_fwd")
         ctx.cfg, ctx.meta, ctx.dims = cfg, meta, (E, T, D, H, Cc, S, R, A, fuse)
+        ctx.groups = groups
         ctx.tensors = t            # inputs + weights (kept alive; plain references, no graph)
         ctx.saved_bufs = (qkvs, attn, lse, ea, sg)
         if alpha is not None:
@@ -128,6 +145,8 @@ class _SBFConvFn(torch.autograd.Function):
         desc.w_edge = _lib.ptr(t["w_edge"]) if A else None
         for n in ("src", "tgt", "rowptr_tgt", "order_tgt", "rowptr_src", "order_src"):
             setattr(desc, n, _lib.ptr(getattr(meta, n)))
+        _set_groups(desc, ctx.groups)
+        n_ea = ctx.groups.rows if ctx.groups is not None else T
         saved = _lib.ConvSaved(_lib.ptr(qkvs), _lib.ptr(attn), _lib.ptr(lse), _lib.ptr(ea), _lib.ptr(sg))
 
         f32 = dict(dtype=torch.float32, device=dev)
@@ -135,7 +154,7 @@ class _SBFConvFn(torch.autograd.Function):
         g = {
             "dx": torch.empty((E, D), **f32), "drbf": torch.empty((E, R), **f32),
             "dsbf": torch.empty((T, S), **f32) if need[4] else None,
-            "dedge_attr": torch.empty((T, A), **f32) if (A and need[5]) else None,
+            "dedge_attr": torch.empty((n_ea, A), **f32) if (A and need[5]) else None,
             "dw_rbf": torch.empty((D, R), **f32),
             "dw_q": torch.empty((D, D), **f32), "db_q": torch.empty(D, **f32),
             "dw_k": torch.empty((D, D), **f32), "db_k": torch.empty(D, **f32),
@@ -221,7 +240,14 @@ class SBFTransformerConv(nn.Module):
         if self.beta:
             self.lin_beta.reset_parameters()
 
-    def forward(self, sbf, rbf, x, edge_index, edge_attr=None, return_attention_weights=None):
+    def forward(self, sbf, rbf, x, edge_index, edge_attr=None, return_attention_weights=None,
+                edge_attr_index=None):
+        """Reference signature (sbftransformer_conv.py:93-94) plus one opt-in keyword (SURVEY.md §8f row
+        1): with `edge_attr_index` [E] (integer tensor), `edge_attr` is a TABLE [M, edge_dim] and every
+        edge_index column whose target is line-node e uses row edge_attr_index[e] -- identical in value to
+        passing edge_attr[edge_attr_index[edge_index[1]]] ([T, edge_dim]), without streaming T rows
+        through lin_edge.  (xgnn.py:57-58 builds edge_attr from the central atom only, so there
+        edge_attr = edgenn(atom_embeddings), edge_attr_index = the bond's second atom.)"""
         if not isinstance(x, Tensor):
             raise TypeError("SBFTransformerConv: `x` must be a Tensor (the reference's tuple path is dead code)")
         if not isinstance(edge_index, Tensor):
@@ -238,6 +264,8 @@ class SBFTransformerConv(nn.Module):
         mode = default_mode(H * Cc) if self.precision is None else self.precision
         cfg = dict(heads=H, out_channels=Cc, mode=mode, dropout_p=p_drop, seed=seed,
                    want_alpha=isinstance(return_attention_weights, bool))
+        if edge_attr_index is not None and self.lin_edge is not None:
+            cfg["ea_groups"] = graph_meta.get_groups(edge_attr_index, edge_attr.size(0))
         out, alpha = _SBFConvFn.apply(
             cfg, meta, x, rbf, sbf, edge_attr if self.lin_edge is not None else None,
             self.lin_rbf.weight, self.lin_query.weight, self.lin_query.bias, self.lin_key.weight,

@@ -54,6 +54,16 @@ __device__ __forceinline__ float head_sum(float v, int lph) {
   for (int o = 1; o < lph; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+template <int LPH>
+__device__ __forceinline__ float head_sum_t(float v, int lph) {
+  if constexpr (LPH > 0) {
+#pragma unroll
+    for (int o = 1; o < LPH; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  } else {
+    return head_sum(v, lph);
+  }
+}
 
 // Attention-dropout keep factor for (triplet, head): 0 or 1/(1-p); counter-based so forward and
 // backward regenerate the same mask.
@@ -128,9 +138,15 @@ __global__ void k_filter_bwd_sum(const float4* __restrict__ x, const float4* __r
 }
 
 // ------------------------------------------------------------------ segmented attention fwd
-// SEG: `ea` is a table and every triplet of target e uses its row ea_index[e] (segment-constant edge
-// features): the row is loaded once per segment instead of one row per triplet.
-template <int VEC, bool SEG>
+// lin_edge term of a triplet: none (edge_dim=None), one row per triplet (reference layout), or one row
+// per target segment (segment-constant edge features, SURVEY.md §8f row 1: the row is loaded once).
+enum { kEaNone = 0, kEaTriplet = 1, kEaSegment = 2 };
+constexpr int kRing = 2;      // forward: register ring of triplet rows, kRing - 1 triplets of loads in flight ahead
+constexpr int kRingBwd = 1;   // by-target backward: more rows in registers cost more occupancy than they hide latency
+
+// GENERAL = attention dropout and/or the alpha output requested (rare paths; the plain instantiation
+// has no branches in the triplet loop, so the loads of the next triplets are issued ahead).
+template <int VEC, int EA, bool GENERAL, int LPH>
 __global__ void __launch_bounds__(128)
 k_attn_fwd(const float* __restrict__ qkvs, int ldq, const float* __restrict__ ea,
            const int32_t* __restrict__ ea_index,
@@ -145,7 +161,7 @@ k_attn_fwd(const float* __restrict__ qkvs, int ldq, const float* __restrict__ ea
   const int lane = threadIdx.x & 31;
   const int ch = lane * VEC;
   const int head = ch / C;
-  const int lph = C / VEC;
+  const int lph = LPH > 0 ? LPH : C / VEC;      // lanes per head: compile-time for the common shapes
   const bool leader = (ch % C) == 0;
 
   float q[VEC];
@@ -153,47 +169,66 @@ k_attn_fwd(const float* __restrict__ qkvs, int ldq, const float* __restrict__ ea
   const int beg = rowptr[e], end = rowptr[e + 1];
 
   float m = -INFINITY, z = 0.f;
-  float acc[VEC];
+  float acc[VEC], a_seg[VEC];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-  float a_[VEC];
-#pragma unroll
-  for (int j = 0; j < VEC; ++j) a_[j] = 0.f;
-  if constexpr (SEG) ldv<VEC>(ea + (int64_t)ea_index[e] * D + ch, a_);
+  for (int i = 0; i < VEC; ++i) acc[i] = a_seg[i] = 0.f;
+  if constexpr (EA == kEaSegment) ldv<VEC>(ea + (int64_t)ea_index[e] * D + ch, a_seg);
 
+  struct Row {
+    float k[VEC], v[VEC], g[VEC], a[EA == kEaTriplet ? VEC : 1];
+    int t;
+  };
   for (int base = beg; base < end; base += 32) {
     const int my = base + lane;
     int t_l = 0, s_l = 0;
     if (my < end) {
-      t_l = order[my];
+      t_l = order ? order[my] : my;            // order == NULL: the triplet list is target-sorted
       s_l = src[t_l];
     }
     const int cnt = min(32, end - base);
-#pragma unroll 4
-    for (int i = 0; i < cnt; ++i) {
-      const int t = __shfl_sync(0xffffffffu, t_l, i);
+    auto fetch = [&](Row& r, int i) {          // i is clamped: re-reading the last triplet is harmless
+      i = min(i, cnt - 1);
+      r.t = __shfl_sync(0xffffffffu, t_l, i);
       const int s = __shfl_sync(0xffffffffu, s_l, i);
-      float k[VEC], v[VEC], g[VEC];
-      ldv<VEC>(qkvs + (int64_t)s * ldq + D + ch, k);
-      ldv<VEC>(qkvs + (int64_t)s * ldq + 2 * D + ch, v);
-      ldv<VEC>(sg + (int64_t)t * D + ch, g);
-      if constexpr (!SEG) {
-        if (ea) ldv<VEC>(ea + (int64_t)t * D + ch, a_);
-      }
+      ldv<VEC>(qkvs + (int64_t)s * ldq + D + ch, r.k);
+      ldv<VEC>(qkvs + (int64_t)s * ldq + 2 * D + ch, r.v);
+      ldv<VEC>(sg + (int64_t)r.t * D + ch, r.g);
+      if constexpr (EA == kEaTriplet) ldv<VEC>(ea + (int64_t)r.t * D + ch, r.a);
+    };
+    auto consume = [&](const Row& r) {
+      float a_[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) a_[j] = EA == kEaTriplet ? r.a[EA == kEaTriplet ? j : 0] : a_seg[j];
       float dot = 0.f;
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) dot = fmaf(q[j], k[j] + a_[j], dot);
-      const float a = head_sum(dot, lph) * scale;           // :150
-      if (alpha && leader) alpha[(int64_t)t * H + head] = a;  // raw logit, normalised below
+      for (int j = 0; j < VEC; ++j) dot = fmaf(q[j], r.k[j] + a_[j], dot);
+      const float a = head_sum_t<LPH>(dot, lph) * scale;    // :150
+      if constexpr (GENERAL) {
+        if (alpha && leader) alpha[(int64_t)r.t * H + head] = a;  // raw logit, normalised below
+      }
       const float mn = fmaxf(m, a);
       const float corr = expf(m - mn);                    // exp(-inf) = 0 on the first triplet
       const float p = expf(a - mn);
       z = z * corr + p;
       float pk = p;
-      if (dropout_p > 0.f) pk *= keep_scale(seed, t, head, H, dropout_p);
+      if constexpr (GENERAL) {
+        if (dropout_p > 0.f) pk *= keep_scale(seed, r.t, head, H, dropout_p);
+      }
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) acc[j] = acc[j] * corr + pk * (v[j] + a_[j]) * g[j];  // :155-160
+      for (int j = 0; j < VEC; ++j) acc[j] = acc[j] * corr + pk * (r.v[j] + a_[j]) * r.g[j];  // :155-160
       m = mn;
+    };
+    Row ring[kRing];
+#pragma unroll
+    for (int u = 0; u < kRing - 1; ++u) fetch(ring[u], u);
+    for (int i = 0; i < cnt; i += kRing) {
+#pragma unroll
+      for (int u = 0; u < kRing; ++u) {
+        if (i + u < cnt) {
+          fetch(ring[(u + kRing - 1) % kRing], i + u + kRing - 1);
+          consume(ring[u]);
+        }
+      }
     }
   }
   const float inv = 1.0f / (z + 1e-16f);                    // PyG softmax: out / (sum + 1e-16)
@@ -210,30 +245,32 @@ k_attn_fwd(const float* __restrict__ qkvs, int ldq, const float* __restrict__ ea
   stv<VEC>(out + e * D + ch, o);
   const float l = (end > beg) ? m + logf(z) : 0.f;
   if (leader) lse[e * H + head] = l;
-  if (alpha) {
-    __syncwarp();
-    for (int idx = beg; idx < end; ++idx) {
-      const int t = order[idx];
-      if (leader) {
-        const float a = alpha[(int64_t)t * H + head];
-        alpha[(int64_t)t * H + head] = expf(a - m) * inv;
+  if constexpr (GENERAL) {
+    if (alpha) {
+      __syncwarp();
+      for (int idx = beg; idx < end; ++idx) {
+        const int t = order ? order[idx] : idx;
+        if (leader) {
+          const float a = alpha[(int64_t)t * H + head];
+          alpha[(int64_t)t * H + head] = expf(a - m) * inv;
+        }
       }
     }
   }
 }
 
 // ------------------------------------------------------------------ backward pass 1 (by target)
-// SEG (see k_attn_fwd): d(lin_edge out) is summed over the segment in registers and written as ONE
-// row per target, dea[e, :] -- the per-triplet [T, D] stream disappears.
-template <int VEC, bool SEG>
+// EA == kEaSegment: d(lin_edge out) is summed over the segment in registers and written as ONE row per
+// target, dea[e, :] -- the per-triplet [T, D] stream disappears.  DROP: attention dropout active.
+template <int VEC, int EA, bool DROP, int LPH>
 __global__ void __launch_bounds__(128)
 k_attn_bwd_tgt(const float* __restrict__ qkvs, int ldq, const float* __restrict__ ea,
                const int32_t* __restrict__ ea_index,
                const float* __restrict__ sg, const float* __restrict__ attn,
                const float* __restrict__ lse, const float* __restrict__ gout,
                const int32_t* __restrict__ src, const int32_t* __restrict__ rowptr,
-               const int32_t* __restrict__ order, int64_t E, int H, int C, float scale,
-               float dropout_p, uint64_t seed, float* __restrict__ dqkv, int ldg,
+               const int32_t* __restrict__ order, int64_t E, int H, int C,
+               float scale, float dropout_p, uint64_t seed, float* __restrict__ dqkv, int ldg,
                float* __restrict__ dea, float* __restrict__ dsg, float* __restrict__ al,
                float* __restrict__ da_out) {
   constexpr int D = 32 * VEC;
@@ -242,7 +279,7 @@ k_attn_bwd_tgt(const float* __restrict__ qkvs, int ldq, const float* __restrict_
   const int lane = threadIdx.x & 31;
   const int ch = lane * VEC;
   const int head = ch / C;
-  const int lph = C / VEC;
+  const int lph = LPH > 0 ? LPH : C / VEC;
   const bool leader = (ch % C) == 0;
 
   float q[VEC], g[VEC], o[VEC], dq[VEC];
@@ -255,49 +292,62 @@ k_attn_bwd_tgt(const float* __restrict__ qkvs, int ldq, const float* __restrict_
     r = fmaf(g[i], o[i], r);
     dq[i] = 0.f;
   }
-  r = head_sum(r, lph);                       // r_eh = sum_t alpha dalpha = <G, O>  (App. A)
+  r = head_sum_t<LPH>(r, lph);                // r_eh = sum_t alpha dalpha = <G, O>  (App. A)
   const float l = lse[e * H + head];
   const int beg = rowptr[e], end = rowptr[e + 1];
-  float a_[VEC], dea_acc[VEC];
+  float a_seg[VEC], dea_acc[VEC];
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) a_[j] = dea_acc[j] = 0.f;
-  if constexpr (SEG) ldv<VEC>(ea + (int64_t)ea_index[e] * D + ch, a_);
+  for (int j = 0; j < VEC; ++j) a_seg[j] = dea_acc[j] = 0.f;
+  if constexpr (EA == kEaSegment) ldv<VEC>(ea + (int64_t)ea_index[e] * D + ch, a_seg);
 
+  struct Row {
+    float k[VEC], v[VEC], g[VEC], a[EA == kEaTriplet ? VEC : 1];
+    int t;
+  };
   for (int base = beg; base < end; base += 32) {
     const int my = base + lane;
     int t_l = 0, s_l = 0;
     if (my < end) {
-      t_l = order[my];
+      t_l = order ? order[my] : my;            // order == NULL: the triplet list is target-sorted
       s_l = src[t_l];
     }
     const int cnt = min(32, end - base);
-#pragma unroll 4
-    for (int i = 0; i < cnt; ++i) {
-      const int t = __shfl_sync(0xffffffffu, t_l, i);
+    auto fetch = [&](Row& rw, int i) {         // i is clamped: re-reading the last triplet is harmless
+      i = min(i, cnt - 1);
+      rw.t = __shfl_sync(0xffffffffu, t_l, i);
       const int s = __shfl_sync(0xffffffffu, s_l, i);
-      float k[VEC], v[VEC], sgv[VEC];
-      ldv<VEC>(qkvs + (int64_t)s * ldq + D + ch, k);
-      ldv<VEC>(qkvs + (int64_t)s * ldq + 2 * D + ch, v);
-      ldv<VEC>(sg + (int64_t)t * D + ch, sgv);
-      if constexpr (!SEG) {
-        if (ea) ldv<VEC>(ea + (int64_t)t * D + ch, a_);
-      }
+      ldv<VEC>(qkvs + (int64_t)s * ldq + D + ch, rw.k);
+      ldv<VEC>(qkvs + (int64_t)s * ldq + 2 * D + ch, rw.v);
+      ldv<VEC>(sg + (int64_t)rw.t * D + ch, rw.g);
+      if constexpr (EA == kEaTriplet) ldv<VEC>(ea + (int64_t)rw.t * D + ch, rw.a);
+    };
+    auto consume = [&](const Row& rw) {
+      float k[VEC], v[VEC];
       float dot = 0.f, dal = 0.f;
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        k[j] += a_[j];                         // kk
-        v[j] += a_[j];                         // vv
+        const float a_ = EA == kEaTriplet ? rw.a[EA == kEaTriplet ? j : 0] : a_seg[j];
+        k[j] = rw.k[j] + a_;                   // kk
+        v[j] = rw.v[j] + a_;                   // vv
         dot = fmaf(q[j], k[j], dot);
-        dal = fmaf(g[j] * v[j], sgv[j], dal);
+        dal = fmaf(g[j] * v[j], rw.g[j], dal);
       }
       // both reductions share the shuffle steps
-      for (int off = 1; off < lph; off <<= 1) {
-        dot += __shfl_xor_sync(0xffffffffu, dot, off);
-        dal += __shfl_xor_sync(0xffffffffu, dal, off);
+      if constexpr (LPH > 0) {
+#pragma unroll
+        for (int off = 1; off < LPH; off <<= 1) {
+          dot += __shfl_xor_sync(0xffffffffu, dot, off);
+          dal += __shfl_xor_sync(0xffffffffu, dal, off);
+        }
+      } else {
+        for (int off = 1; off < lph; off <<= 1) {
+          dot += __shfl_xor_sync(0xffffffffu, dot, off);
+          dal += __shfl_xor_sync(0xffffffffu, dal, off);
+        }
       }
       const float alpha = expf(dot * scale - l);
       float keep = 1.f;
-      if (dropout_p > 0.f) keep = keep_scale(seed, t, head, H, dropout_p);
+      if constexpr (DROP) keep = keep_scale(seed, rw.t, head, H, dropout_p);
       const float alpha_d = alpha * keep;      // weight actually applied to the value
       const float da = alpha * (dal * keep - r);
       const float sda = scale * da;
@@ -306,25 +356,37 @@ k_attn_bwd_tgt(const float* __restrict__ qkvs, int ldq, const float* __restrict_
       for (int j = 0; j < VEC; ++j) {
         dq[j] = fmaf(sda, k[j], dq[j]);
         const float dkk = sda * q[j];
-        const float dvv = g[j] * sgv[j] * alpha_d;
+        const float dvv = g[j] * rw.g[j] * alpha_d;
         o_ea[j] = dkk + dvv;
         o_sg[j] = g[j] * v[j] * alpha_d;
       }
-      if constexpr (SEG) {
+      if constexpr (EA == kEaSegment) {
 #pragma unroll
         for (int j = 0; j < VEC; ++j) dea_acc[j] += o_ea[j];
-      } else {
-        if (dea) stv<VEC>(dea + (int64_t)t * D + ch, o_ea);
+      } else if constexpr (EA == kEaTriplet) {
+        stv<VEC>(dea + (int64_t)rw.t * D + ch, o_ea);
       }
-      stv<VEC>(dsg + (int64_t)t * D + ch, o_sg);
+      stv<VEC>(dsg + (int64_t)rw.t * D + ch, o_sg);
       if (leader) {
-        al[(int64_t)t * H + head] = alpha_d;
-        da_out[(int64_t)t * H + head] = da;
+        al[(int64_t)rw.t * H + head] = alpha_d;
+        da_out[(int64_t)rw.t * H + head] = da;
+      }
+    };
+    Row ring[kRingBwd];
+#pragma unroll
+    for (int u = 0; u < kRingBwd - 1; ++u) fetch(ring[u], u);
+    for (int i = 0; i < cnt; i += kRingBwd) {
+#pragma unroll
+      for (int u = 0; u < kRingBwd; ++u) {
+        if (i + u < cnt) {
+          fetch(ring[(u + kRingBwd - 1) % kRingBwd], i + u + kRingBwd - 1);
+          consume(ring[u]);
+        }
       }
     }
   }
   stv<VEC>(dqkv + e * ldg + ch, dq);
-  if constexpr (SEG) stv<VEC>(dea + e * D + ch, dea_acc);
+  if constexpr (EA == kEaSegment) stv<VEC>(dea + e * D + ch, dea_acc);
 }
 
 // out[m, :] = sum of in[order[i], :] over i in [rowptr[m], rowptr[m+1]) in that (ascending) order: the
@@ -524,21 +586,52 @@ static size_t bwd_layout(const x2_conv_desc* d, void* ws, BwdWs* w) {
   return align_up(a.off, 256) + 256;
 }
 
+template <int VEC, int EA, bool GENERAL>
+static void launch_attn_fwd_inst(const x2_conv_desc* d, const x2_conv_saved* s, float* out, float* alpha,
+                                 cudaStream_t st) {
+  const float scale = 1.0f / sqrtf((float)d->C);
+  const int32_t* order = d->tgt_sorted ? nullptr : d->order_tgt;     // sorted: order_tgt is the identity
+  const unsigned grid = (unsigned)cdiv(d->E * 32, 128);
+  if (d->C == 2 * VEC)     // config.json: C = 8, 4 channels per lane => 2 lanes per head
+    k_attn_fwd<VEC, EA, GENERAL, 2><<<grid, 128, 0, st>>>(
+        s->qkvs, 4 * d->D, s->ea, d->ea_index, s->sg, d->src, d->rowptr_tgt, order, d->E,
+        d->H, d->C, scale, d->fuse_skip, d->dropout_p, d->seed, s->attn, out, s->lse, alpha);
+  else
+    k_attn_fwd<VEC, EA, GENERAL, 0><<<grid, 128, 0, st>>>(
+        s->qkvs, 4 * d->D, s->ea, d->ea_index, s->sg, d->src, d->rowptr_tgt, order, d->E,
+        d->H, d->C, scale, d->fuse_skip, d->dropout_p, d->seed, s->attn, out, s->lse, alpha);
+}
 template <int VEC>
 static int launch_attn_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, float* alpha,
                            cudaStream_t st) {
-  const float scale = 1.0f / sqrtf((float)d->C);
-  const unsigned grid = (unsigned)cdiv(d->E * 32, 128);
-  if (d->ea_index)
-    k_attn_fwd<VEC, true><<<grid, 128, 0, st>>>(
-        s->qkvs, 4 * d->D, s->ea, d->ea_index, s->sg, d->src, d->rowptr_tgt, d->order_tgt, d->E,
-        d->H, d->C, scale, d->fuse_skip, d->dropout_p, d->seed, s->attn, out, s->lse, alpha);
-  else
-    k_attn_fwd<VEC, false><<<grid, 128, 0, st>>>(
-        s->qkvs, 4 * d->D, d->A > 0 ? s->ea : nullptr, nullptr, s->sg, d->src, d->rowptr_tgt, d->order_tgt, d->E,
-        d->H, d->C, scale, d->fuse_skip, d->dropout_p, d->seed, s->attn, out, s->lse, alpha);
+  const bool general = alpha != nullptr || d->dropout_p > 0.f;
+  const int ea = d->A == 0 ? kEaNone : (d->ea_index ? kEaSegment : kEaTriplet);
+  switch (ea * 2 + (general ? 1 : 0)) {
+    case 0: launch_attn_fwd_inst<VEC, kEaNone, false>(d, s, out, alpha, st); break;
+    case 1: launch_attn_fwd_inst<VEC, kEaNone, true>(d, s, out, alpha, st); break;
+    case 2: launch_attn_fwd_inst<VEC, kEaTriplet, false>(d, s, out, alpha, st); break;
+    case 3: launch_attn_fwd_inst<VEC, kEaTriplet, true>(d, s, out, alpha, st); break;
+    case 4: launch_attn_fwd_inst<VEC, kEaSegment, false>(d, s, out, alpha, st); break;
+    default: launch_attn_fwd_inst<VEC, kEaSegment, true>(d, s, out, alpha, st); break;
+  }
   X2_LAUNCH_OK();
   return X2_OK;
+}
+
+template <int VEC, int EA, bool DROP>
+static void launch_attn_bwd_tgt_inst(const x2_conv_desc* d, const x2_conv_saved* s, const float* gout,
+                                     const BwdWs& w, cudaStream_t st) {
+  const float scale = 1.0f / sqrtf((float)d->C);
+  const unsigned grid = (unsigned)cdiv(d->E * 32, 128);
+  const int32_t* order = d->tgt_sorted ? nullptr : d->order_tgt;     // sorted: order_tgt is the identity
+  if (d->C == 2 * VEC)
+    k_attn_bwd_tgt<VEC, EA, DROP, 2><<<grid, 128, 0, st>>>(
+        s->qkvs, 4 * d->D, s->ea, d->ea_index, s->sg, s->attn, s->lse, gout, d->src, d->rowptr_tgt, order, d->E,
+        d->H, d->C, scale, d->dropout_p, d->seed, w.dqkv, 3 * d->D, w.dea, w.dsg, w.al, w.da);
+  else
+    k_attn_bwd_tgt<VEC, EA, DROP, 0><<<grid, 128, 0, st>>>(
+        s->qkvs, 4 * d->D, s->ea, d->ea_index, s->sg, s->attn, s->lse, gout, d->src, d->rowptr_tgt, order, d->E,
+        d->H, d->C, scale, d->dropout_p, d->seed, w.dqkv, 3 * d->D, w.dea, w.dsg, w.al, w.da);
 }
 
 template <int VEC>
@@ -547,16 +640,16 @@ static int launch_attn_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const 
   const float scale = 1.0f / sqrtf((float)d->C);
   const unsigned grid = (unsigned)cdiv(d->E * 32, 128);
   phase_begin(st);
-  if (d->ea_index)
-    k_attn_bwd_tgt<VEC, true><<<grid, 128, 0, st>>>(s->qkvs, 4 * d->D, s->ea, d->ea_index, s->sg, s->attn,
-                                                    s->lse, gout, d->src, d->rowptr_tgt, d->order_tgt, d->E,
-                                                    d->H, d->C, scale, d->dropout_p, d->seed, w.dqkv, 3 * d->D,
-                                                    w.dea, w.dsg, w.al, w.da);
-  else
-    k_attn_bwd_tgt<VEC, false><<<grid, 128, 0, st>>>(s->qkvs, 4 * d->D, d->A > 0 ? s->ea : nullptr, nullptr,
-                                                     s->sg, s->attn, s->lse, gout, d->src, d->rowptr_tgt,
-                                                     d->order_tgt, d->E, d->H, d->C, scale, d->dropout_p,
-                                                     d->seed, w.dqkv, 3 * d->D, w.dea, w.dsg, w.al, w.da);
+  const bool drop = d->dropout_p > 0.f;
+  const int ea = d->A == 0 ? kEaNone : (d->ea_index ? kEaSegment : kEaTriplet);
+  switch (ea * 2 + (drop ? 1 : 0)) {
+    case 0: launch_attn_bwd_tgt_inst<VEC, kEaNone, false>(d, s, gout, w, st); break;
+    case 1: launch_attn_bwd_tgt_inst<VEC, kEaNone, true>(d, s, gout, w, st); break;
+    case 2: launch_attn_bwd_tgt_inst<VEC, kEaTriplet, false>(d, s, gout, w, st); break;
+    case 3: launch_attn_bwd_tgt_inst<VEC, kEaTriplet, true>(d, s, gout, w, st); break;
+    case 4: launch_attn_bwd_tgt_inst<VEC, kEaSegment, false>(d, s, gout, w, st); break;
+    default: launch_attn_bwd_tgt_inst<VEC, kEaSegment, true>(d, s, gout, w, st); break;
+  }
   X2_LAUNCH_OK();
   if (d->ea_index) {       // per-target rows -> per-table-row sums (fixed order)
     k_rows_segsum<VEC><<<(unsigned)cdiv(d->ea_rows * 32, 128), 128, 0, st>>>(w.dea, d->ea_rowptr, d->ea_order,

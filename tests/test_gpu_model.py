@@ -10,10 +10,14 @@ from util import relerr, to_t
 pytestmark = pytest.mark.gpu
 
 
-def test_golden_small_model(golden):
+# segment_edge_attr: True = conv layers get the per-atom edgenn table (opt-in fast path),
+# False = the [T, A] per-triplet gather of the reference (xgnn.py:57-58).  Same function either way.
+@pytest.mark.parametrize("segment_edge_attr", [True, False])
+def test_golden_small_model(golden, segment_edge_attr):
     from x2gnn_b200.xgnn_model import XGNNPoly
     rec = golden("model")["small"]
     net = XGNNPoly(**rec["hparams"])
+    net.segment_edge_attr = segment_edge_attr
     assert list(net.state_dict().keys()) == list(rec["state_dict"].keys())
     net.load_state_dict(rec["state_dict"])        # reference checkpoint loads unchanged
     net = net.cuda().eval()
@@ -23,13 +27,15 @@ def test_golden_small_model(golden):
     assert relerr(pred, rec["pred_f64"]) < 2e-5
 
 
-def test_config_dims_keys_and_u0_prediction(golden):
+@pytest.mark.parametrize("segment_edge_attr", [True, False])
+def test_config_dims_keys_and_u0_prediction(golden, segment_edge_attr):
     from x2gnn_b200 import synth
     from x2gnn_b200.xgnn_model import XGNNPoly
     hp = dict(conv_layers=4, sbf_dim=7, rbf_dim=6, in_channels=128, heads=16, embedding_size=128)
     torch.manual_seed(0)
     ref = omodel.XGNNPoly(**hp)
     net = XGNNPoly(**hp)
+    net.segment_edge_attr = segment_edge_attr
     assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == golden("model")["cfg_keys"]
     net.load_state_dict(ref.state_dict())
     net = net.cuda()

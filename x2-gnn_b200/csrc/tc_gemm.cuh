@@ -39,9 +39,12 @@ namespace tc {
 constexpr int kProducerWarps = 16;   // LDG bandwidth of one CTA/SM is capped by its warp count: 8 warps ->
                                      // 3.8 TB/s, 16 -> 6.0 TB/s whatever the loads in flight (tools/bw_probe.cu)
 constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kEpilogueWarps = 8;    // two per TMEM lane quarter: 4 warps cap the C-tile writes at ~2 TB/s
+constexpr int kEpilogueWarps = 4;    // one per TMEM lane quarter.  21 warps in all: registers are allocated per
+                                     // 4 warps, so 24 warps' worth = 80 registers per thread (25 warps gave 72),
+                                     // which is what a 4th chunk of loads in flight per producer thread needs
+constexpr int kEpiHalves = kEpilogueWarps / 4;
 constexpr int kThreads = 32 + kProducerThreads + kEpilogueWarps * 32;   // MMA warp + producers + epilogue
-constexpr int kEpilogueThreads = 256;
+constexpr int kEpilogueThreads = kEpilogueWarps * 32;
 constexpr int kStageWords = 20;      // padded row pitch (words) of the [32][16] epilogue transpose tiles
 constexpr int kTileM = 128;          // rows per tile (UMMA M)
 constexpr int kChunkK = 32;          // fp32 per 128-byte swizzle row
@@ -204,7 +207,7 @@ constexpr int kTmemWHi = 256;        // TMEM columns [256, 384): W_hi ; [384, 51
 constexpr int kTmemWLo = 384;
 
 constexpr int kMaxProb = 4;
-constexpr int kG1Flight = 3;         // chunks of global loads in flight per producer thread
+constexpr int kG1Flight = 4;         // chunks of global loads in flight per producer thread
 struct G1Prob {
   const float* A;        // streamed activations X[M, K]
   int64_t lda;
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
       tc_fence_after();
       const int64_t row0 = tile * kTileM;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128;
-      for (int c0 = half * 16; c0 < kTileM; c0 += 32) {
+      for (int c0 = half * 16; c0 < kTileM; c0 += 16 * kEpiHalves) {
         float v[16];
         tmem_ld16(taddr + c0, v);
         if (nvalid) {

@@ -98,18 +98,24 @@ class SBFTransformer(nn.Module):
         self.conv_layers = conv_layers
 
     def forward(self, x, edge_index, edge_attr, batch, edge_sbf, node_rbf, edge_index_0, atom_batch, num_graphs,
-                edge_attr_index=None):
-        """`edge_attr` is [T, A] as in the reference, or -- with `edge_attr_index` [T] -- a per-atom table
-        [N, A] whose rows are gathered AFTER edgenn."""
+                edge_attr_index=None, edge_attr_target_index=None):
+        """`edge_attr` is [T, A] as in the reference; or a per-atom table [N, A] with either
+        `edge_attr_index` [T] (rows gathered per triplet AFTER edgenn) or `edge_attr_target_index` [E] (the
+        conv layers take the table itself: the row is constant over the triplets of a target bond, so
+        lin_edge runs on N rows instead of T -- SURVEY.md §8f row 1)."""
         edge_attr = self.edgenn(edge_attr)
-        if edge_attr_index is not None:
+        conv_kw = {}
+        if edge_attr_target_index is not None:
+            conv_kw["edge_attr_index"] = edge_attr_target_index
+        elif edge_attr_index is not None:
             edge_attr = edge_attr[edge_attr_index]
         out = x
         n_atoms = atom_batch.size(0)
         results = self.readouts[0](out, node_rbf, n_atoms, edge_index_0)
         for i in range(self.conv_layers):
             res0 = out
-            out = self.convs[i](sbf=edge_sbf, rbf=node_rbf, x=out, edge_index=edge_index, edge_attr=edge_attr)
+            out = self.convs[i](sbf=edge_sbf, rbf=node_rbf, x=out, edge_index=edge_index, edge_attr=edge_attr,
+                                **conv_kw)
             out = graph_layer_norm(out, batch, num_graphs)
             out = self.bf_skip[i](out)
             out = F.silu(self.dense_bf_skip[i](out)) + res0
@@ -133,6 +139,9 @@ class XGNNPoly(nn.Module):
         self.mat_trans = _lin(338, 2 * embedding_size)
         self.rbf_trans = _lin(rbf_dim, embedding_size)      # declared but unused in the reference too
         self.emb_trans = _lin(2 * embedding_size, in_channels)
+        # True: hand the conv layers the per-atom edgenn table + the central atom of every bond (same
+        # values as the reference's [T, A] gather, xgnn.py:57-58); False: gather per triplet as the reference
+        self.segment_edge_attr = True
 
     def forward(self, data: dict):
         """data: x[N] i64, atom_pos[N,3], edge_index[2,E] i64, edge_attr[E,338], edge_num[B], batch[N],
@@ -151,5 +160,8 @@ class XGNNPoly(nn.Module):
         edge_sbf = self.sbf_layer(d, ang, tri[0])
         node_rbf = self.rbf_layer(d) * env
         neo_x = F.silu(self.emb_trans(neo_x))
+        if self.segment_edge_attr:      # a_j[t] == ei[1][tri[1][t]]: the atom shared by both bonds of the triplet
+            return self.fin_model(neo_x, tri, atom_emb, batch, edge_sbf, node_rbf, ei[0], data["batch"], B,
+                                  edge_attr_target_index=ei[1])
         return self.fin_model(neo_x, tri, atom_emb, batch, edge_sbf, node_rbf, ei[0], data["batch"], B,
                               edge_attr_index=a_j)

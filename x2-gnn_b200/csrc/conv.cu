@@ -84,8 +84,8 @@ constexpr int kFilterRows = 8;   // rows (warps) per block
 __global__ void __launch_bounds__(kFilterRows * 32)
 k_rbf_filter(const float* __restrict__ x, const float* __restrict__ rbf, const float* __restrict__ w_rbf,
              int64_t E, int D, int R, float* __restrict__ xs, float* __restrict__ F) {
-  extern __shared__ float s_w[];                   // [D][R]
-  for (int i = threadIdx.x; i < D * R; i += blockDim.x) s_w[i] = w_rbf[i];
+  extern __shared__ __align__(16) float s_w[];     // W_r transposed to [R][D]: lanes read consecutive words
+  for (int i = threadIdx.x; i < D * R; i += blockDim.x) s_w[(i % R) * D + i / R] = w_rbf[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   // grid-stride over rows: the W_r copy above is paid once per resident block, not once per 8 rows
@@ -98,8 +98,9 @@ k_rbf_filter(const float* __restrict__ x, const float* __restrict__ rbf, const f
     float f[4] = {0.f, 0.f, 0.f, 0.f};
     for (int r = 0; r < R; ++r) {
       const float b = __shfl_sync(0xffffffffu, rv[r >> 5], r & 31);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) f[j] = fmaf(b, s_w[(d0 + j) * R + r], f[j]);
+      const float4 wv = *reinterpret_cast<const float4*>(s_w + r * D + d0);
+      f[0] = fmaf(b, wv.x, f[0]); f[1] = fmaf(b, wv.y, f[1]);
+      f[2] = fmaf(b, wv.z, f[2]); f[3] = fmaf(b, wv.w, f[3]);
     }
     const float4 xv = *reinterpret_cast<const float4*>(x + e * D + d0);
     *reinterpret_cast<float4*>(xs + e * D + d0) = make_float4(xv.x * f[0], xv.y * f[1], xv.z * f[2], xv.w * f[3]);
@@ -135,6 +136,82 @@ __global__ void k_filter_bwd_sum(const float4* __restrict__ x, const float4* __r
   const float4 g = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
   dx[i] = make_float4(o.x + g.x * f.x, o.y + g.y * f.y, o.z + g.z * f.z, o.w + g.w * f.w);
   dxs[i] = make_float4(g.x * xv.x, g.y * xv.y, g.z * xv.z, g.w * xv.w);
+}
+
+// The whole tail of the backward for D = 128 in one pass over the rows (replaces k_filter_bwd_sum, the
+// F recompute, the d rbf GEMM and the dW_r weight-gradient GEMM + reduction):
+//   F = rbf W_r^T (recomputed) ; g = dxs + dxs2 ; dx = (dx + dx2) + g * F ; dF = g * x ;
+//   drbf[e, :] = dF W_r ; dW_r[d, r] = sum_e dF[e, d] rbf[e, r].
+// Warp per row (grid-stride, fixed row -> warp assignment), lane owns 4 channels; the dW_r terms are
+// accumulated in registers, combined over the block's warps in fixed order and written as one partial
+// tile per block (summed afterwards by k_splitk_reduce): deterministic, fp32-exact.
+template <int RMAX>
+__global__ void __launch_bounds__(kFilterRows * 32)
+k_filter_bwd_full(const float* __restrict__ x, const float* __restrict__ rbf, const float* __restrict__ w_rbf,
+                  const float* __restrict__ dxs, const float* __restrict__ dxs2, float* __restrict__ dx,
+                  const float* __restrict__ dx2, int64_t E, int R, float* __restrict__ drbf,
+                  float* __restrict__ partial) {
+  constexpr int D = 128;
+  extern __shared__ __align__(16) float s_w[];     // [R][D] transposed W_r, then [warps][RMAX][D] for the reduction
+  for (int i = threadIdx.x; i < D * R; i += blockDim.x) s_w[(i % R) * D + i / R] = w_rbf[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d0 = lane * 4;
+  float4 wv[RMAX];
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r)
+    wv[r] = r < R ? *reinterpret_cast<const float4*>(s_w + r * D + d0) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc[RMAX];
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int64_t e = (int64_t)blockIdx.x * kFilterRows + warp; e < E; e += (int64_t)gridDim.x * kFilterRows) {
+    const float rv = lane < R ? rbf[e * R + lane] : 0.f;       // RMAX <= 32: lane r holds rbf[e, r]
+    const float4 a = *reinterpret_cast<const float4*>(dxs + e * D + d0);
+    const float4 b = *reinterpret_cast<const float4*>(dxs2 + e * D + d0);
+    const float4 xv = *reinterpret_cast<const float4*>(x + e * D + d0);
+    float4 o = *reinterpret_cast<const float4*>(dx + e * D + d0);
+    if (dx2) {
+      const float4 o2 = *reinterpret_cast<const float4*>(dx2 + e * D + d0);
+      o.x += o2.x; o.y += o2.y; o.z += o2.z; o.w += o2.w;
+    }
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+      const float br = __shfl_sync(0xffffffffu, rv, r);
+      f.x = fmaf(br, wv[r].x, f.x); f.y = fmaf(br, wv[r].y, f.y);
+      f.z = fmaf(br, wv[r].z, f.z); f.w = fmaf(br, wv[r].w, f.w);
+    }
+    const float4 g = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    *reinterpret_cast<float4*>(dx + e * D + d0) =
+        make_float4(o.x + g.x * f.x, o.y + g.y * f.y, o.z + g.z * f.z, o.w + g.w * f.w);
+    const float4 dF = make_float4(g.x * xv.x, g.y * xv.y, g.z * xv.z, g.w * xv.w);
+    float mine = 0.f;                                           // lane r ends up with drbf[e, r]
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+      const float br = __shfl_sync(0xffffffffu, rv, r);
+      acc[r].x = fmaf(dF.x, br, acc[r].x); acc[r].y = fmaf(dF.y, br, acc[r].y);
+      acc[r].z = fmaf(dF.z, br, acc[r].z); acc[r].w = fmaf(dF.w, br, acc[r].w);
+      float p = dF.x * wv[r].x + dF.y * wv[r].y + dF.z * wv[r].z + dF.w * wv[r].w;
+#pragma unroll
+      for (int o_ = 16; o_ > 0; o_ >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o_);
+      if (lane == r) mine = p;
+    }
+    if (lane < R) drbf[e * R + lane] = mine;
+  }
+  // block partial of dW_r: warps summed in fixed order
+  __syncthreads();                                   // everyone is done with the W_r copy
+  float* red = s_w;                                  // [warps][RMAX][D]
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) *reinterpret_cast<float4*>(red + (warp * RMAX + r) * D + d0) = acc[r];
+  __syncthreads();
+  for (int i = threadIdx.x; i < D * R; i += blockDim.x) {
+    const int d = i / R, r = i - d * R;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kFilterRows; ++w) t += red[(w * RMAX + r) * D + d];
+    partial[(int64_t)blockIdx.x * D * R + i] = t;    // [block][D][R], the layout of dW_r
+  }
 }
 
 // ------------------------------------------------------------------ segmented attention fwd
@@ -853,12 +930,13 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
 
   phase_end(X2_PHASE_TROW_WGRAD, st);
   // (5) recompute the filtered sources
-  k_rbf_filter<<<filter_grid(E), kFilterRows * 32, (size_t)D * R * sizeof(float), st>>>(
-      d->x, d->rbf, d->w_rbf, E, D, R, w.xs, w.F);
-  X2_LAUNCH_OK();
-  // (6) node-level weight gradients
   const bool batched = L.mode == X2_MODE_TF32X3 && D == kTcBlock &&
                        ((reinterpret_cast<uintptr_t>(d->x) | reinterpret_cast<uintptr_t>(g->dx)) & 15) == 0;
+  const bool fused_tail = batched && R <= 16;        // k_filter_bwd_full recomputes F itself
+  k_rbf_filter<<<filter_grid(E), kFilterRows * 32, (size_t)D * R * sizeof(float), st>>>(
+      d->x, d->rbf, d->w_rbf, E, D, R, w.xs, fused_tail ? nullptr : w.F);
+  X2_LAUNCH_OK();
+  // (6) node-level weight gradients
   if (batched) {          // the four weight gradients as problems of ONE launch (+ one reduction)
     const tc::G2Job jobs[4] = {
         {dq, 3 * D, d->x, D, g->dw_q, D, g->db_q},
@@ -882,6 +960,30 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
         {grad_out, D, d->w_skip, nullptr, w.dx2, D, 0}};
     const int np = d->fuse_skip ? 4 : 3;
     X2_TRY(tc::tc_gemm_batch(pr, np, np, E, D, D, 1, D, st));
+    if (fused_tail) {
+      // (9 + 10) the whole tail in one pass: dx, d rbf and the per-block partials of dW_r
+      const int RM = R <= 8 ? 8 : 16;
+      const int64_t fneed = cdiv(E, kFilterRows);
+      const unsigned fgrid = (unsigned)(fneed < kNumSM * 4 ? fneed : kNumSM * 4);
+      const size_t fsmem = (size_t)kFilterRows * RM * D * sizeof(float);
+      static bool attr_set = false;
+      if (!attr_set) {
+        X2_CUDA_OK(cudaFuncSetAttribute(k_filter_bwd_full<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        attr_set = true;
+      }
+      if (RM == 8)
+        k_filter_bwd_full<8><<<fgrid, kFilterRows * 32, fsmem, st>>>(d->x, d->rbf, d->w_rbf, w.dxs, w.dxs2, g->dx,
+            d->fuse_skip ? w.dx2 : nullptr, E, R, g->drbf, w.wg);
+      else
+        k_filter_bwd_full<16><<<fgrid, kFilterRows * 32, fsmem, st>>>(d->x, d->rbf, d->w_rbf, w.dxs, w.dxs2, g->dx,
+            d->fuse_skip ? w.dx2 : nullptr, E, R, g->drbf, w.wg);
+      X2_LAUNCH_OK();
+      k_splitk_reduce<<<splitk_reduce_blocks(D, R, false), 256, 0, st>>>(w.wg, nullptr, (int)fgrid, D, R, g->dw_rbf, R,
+                                                                         nullptr);
+      X2_LAUNCH_OK();
+      phase_end(X2_PHASE_NODE_BWD, st);
+      return X2_OK;
+    }
     k_filter_bwd_sum<<<(unsigned)cdiv(E * D / 4, 256), 256, 0, st>>>(
         reinterpret_cast<const float4*>(d->x), reinterpret_cast<const float4*>(w.F),
         reinterpret_cast<float4*>(w.dxs), reinterpret_cast<const float4*>(w.dxs2),

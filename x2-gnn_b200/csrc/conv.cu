@@ -224,7 +224,7 @@ constexpr int kRingBwd = 1;   // by-target backward: more rows in registers cost
 // GENERAL = attention dropout and/or the alpha output requested (rare paths; the plain instantiation
 // has no branches in the triplet loop, so the loads of the next triplets are issued ahead).
 template <int VEC, int EA, bool GENERAL, int LPH>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 k_attn_fwd(const float* __restrict__ qkvs, int ldq, const float* __restrict__ ea,
            const int32_t* __restrict__ ea_index,
            const float* __restrict__ sg, const int32_t* __restrict__ src,
@@ -340,7 +340,7 @@ k_attn_fwd(const float* __restrict__ qkvs, int ldq, const float* __restrict__ ea
 // EA == kEaSegment: d(lin_edge out) is summed over the segment in registers and written as ONE row per
 // target, dea[e, :] -- the per-triplet [T, D] stream disappears.  DROP: attention dropout active.
 template <int VEC, int EA, bool DROP, int LPH>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 k_attn_bwd_tgt(const float* __restrict__ qkvs, int ldq, const float* __restrict__ ea,
                const int32_t* __restrict__ ea_index,
                const float* __restrict__ sg, const float* __restrict__ attn,

@@ -128,15 +128,16 @@ def test_variants(kw):
     _compare(ref, mine, _graph_inputs(3, dims, seed=4))
 
 
-def test_no_edge_dim():
+@pytest.mark.parametrize("heads", [8, 16])       # D = 64 and D = 128 (the latter: staged forward kernel)
+def test_no_edge_dim(heads):
     from x2gnn_b200.sbftransformer_conv import SBFTransformerConv
     torch.manual_seed(0)
-    ref = oconv.OracleSBFTransformerConv(64, 8, heads=8, sbf_dim=10, rbf_dim=3, edge_dim=None)
-    mine = SBFTransformerConv(64, 8, heads=8, sbf_dim=10, rbf_dim=3, edge_dim=None)
+    ref = oconv.OracleSBFTransformerConv(8 * heads, 8, heads=heads, sbf_dim=10, rbf_dim=3, edge_dim=None)
+    mine = SBFTransformerConv(8 * heads, 8, heads=heads, sbf_dim=10, rbf_dim=3, edge_dim=None)
     assert "lin_edge.weight" not in mine.state_dict()
     mine.load_state_dict(ref.state_dict())
     mine = mine.cuda()
-    rec = _graph_inputs(3, (64, 8, 10, 3, 1), seed=5)
+    rec = _graph_inputs(3, (8 * heads, heads, 10, 3, 1), seed=5)
     x = {k: rec[k] for k in ("x", "rbf", "sbf")}
     o_ref = ref.double()(x["sbf"].double(), x["rbf"].double(), x=x["x"].double(), edge_index=rec["edge_index"])
     o = mine(x["sbf"].cuda(), x["rbf"].cuda(), x=x["x"].cuda(), edge_index=rec["edge_index"].cuda())
@@ -272,6 +273,12 @@ def test_segment_constant_edge_attr_table(dims, mode, rows):
         o_full = mine(xs["sbf"], xs["rbf"], x=xs["x"], edge_index=rec["edge_index"].cuda(),
                       edge_attr=tab[index.cuda()[tgt.cuda()]])
     assert relerr(o, o_full) < 2e-6
+    # without the alpha request the forward takes the plain (for D=128, C=8: bulk-copy staged) kernel
+    with torch.no_grad():
+        o_plain = mine(xs["sbf"], xs["rbf"], x=xs["x"], edge_index=rec["edge_index"].cuda(), edge_attr=tab,
+                       edge_attr_index=index.cuda())
+    assert relerr(o_plain, o_ref) < FP32_TOL
+    assert relerr(o_plain, o) < 2e-6
     with pytest.raises(IndexError):
         mine(xs["sbf"], xs["rbf"], x=xs["x"], edge_index=rec["edge_index"].cuda(), edge_attr=tab,
              edge_attr_index=(index + M).cuda())

@@ -16,6 +16,22 @@ from . import _lib
 
 _BLK = 128
 
+# Scratch for the GEMM kernels, one buffer per (device, stream), grown on demand.  The kernels of one
+# call only use it between their own launches and calls on a stream are ordered, so it can be shared
+# by every TCLinear on that stream -- saves two allocator round trips per call (the harness model makes
+# ~290 of these calls per training step and is bound by host overhead).
+_ws_cache: dict = {}
+
+
+def _scratch(nbytes: int, dev):
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws[0].numel() < nbytes:
+        t = _lib.workspace(nbytes, dev)
+        ws = (t, _lib.ptr(t), t.numel())
+        _ws_cache[key] = ws
+    return ws
+
 
 class _TCLinearFn(torch.autograd.Function):
     @staticmethod
@@ -28,7 +44,7 @@ class _TCLinearFn(torch.autograd.Function):
         N = w.size(0)
         L = _lib.lib()
         y = torch.empty((M, N), dtype=torch.float32, device=dev)
-        ws = _lib.workspace(L.x2_tc_gemm_workspace_bytes(_BLK, _BLK), dev)
+        _, ws_p, ws_n = _scratch(L.x2_tc_gemm_workspace_bytes(_BLK, _BLK), dev)
         st = _lib.stream()
         esz = 4
         for n0 in range(0, N, _BLK):
@@ -38,7 +54,7 @@ class _TCLinearFn(torch.autograd.Function):
                 _lib.check(L.x2_tc_gemm(
                     x2.data_ptr() + k0 * esz, K, M, kb, w.data_ptr() + (n0 * K + k0) * esz, 1, K, nb,
                     (b.data_ptr() + n0 * esz) if (b is not None and k0 == 0) else None,
-                    y.data_ptr() + n0 * esz, N, 1 if k0 > 0 else 0, _lib.ptr(ws), ws.numel(), st), "x2_tc_gemm")
+                    y.data_ptr() + n0 * esz, N, 1 if k0 > 0 else 0, ws_p, ws_n, st), "x2_tc_gemm")
         ctx.save_for_backward(x2, w)
         ctx.has_bias = b is not None
         ctx.x_shape = x.shape
@@ -55,7 +71,7 @@ class _TCLinearFn(torch.autograd.Function):
         st = _lib.stream()
         esz = 4
         gx = gw = gb = None
-        ws = _lib.workspace(max(L.x2_tc_gemm_workspace_bytes(_BLK, _BLK), L.x2_tc_wgrad_workspace_bytes(M, _BLK)), dev)
+        _, ws_p, ws_n = _scratch(max(L.x2_tc_gemm_workspace_bytes(_BLK, _BLK), L.x2_tc_wgrad_workspace_bytes(M, _BLK)), dev)
         if ctx.needs_input_grad[0]:
             gx = torch.empty((M, K), dtype=torch.float32, device=dev)
             for k0 in range(0, K, _BLK):          # output columns (in_features)
@@ -64,7 +80,7 @@ class _TCLinearFn(torch.autograd.Function):
                     nb = min(_BLK, N - n0)
                     _lib.check(L.x2_tc_gemm(
                         gy2.data_ptr() + n0 * esz, N, M, nb, w.data_ptr() + (n0 * K + k0) * esz, K, 1, kb, None,
-                        gx.data_ptr() + k0 * esz, K, 1 if n0 > 0 else 0, _lib.ptr(ws), ws.numel(), st), "x2_tc_gemm")
+                        gx.data_ptr() + k0 * esz, K, 1 if n0 > 0 else 0, ws_p, ws_n, st), "x2_tc_gemm")
             gx = gx.view(ctx.x_shape)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             gw = torch.empty((N, K), dtype=torch.float32, device=dev)
@@ -76,7 +92,7 @@ class _TCLinearFn(torch.autograd.Function):
                         gy2.data_ptr() + n0 * esz, N, x2.data_ptr() + k0 * esz, K, M, kb,
                         gw.data_ptr() + (n0 * K + k0) * esz, K,
                         (gb.data_ptr() + n0 * esz) if (gb is not None and k0 == 0) else None,
-                        _lib.ptr(ws), ws.numel(), st), "x2_tc_wgrad")
+                        ws_p, ws_n, st), "x2_tc_wgrad")
         return gx, gw, gb
 
 

@@ -155,31 +155,79 @@ __device__ __forceinline__ void y_l0(double theta, int L, float* out, int stride
   }
 }
 
-constexpr int kSbfTile = 64;  // triplets per block
+constexpr int kSbfTile = 256;  // triplets per block (= threads per block)
 
-__global__ void __launch_bounds__(256)
+// sbf[t, l R + n] = table[idx[t], l R + n] * Y_l0(theta_t)       (angular_basis_layer.py:80-93)
+// Phase 1: one thread per triplet evaluates Y_l0 in fp64 (normalisation constants from a per-block
+// table, no per-triplet sqrt).  Phase 2: the block's [256, S] output tile is contiguous; consecutive
+// threads produce consecutive 2-column units (the (triplet, column) cursor advances incrementally --
+// no division in the loop): coalesced 64-bit table-row loads and output stores.
+// Write-bandwidth bound: 4 (S+1) + 8 bytes per triplet.
+__global__ void __launch_bounds__(kSbfTile)
 k_sbf_fwd(const float* __restrict__ table, const float* __restrict__ angles,
           const int64_t* __restrict__ idx, int64_t T, int64_t E, int L, int R,
           float* __restrict__ out) {
-  __shared__ float ys[kSbfTile * kMaxL];
-  __shared__ int64_t rows[kSbfTile];
+  extern __shared__ __align__(16) float sbf_smem[];          // [kSbfTile][L] ys | [S] column -> l (as int)
+  __shared__ int64_t rowoff[kSbfTile];
+  __shared__ float ynorm[kMaxL];
   const int S = L * R;
+  float* ys = sbf_smem;
+  int* lcol = reinterpret_cast<int*>(sbf_smem + kSbfTile * L);
   const int64_t t0 = (int64_t)blockIdx.x * kSbfTile;
   const int nt = (int)min((int64_t)kSbfTile, T - t0);
+  if (threadIdx.x < L) ynorm[threadIdx.x] = (float)sqrt((double)(2 * threadIdx.x + 1) * 0.07957747154594767);
+  for (int c = threadIdx.x; c < S; c += kSbfTile) lcol[c] = c / R;
+  __syncthreads();
   if (threadIdx.x < nt) {
-    y_l0((double)angles[t0 + threadIdx.x], L, ys + threadIdx.x * L, 1);
-    int64_t r = idx[t0 + threadIdx.x];
-    rows[threadIdx.x] = (r < 0 || r >= E) ? 0 : r;  // bounds are validated by the caller
+    // the Legendre recurrence is stable on [-1, 1]: fp32 (error ~1e-7 per step) is enough here, unlike
+    // the Bessel part, which lives in the fp64 table
+    const float c = cosf(angles[t0 + threadIdx.x]);
+    float p0 = 1.f, p1 = c;
+    float* o = ys + threadIdx.x * L;
+    o[0] = ynorm[0];
+    if (L > 1) o[1] = ynorm[1] * c;
+    for (int j = 2; j < L; ++j) {
+      const float pj = ((float)(2 * j - 1) * c * p1 - (float)(j - 1) * p0) / (float)j;
+      p0 = p1;
+      p1 = pj;
+      o[j] = ynorm[j] * pj;
+    }
+    const int64_t r = idx[t0 + threadIdx.x];
+    rowoff[threadIdx.x] = ((r < 0 || r >= E) ? 0 : r) * S;  // bounds are validated by the caller
   }
   __syncthreads();
-  const int total = nt * S;
   float* o = out + t0 * S;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int tb = i / S;
-    const int col = i - tb * S;
-    o[i] = __ldg(table + rows[tb] * S + col) * ys[tb * L + col / R];
+  if ((S & 1) == 0 && (R & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0 &&
+      (reinterpret_cast<uintptr_t>(table) & 7) == 0) {
+    // even S and R (config: 42, 6): units of 2 consecutive columns never straddle a triplet or an l
+    // block; 64-bit table loads and output stores, cursor advanced without divisions
+    const int S2 = S >> 1;
+    const int total2 = nt * S2;
+    const int dq = kSbfTile / S2, dr = kSbfTile - dq * S2;
+    int u = threadIdx.x;
+    int tb = u / S2, c2 = u - tb * S2;             // the only division: once per thread
+    for (; u < total2; u += kSbfTile) {
+      const float2 tv = __ldg(reinterpret_cast<const float2*>(table + rowoff[tb]) + c2);
+      const float y = ys[tb * L + lcol[2 * c2]];
+      reinterpret_cast<float2*>(o + (size_t)tb * S)[c2] = make_float2(tv.x * y, tv.y * y);
+      tb += dq;
+      c2 += dr;
+      if (c2 >= S2) { c2 -= S2; ++tb; }
+    }
+    return;
+  }
+  const int total = nt * S;
+  int i = threadIdx.x;
+  int tb = i / S, col = i - tb * S;
+  const int dq = kSbfTile / S, dr = kSbfTile - dq * S;
+  for (; i < total; i += kSbfTile) {
+    o[i] = __ldg(table + rowoff[tb] + col) * ys[tb * L + lcol[col]];
+    tb += dq;
+    col += dr;
+    if (col >= S) { col -= S; ++tb; }
   }
 }
+
 
 __global__ void k_angular_fwd(const float* __restrict__ angles, int64_t T, int L,
                               float* __restrict__ out) {
@@ -260,7 +308,8 @@ int x2_sbf_fwd(const float* table, const float* angles, const int64_t* idx, int6
                int32_t L, int32_t R, float* out, void* stream) {
   X2_CHECK_ARG(T >= 0 && L >= 1 && L <= kMaxL && R >= 1 && R <= 64, "x2_sbf_fwd: need 1<=L<=%d, 1<=R<=64", kMaxL);
   if (T == 0) return X2_OK;
-  k_sbf_fwd<<<(unsigned)cdiv(T, kSbfTile), 256, 0, (cudaStream_t)stream>>>(table, angles, idx, T, E, L, R, out);
+  const size_t smem = (size_t)(kSbfTile * L + L * R) * sizeof(float);
+  k_sbf_fwd<<<(unsigned)cdiv(T, kSbfTile), kSbfTile, smem, (cudaStream_t)stream>>>(table, angles, idx, T, E, L, R, out);
   X2_LAUNCH_OK();
   return X2_OK;
 }

@@ -194,6 +194,10 @@ typedef struct {
 #define X2_MODE_FP32 0    /* fp32 SIMT arithmetic everywhere (1e-5 parity) */
 #define X2_MODE_TF32X3 1  /* Linear layers on tcgen05 tensor cores in 3xTF32 split precision (fp32-accurate,
                              1e-5 parity); needs D % 128 == 0.  Attention arithmetic stays fp32 SIMT. */
+#define X2_MODE_TF32 3    /* reduced precision: as TF32X3 but ONE tf32 pass per product (operands truncated to
+                             10 mantissa bits by the tensor core, fp32 accumulation): ~5e-4 relative error on
+                             layer outputs and gradients, inside the 2e-2 tolerance class of the bf16-projection
+                             mode; the lo-half passes of the producers and two of three MMAs are skipped */
 #define X2_MODE_TF32X3_FUSED 2  /* experimental: as TF32X3, with lin_edge / lin_sbf and the forward attention
                                    fused into one tcgen05 kernel (csrc/fused_fwd.cuh) when edge_index is
                                    target-sorted, D == 128, A <= 128, S <= 64, no dropout / alpha request */

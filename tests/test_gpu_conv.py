@@ -12,13 +12,13 @@ pytestmark = pytest.mark.gpu
 INPUTS = ("x", "rbf", "sbf", "edge_attr")
 
 
-MODES = {"fp32": 0, "tf32x3": 1, "fused": 2}   # X2_MODE_FP32 / X2_MODE_TF32X3 / X2_MODE_TF32X3_FUSED
+MODES = {"fp32": 0, "tf32x3": 1, "fused": 2, "tf32": 3}   # X2_MODE_FP32 / _TF32X3 / _TF32X3_FUSED / _TF32
 
 
 def _mine(dims, state, mode=None, **kw):
     from x2gnn_b200.sbftransformer_conv import SBFTransformerConv
     D, H, S, R, A = dims
-    if mode in ("tf32x3", "fused") and D % 128:
+    if mode in ("tf32x3", "fused", "tf32") and D % 128:
         pytest.skip("tensor-core mode needs D % 128 == 0")
     c = SBFTransformerConv(D, D // H, heads=H, sbf_dim=S, rbf_dim=R, dropout=kw.pop("dropout", 0),
                            edge_dim=A, **kw)
@@ -37,6 +37,24 @@ def _run(conv, rec, dev, dtype, want_alpha=False, sbf_grad=True):
     out, alpha = (r[0], r[1][1]) if want_alpha else (r, None)
     out.backward(rec["grad_out"][:, :out.size(1)].to(device=dev, dtype=dtype))
     return out, alpha, xs
+
+
+def test_reduced_precision_tf32_mode(golden):
+    """X2_MODE_TF32 (one tf32 pass per product in the Linear layers) against the reference's fp64 results:
+    inside the north_star's reduced-precision tolerance (2e-2), and measurably NOT fp32-accurate, i.e.
+    the mode really runs a different arithmetic."""
+    rec = golden("conv")["cfg"]
+    conv = _mine(rec["dims"], rec["state_dict"], mode="tf32")
+    out, _, xs = _run(conv, rec, "cuda", torch.float32)
+    errs = {"out": relerr(out, rec["out_f64"])}
+    for k in INPUTS:
+        errs[k] = relerr(xs[k].grad, rec[f"grad_{k}_f64"])
+    for k, p in conv.named_parameters():
+        ref = rec[f"gradp_{k}_f64"]
+        if float(ref.abs().max()) > 1e-12:
+            errs[k] = relerr(p.grad, ref)
+    assert max(errs.values()) < 2e-2, errs
+    assert max(errs.values()) > FP32_TOL, errs
 
 
 @pytest.mark.parametrize("mode", ["fp32", "tf32x3", "fused"])

@@ -658,13 +658,16 @@ k_attn_bwd_src(const float* __restrict__ qkvs, int ldq, const float* __restrict_
 }
 
 // ------------------------------------------------------------------ Linear dispatch (SIMT / tensor core)
-static inline int lin_mode(int mode) { return mode == X2_MODE_TF32X3_FUSED ? X2_MODE_TF32X3 : mode; }
+static inline int lin_mode(int mode) {
+  return (mode == X2_MODE_TF32X3_FUSED || mode == X2_MODE_TF32) ? X2_MODE_TF32X3 : mode;
+}
 
 struct Lin {
-  int mode;          // X2_MODE_FP32: SIMT fp32;  X2_MODE_TF32X3: tcgen05 3xTF32
+  int mode;          // X2_MODE_FP32: SIMT fp32;  X2_MODE_TF32X3: tcgen05 (3xTF32, or one pass if `single`)
   void* img;         // weight-image scratch (tensor-core mode)
   float* wg;         // wgrad partial-tile scratch
   cudaStream_t st;
+  int single;        // X2_MODE_TF32: one tf32 pass per product
 };
 
 constexpr int kTcBlock = 128;   // the tcgen05 kernels take N <= 128 and a K block whose image fits smem
@@ -678,7 +681,7 @@ static int tc_linear(const Lin& L, const float* A, int64_t lda, int64_t M, int K
       const int kb = K - k0 < kTcBlock ? K - k0 : kTcBlock;
       int rc = tc::tc_gemm(A + k0, lda, M, kb, W + (int64_t)k0 * sbk + (int64_t)n0 * sbn, sbk, sbn, nb,
                            (bias && k0 == 0) ? bias + n0 : nullptr, C + n0, ldc, (beta || k0 > 0) ? 1 : 0,
-                           L.img, L.st);
+                           L.img, L.st, L.single);
       if (rc != X2_OK) return rc;
     }
   }
@@ -705,7 +708,7 @@ static int lin_wgrad(const Lin& L, const float* dy, int64_t lddy, const float* x
       for (int n0 = 0; n0 < N; n0 += kTcBlock) {
         const int nb = N - n0 < kTcBlock ? N - n0 : kTcBlock;
         int rc = tc::tc_wgrad(dy + m0, lddy, x + n0, ldx, rows, nb, dW + (int64_t)m0 * lddw + n0, lddw,
-                              (db && n0 == 0) ? db + m0 : nullptr, L.wg, L.st);
+                              (db && n0 == 0) ? db + m0 : nullptr, L.wg, L.st, L.single);
         if (rc != X2_OK) return rc;
       }
     return X2_OK;
@@ -717,8 +720,8 @@ static int lin_wgrad(const Lin& L, const float* dy, int64_t lddy, const float* x
 static int check_desc(const x2_conv_desc* d) {
   X2_CHECK_ARG(d != nullptr, "conv: null descriptor");
   X2_CHECK_ARG(d->E >= 0 && d->T >= 0 && d->E < 2147483647LL && d->T < 2147483647LL, "conv: bad E/T");
-  X2_CHECK_ARG(d->mode == X2_MODE_FP32 || d->mode == X2_MODE_TF32X3 || d->mode == X2_MODE_TF32X3_FUSED,
-               "conv: unknown mode %d", d->mode);
+  X2_CHECK_ARG(d->mode == X2_MODE_FP32 || d->mode == X2_MODE_TF32X3 || d->mode == X2_MODE_TF32X3_FUSED ||
+                   d->mode == X2_MODE_TF32, "conv: unknown mode %d", d->mode);
   X2_CHECK_ARG(d->mode == X2_MODE_FP32 || d->D % 128 == 0,
                "conv: X2_MODE_TF32X3 needs heads*out_channels to be a multiple of 128 (got %d)", d->D);
   X2_CHECK_ARG(d->D == d->H * d->C && d->H >= 1 && d->C >= 1, "conv: D=%d != H*C=%d*%d", d->D, d->H, d->C);
@@ -948,7 +951,7 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
   k_rbf_filter<<<filter_grid(E), kFilterRows * 32, (size_t)D * d->R * sizeof(float), st>>>(
       d->x, d->rbf, d->w_rbf, E, D, d->R, w.xs, nullptr);
   X2_LAUNCH_OK();
-  const Lin L{lin_mode(d->mode), w.img, nullptr, st};
+  const Lin L{lin_mode(d->mode), w.img, nullptr, st, d->mode == X2_MODE_TF32};
   // (2) Q | K | V | skip                                                     :105-107, :121
   if (L.mode == X2_MODE_TF32X3 && D == kTcBlock) {   // the four projections as problems of ONE launch
     tc::G1Prob pr[4] = {
@@ -956,7 +959,7 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
         {w.xs, D, d->w_k, d->b_k, s->qkvs + D, 4 * D, 0},
         {w.xs, D, d->w_v, d->b_v, s->qkvs + 2 * D, 4 * D, 0},
         {d->x, D, d->w_skip, d->b_skip, s->qkvs + 3 * D, 4 * D, 0}};
-    X2_TRY(tc::tc_gemm_batch(pr, d->fuse_skip ? 4 : 3, d->fuse_skip ? 4 : 3, E, D, 1, D, D, st));   // one group each
+    X2_TRY(tc::tc_gemm_batch(pr, d->fuse_skip ? 4 : 3, d->fuse_skip ? 4 : 3, E, D, 1, D, D, st, L.single));   // one group each
   } else if (L.mode == X2_MODE_TF32X3) {
     X2_TRY(lin_fwd(L, d->x, D, d->w_q, D, d->b_q, s->qkvs, 4 * D, E, D, D));
     X2_TRY(lin_fwd(L, w.xs, D, d->w_k, D, d->b_k, s->qkvs + D, 4 * D, E, D, D));
@@ -1056,7 +1059,7 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
   const float* dk = w.dqkv + D;
   const float* dv = w.dqkv + 2 * D;
 
-  const Lin L{lin_mode(d->mode), w.img, w.wg, st};
+  const Lin L{lin_mode(d->mode), w.img, w.wg, st, d->mode == X2_MODE_TF32};
   // (3) T-row input gradients
   const float* dea_rows = d->ea_index ? w.dea_tab : w.dea;          // rows lin_edge was applied to
   const int64_t n_ea = d->ea_index ? d->ea_rows : T;
@@ -1082,7 +1085,7 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
         {dk, 3 * D, w.xs, D, g->dw_k, D, g->db_k},
         {dv, 3 * D, w.xs, D, g->dw_v, D, g->db_v},
         {grad_out, D, d->x, D, g->dw_skip, D, g->db_skip}};
-    X2_TRY(tc::tc_wgrad_batch(jobs, d->fuse_skip ? 4 : 3, E, D, L.wg, st));
+    X2_TRY(tc::tc_wgrad_batch(jobs, d->fuse_skip ? 4 : 3, E, D, L.wg, st, L.single));
   } else {
   X2_TRY(lin_wgrad(L, dq, 3 * D, d->x, D, g->dw_q, D, g->db_q, E, D, D));
   X2_TRY(lin_wgrad(L, dk, 3 * D, w.xs, D, g->dw_k, D, g->db_k, E, D, D));
@@ -1098,7 +1101,7 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
         {dq, 3 * D, d->w_q, nullptr, g->dx, D, 0},
         {grad_out, D, d->w_skip, nullptr, w.dx2, D, 0}};
     const int np = d->fuse_skip ? 4 : 3;
-    X2_TRY(tc::tc_gemm_batch(pr, np, np, E, D, D, 1, D, st));
+    X2_TRY(tc::tc_gemm_batch(pr, np, np, E, D, D, 1, D, st, L.single));
     if (fused_tail) {
       // (9 + 10) the whole tail in one pass: dx, d rbf and the per-block partials of dW_r
       const int RM = R <= 8 ? 8 : 16;

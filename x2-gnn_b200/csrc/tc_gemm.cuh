@@ -176,9 +176,40 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
+}
+
+// Ampere-style asynchronous copies global -> shared (LDGSTS): no register staging, arbitrary 8/16-byte
+// destination, so a thread can drop raw fp32 straight into a swizzled UMMA operand layout and keep as
+// many chunks in flight as the smem ring is deep.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t dst, const void* src) {
+  if constexpr (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// lo part when the hi part is the RAW fp32 word (the tensor core truncates it to tf32):
+// lo = rn_tf32(x - trunc_tf32(x)); x - trunc(x) is exact (13 significant bits), |x - hi - lo| <= 2^-21 |x|
+__device__ __forceinline__ uint32_t lo_of_raw(float x) {
+  const float l = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  return hi_bits(l);
+}
+__device__ __forceinline__ float2 lds64f(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 
 // UMMA shared-memory descriptor, Blackwell version (cute SmemDescriptor layout):
@@ -233,8 +264,15 @@ struct G1Params {
   int64_t sbk, sbn;      // weight strides (shared by the problems)
   int N;                 // output channels <= 128
   int stages;
+  int single;            // 1: one tf32 pass (hi . hi only): X2_MODE_TF32, ~5e-4 relative error
 };
 
+// PIECE = 0: producers stage through registers (LDG -> split -> STS; any alignment).
+// PIECE = 16 / 8: producers copy raw fp32 pieces of that many bytes with cp.async straight into the hi
+// half of the ring stage (kG1Ahead chunks ahead of their use, no registers held), then read their OWN
+// pieces back, derive the lo half and publish the stage.  The hi operand is the raw word: the tensor core
+// truncates it.  Needs lda * 4 and the base address to be multiples of PIECE and K * 4 a multiple of PIECE.
+template <int PIECE>
 __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -331,8 +369,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint64_t adv = (uint64_t)(ks * 2);      // +32 bytes (>>4) along K inside the swizzle row
             umma_tf32_ts(taddr, w_hi + ks * 8, dxh + adv, idesc, (kc | ks) != 0);
-            umma_tf32_ts(taddr, w_lo + ks * 8, dxh + adv, idesc, 1);
-            umma_tf32_ts(taddr, w_hi + ks * 8, dxl + adv, idesc, 1);
+            if (!p.single) {
+              umma_tf32_ts(taddr, w_lo + ks * 8, dxh + adv, idesc, 1);
+              umma_tf32_ts(taddr, w_hi + ks * 8, dxl + adv, idesc, 1);
+            }
           }
           umma_commit(&empty[st]);          // smem slot reusable once these MMAs retire
           if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
@@ -344,6 +384,87 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
     }
   } else if (warp <= kProducerWarps) {
     // =============================== producers ===============================
+    if constexpr (PIECE != 0) {
+      constexpr int PPR = 128 / PIECE;                       // pieces per 128-byte row segment (8 / 16)
+      constexpr int NP = kTileM * PPR / kProducerThreads;    // pieces per thread per chunk (2 / 4)
+      constexpr int RS = kProducerThreads / PPR;             // rows between a thread's pieces (64 / 32)
+      constexpr int EPP = PIECE / 4;                         // fp32 per piece
+      const int pt = threadIdx.x - 32;
+      const int cp = pt % PPR, r0 = pt / PPR;
+      const int kel = cp * EPP;                              // first k of the piece inside its chunk
+      const int64_t my_tiles = cta < ntiles ? (ntiles - cta + ncta - 1) / ncta : 0;
+      const int64_t nchunk = my_tiles * KC;
+      const uint32_t sA_u = smem_u32(sA);
+      uint32_t soff[NP];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) soff[i] = kmajor_off(r0 + RS * i, (cp * PIECE) >> 4) + (uint32_t)((cp * PIECE) & 15);
+      uint32_t ist = 0, iph = 0;                             // issue cursor (ring stage, phase)
+      uint32_t cst = 0;                                      // consume cursor
+      const int64_t m_step = ncta * kTileM;
+      for (int pi = pi_beg; pi < pi_end; ++pi) {
+        const G1Prob& pr = p.prob[pi];
+        const int64_t lda = pr.lda;
+        const float* const a_thr = pr.A + (int64_t)r0 * lda + kel;
+        const int64_t row_step = (int64_t)RS * lda;
+        int64_t ld_m0 = cta * kTileM;
+        int ld_kc = 0;
+        auto issue = [&]() {
+          const int64_t m0 = ld_m0;
+          const int kc0 = ld_kc * kChunkK;
+          if (++ld_kc == KC) { ld_kc = 0; ld_m0 += m_step; }
+          mbar_wait(&empty[ist], iph ^ 1);                   // the MMAs that read this stage have retired
+          const uint32_t base = sA_u + ist * 2 * kChunkBytes;
+          const float* src = a_thr + m0 * lda + kc0;
+          if (kc0 + kel + EPP <= p.K) {
+            if (m0 + kTileM <= p.M) {
+#pragma unroll
+              for (int i = 0; i < NP; ++i) cp_async<PIECE>(base + soff[i], src + i * row_step);
+            } else {                                         // rows past M keep stale data: row-local, never stored
+#pragma unroll
+              for (int i = 0; i < NP; ++i)
+                if (m0 + r0 + RS * i < p.M) cp_async<PIECE>(base + soff[i], src + i * row_step);
+            }
+          } else {                                           // k >= K inside the last k-step: zeros
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+              if constexpr (PIECE == 16) sts128(base + soff[i], make_uint4(0u, 0u, 0u, 0u));
+              else sts64(base + soff[i], 0u, 0u);
+            }
+          }
+          if (++ist == (uint32_t)S) { ist = 0; iph ^= 1; }
+        };
+        auto consume = [&]() {                               // the thread's own pieces of this stage have landed
+          const uint32_t base = sA_u + cst * 2 * kChunkBytes;
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            if (p.single) break;                               // one tf32 pass: no lo operand
+            if constexpr (PIECE == 16) {
+              const float4 v = lds128f(base + soff[i]);
+              sts128(base + kChunkBytes + soff[i],
+                     make_uint4(lo_of_raw(v.x), lo_of_raw(v.y), lo_of_raw(v.z), lo_of_raw(v.w)));
+            } else {
+              const float2 v = lds64f(base + soff[i]);
+              sts64(base + kChunkBytes + soff[i], lo_of_raw(v.x), lo_of_raw(v.y));
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(&full[cst]);
+          if (++cst == (uint32_t)S) cst = 0;
+        };
+        constexpr int AHEAD = 3;                             // chunks of copies in flight per thread (stages - 2)
+#pragma unroll
+        for (int u = 0; u < AHEAD; ++u) {
+          if (u < nchunk) issue();
+          cp_async_commit();
+        }
+        for (int64_t it = 0; it < nchunk; ++it) {
+          if (it + AHEAD < nchunk) issue();
+          cp_async_commit();
+          cp_async_wait<AHEAD>();                            // the group of chunk `it` is complete
+          consume();
+        }
+      }
+    } else {
     // 512 threads; thread (c16, r0) moves the 16-byte column chunk c16 of rows r0 + 64 i.
     const int pt = threadIdx.x - 32;                 // 0..511
     const int c16 = pt & 7, r0 = pt >> 3;            // 8 threads cover one 128-byte row segment
@@ -401,7 +522,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
         uint4 hi, lo;
         split4(v[i], hi, lo);
         sts128(base + soff[i], hi);
-        sts128(base + kChunkBytes + soff[i], lo);
+        if (!p.single) sts128(base + kChunkBytes + soff[i], lo);
       }
       fence_proxy_async();
       mbar_arrive(&full[st]);
@@ -421,6 +542,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
           commit(v[u]);
         }
       }
+    }
     }
     }
   } else {
@@ -501,6 +623,7 @@ struct G2Params {
   int N, N_pad;          // N_pad multiple of 32, <= 128
   int64_t rows, rows_per_cta;   // rows_per_cta multiple of 32
   int stages;
+  int single;            // 1: one tf32 pass (hi . hi only): X2_MODE_TF32
 };
 
 // Byte offset of (k-row r in [0,32), 16-byte chunk c16 along MN) inside an MN-major operand chunk.
@@ -531,6 +654,14 @@ __device__ __forceinline__ void tmem_st8f(uint32_t taddr, const float (&v)[8], b
 // quarters 1..3.  20 warps: the register file is allocated in groups of 4 warps, so 21 would cap a
 // thread at 80 registers instead of 96 (three chunks of loads in flight need ~90).
 constexpr int kG2Threads = 32 + kProducerThreads + 3 * 32;
+// XMODE selects the producer implementation:
+//   0  generic: loads staged through registers with per-element guards (any N, ldx, alignment)
+//   1  cp.async, N == 128, 16-byte aligned X rows
+//   2  cp.async, ldx == N <= 64 and even (e.g. sbf [T, 42]): 8-byte pieces
+// ncu on the generic version: 298 warp-instructions per producer warp per 32-row chunk, 41 % of the stall
+// samples on the first use of the loaded registers (3.9 TB/s); the cp.async paths hold no registers for
+// data in flight and compute only the lo halves (the hi operands are the raw words).
+template <int XMODE>
 __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
   const G2Prob& pr = p.prob[blockIdx.x % (unsigned)p.nprob];
   const int64_t cta = blockIdx.x / (unsigned)p.nprob;
@@ -538,7 +669,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int S = p.stages;
   const uint32_t xbytes = (uint32_t)(p.N_pad / 32) * 4096;      // one X half (hi or lo)
-  const uint32_t stage_bytes = 2 * xbytes;                      // X hi | X lo
+  const uint32_t stage_bytes = 2 * xbytes + (XMODE != 0 ? 16384u : 0u);   // X hi | X lo (| raw Y block)
   uint8_t* sS = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sS + (size_t)S * stage_bytes);
   uint64_t* full = bars;
@@ -583,8 +714,10 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint64_t adv = (uint64_t)(ks * 64);       // one K=8 step = two 4-row k-groups = 1024 B (>>4)
           umma_tf32_ts(tmem_base, y_hi + ks * 8, dxh + adv, idesc, (c | ks) != 0);
-          umma_tf32_ts(tmem_base, y_lo + ks * 8, dxh + adv, idesc, 1);
-          umma_tf32_ts(tmem_base, y_hi + ks * 8, dxl + adv, idesc, 1);
+          if (!p.single) {
+            umma_tf32_ts(tmem_base, y_lo + ks * 8, dxh + adv, idesc, 1);
+            umma_tf32_ts(tmem_base, y_hi + ks * 8, dxl + adv, idesc, 1);
+          }
         }
         umma_commit(&empty[st]);
         if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
@@ -597,11 +730,136 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
     const int q = warp & 3;                          // TMEM lane quarter of this warp
     const int g = (warp - 1) >> 2;                   // 8-row group of the chunk (0..3)
     const int d = q * 32 + lane;                     // output channel owned by this thread
+    const uint32_t s_u = smem_u32(sS);
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + kG2YCol + 8 * g;
+    float cs = 0.f;
+    if constexpr (XMODE != 0) {
+      // ---- cp.async producers: raw fp32 goes straight into the X hi operand (MN-major layout) and into a
+      // per-stage raw Y block; the hi operands are the raw words (the tensor core truncates them), only the
+      // lo halves are computed.  Warp (q, g) owns the 8-row x 32-channel Y block it later feeds to tensor
+      // memory, so a __syncwarp() is the only synchronisation between the copies and their readers; X pieces
+      // are read back by the thread that copied them.
+      const bool want_cs = pr.colsum != nullptr;
+      const int64_t ldy = pr.ldy;
+      const uint32_t yraw_off = 2 * xbytes;          // stage: X hi | X lo | Y raw [32][128] fp32
+      // Y pieces of this lane: piece pc = lane + 32 i -> row 8g + (pc >> 3), 16-byte column pc & 7 of the block
+      uint32_t ydst[2];
+      const float* ysrc[2];
+      int yrow[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int pc = lane + 32 * i;
+        yrow[i] = 8 * g + (pc >> 3);
+        ydst[i] = yraw_off + (uint32_t)(yrow[i] * 128 + q * 32 + (pc & 7) * 4) * 4;
+        ysrc[i] = pr.Y + (rbeg + yrow[i]) * ldy + q * 32 + (pc & 7) * 4;
+      }
+      const uint32_t yrd = yraw_off + (uint32_t)((8 * g) * 128 + d) * 4;     // word read for row 8g + j: + j * 512
+      // X pieces of this thread
+      constexpr int XP = 2;                          // pieces per thread per chunk
+      uint32_t xdst[XP];
+      const float* xsrc[XP];
+      int xrow[XP];
+      bool xact[XP];
+#pragma unroll
+      for (int i = 0; i < XP; ++i) {
+        const int f = pt + kProducerThreads * i;
+        if constexpr (XMODE == 1) {                  // N == 128: 16-byte pieces, row f >> 5, float4 column f & 31
+          xrow[i] = f >> 5;
+          xact[i] = true;
+          xdst[i] = mnmajor_off(xrow[i], f & 31);
+          xsrc[i] = pr.X + (rbeg + xrow[i]) * pr.ldx + (f & 31) * 4;
+        } else {                                     // ldx == N even: 8-byte pieces, N / 2 per row
+          const int hp = p.N >> 1;
+          xrow[i] = f / hp;
+          const int col = (f - xrow[i] * hp) * 2;
+          xact[i] = f < kChunkK * hp;
+          xdst[i] = mnmajor_off(xrow[i] & 31, col >> 2) + (uint32_t)(col & 3) * 4;
+          xsrc[i] = pr.X + (rbeg + xrow[i]) * (int64_t)p.N + col;
+        }
+      }
+      const int64_t ystep = (int64_t)kChunkK * ldy;
+      const int64_t xstep = XMODE == 1 ? (int64_t)kChunkK * pr.ldx : (int64_t)kChunkK * p.N;
+      uint32_t ist = 0, iph = 0, cst = 0;
+      int64_t ic = 0;                                // next chunk to issue
+      auto issue = [&]() {
+        const int64_t row0 = rbeg + ic * kChunkK;
+        ++ic;
+        mbar_wait(&empty[ist], iph ^ 1);             // MMAs of the chunk that used this stage have retired
+        tc_fence_after();
+        const uint32_t sb = s_u + ist * stage_bytes;
+        if (row0 + kChunkK <= rend) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) cp_async<16>(sb + ydst[i], ysrc[i]);
+#pragma unroll
+          for (int i = 0; i < XP; ++i)
+            if (xact[i]) cp_async<XMODE == 1 ? 16 : 8>(sb + xdst[i], xsrc[i]);
+        } else {                                     // last, partial chunk: rows past the end are zeros
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if (row0 + yrow[i] < rend) cp_async<16>(sb + ydst[i], ysrc[i]);
+            else sts128(sb + ydst[i], make_uint4(0u, 0u, 0u, 0u));
+          }
+#pragma unroll
+          for (int i = 0; i < XP; ++i) {
+            if (!xact[i]) continue;
+            if (row0 + xrow[i] < rend) cp_async<XMODE == 1 ? 16 : 8>(sb + xdst[i], xsrc[i]);
+            else if constexpr (XMODE == 1) sts128(sb + xdst[i], make_uint4(0u, 0u, 0u, 0u));
+            else sts64(sb + xdst[i], 0u, 0u);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) ysrc[i] += ystep;
+#pragma unroll
+        for (int i = 0; i < XP; ++i) xsrc[i] += xstep;
+        if (++ist == (uint32_t)S) { ist = 0; iph ^= 1; }
+      };
+      auto consume = [&]() {
+        const uint32_t sb = s_u + cst * stage_bytes;
+        __syncwarp();                                // the warp's Y block: every lane's copies have landed
+        uint32_t yh[8], yl[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = lds32f(sb + yrd + j * 512);
+          if (want_cs) cs += v;                      // fixed order per thread
+          yh[j] = __float_as_uint(v);
+          yl[j] = lo_of_raw(v);
+        }
+        tmem_st8(trow + cst * 64, yh);
+        if (!p.single) tmem_st8(trow + cst * 64 + 32, yl);
+#pragma unroll
+        for (int i = 0; i < XP; ++i) {
+          if (!xact[i] || p.single) continue;
+          if constexpr (XMODE == 1) {
+            const float4 v = lds128f(sb + xdst[i]);
+            sts128(sb + xbytes + xdst[i], make_uint4(lo_of_raw(v.x), lo_of_raw(v.y), lo_of_raw(v.z), lo_of_raw(v.w)));
+          } else {
+            const float2 v = lds64f(sb + xdst[i]);
+            sts64(sb + xbytes + xdst[i], lo_of_raw(v.x), lo_of_raw(v.y));
+          }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(&full[cst]);
+        if (++cst == (uint32_t)S) cst = 0;
+      };
+      constexpr int AHEAD = 2;                       // chunks of copies in flight per thread (stages - 2); depths
+                                                     // 1..4 and 3..6 stages measured the same (on-chip bound)
+#pragma unroll
+      for (int u = 0; u < AHEAD; ++u) {
+        if (u < nchunks) issue();
+        cp_async_commit();
+      }
+      for (int64_t c = 0; c < nchunks; ++c) {
+        if (c + AHEAD < nchunks) issue();
+        cp_async_commit();
+        cp_async_wait<AHEAD>();                      // this thread's copies of chunk c are complete
+        consume();
+      }
+    } else {
     const bool vecX = ((pr.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(pr.X) & 15) == 0) && ((p.N & 3) == 0);
     const int xq = p.N_pad / 4;                      // float4 per X row (8..32)
     const int nx = kChunkK * xq;                     // float4 per X chunk (256..1024)
-    const uint32_t s_u = smem_u32(sS);
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + kG2YCol + 8 * g;
     const float* const y_thr = pr.Y + (int64_t)(8 * g) * pr.ldy + d;
     const int64_t ldy = pr.ldy;
     constexpr int NV = kChunkK * 32 / kProducerThreads;   // X float4 per thread per chunk (2)
@@ -615,7 +873,6 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
       xcol[i] = xc * 4;
       xoff[i] = mnmajor_off(xr[i] & 31, xc);
     }
-    float cs = 0.f;
 
     auto issue = [&](float (&vy)[8], float4 (&vx)[NV], int64_t c) {
       const int64_t row0 = rbeg + c * kChunkK;
@@ -687,6 +944,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
         commit(yc, xc);
       }
     }
+    }
     // column sums of Y over this CTA's rows: combine the 4 row groups in fixed order
     if (pr.colsum) {
       cs_smem[g * 128 + d] = cs;
@@ -730,41 +988,57 @@ static inline size_t bimage_bytes(int K, int N) { (void)K; (void)N; return 256; 
 
 static inline bool g1_supported(int K, int N) { return K >= 1 && K <= 128 && N >= 1 && N <= 128; }
 
+static inline bool cp_async_enabled() {         // X2GNN_CPASYNC=0 forces the register-staged producers (A/B runs)
+  static const int on = [] { const char* v = getenv("X2GNN_CPASYNC"); return (v && v[0] == '0') ? 0 : 1; }();
+  return on != 0;
+}
 // nprob problems C_i[M,N] (+)= A_i[M,K] . B_i(K,N) + bias_i, B_i(k,n) = W_i[k*sbk + n*sbn], in one launch.
 // The problems are split into `ngroups` groups of nprob / ngroups consecutive problems (see G1Params).
 static int tc_gemm_batch(const G1Prob* probs, int nprob, int ngroups, int64_t M, int K, int64_t sbk, int64_t sbn,
-                         int N, cudaStream_t st) {
+                         int N, cudaStream_t st, int single = 0) {
   if (M <= 0 || nprob <= 0) return X2_OK;
   if (!g1_supported(K, N) || nprob > kMaxProb || ngroups < 1 || nprob % ngroups != 0) {
     set_error("tc_gemm: unsupported K=%d N=%d nprob=%d ngroups=%d", K, N, nprob, ngroups);
     return X2_EINVAL;
   }
-  const int stages = 5;                                   // 5 x 32 KB = 160 KB: stays under the 196 KB carve-out
+  const int stages = 5;                                   // 5 x 32 KB = 160 KB (6 and 7 stages measured the same)
   const size_t smem = 1024 + (size_t)stages * 2 * kChunkBytes + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    X2_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    X2_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    X2_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    X2_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     attr_set = true;
+  }
+  // producer path: the widest cp.async piece every problem's rows are aligned to (0 = register staging)
+  int piece = cp_async_enabled() ? 16 : 0;
+  for (int i = 0; i < nprob && piece; ++i) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(probs[i].A);
+    while (piece && ((a % piece) || ((probs[i].lda * 4) % piece) || ((K * 4) % piece))) piece = piece == 16 ? 8 : 0;
   }
   G1Params p{};
   for (int i = 0; i < nprob; ++i) p.prob[i] = probs[i];
   p.nprob = nprob; p.ngroups = ngroups; p.ppg = nprob / ngroups;
   p.M = M; p.K = K; p.KC = (K + kChunkK - 1) / kChunkK;
   p.sbk = sbk; p.sbn = sbn; p.N = N; p.stages = stages;
+  p.single = single;
   const int64_t ntiles = cdiv(M, kTileM);
   const int64_t per_group = kNumSM / ngroups;
   const int grid = (int)(ntiles < per_group ? ntiles : per_group) * ngroups;
-  k_tc_gemm<<<grid, kThreads, smem, st>>>(p);
+  if (piece == 16) k_tc_gemm<16><<<grid, kThreads, smem, st>>>(p);
+  else if (piece == 8) k_tc_gemm<8><<<grid, kThreads, smem, st>>>(p);
+  else k_tc_gemm<0><<<grid, kThreads, smem, st>>>(p);
   X2_LAUNCH_OK();
   return X2_OK;
 }
 
 // C[M,N] (+)= A[M,K] . B(K,N) + bias, B(k,n) = W[k*sbk + n*sbn].
 static int tc_gemm(const float* A, int64_t lda, int64_t M, int K, const float* W, int64_t sbk, int64_t sbn,
-                   int N, const float* bias, float* C, int64_t ldc, int beta, void* img, cudaStream_t st) {
+                   int N, const float* bias, float* C, int64_t ldc, int beta, void* img, cudaStream_t st,
+                   int single = 0) {
   (void)img;
   G1Prob pr{A, lda, W, bias, C, ldc, beta};
-  return tc_gemm_batch(&pr, 1, 1, M, K, sbk, sbn, N, st);
+  return tc_gemm_batch(&pr, 1, 1, M, K, sbk, sbn, N, st, single);
 }
 
 static inline int wgrad_ctas(int64_t rows, int nprob = 1) {
@@ -831,17 +1105,29 @@ k_splitk_reduce_batch(const ReduceBatch b, int splits, int64_t M, int N) {
 
 // nprob weight gradients over the same `rows` and the same N in one launch + one reduction launch.
 // ws: tc_wgrad_workspace_floats
-static int tc_wgrad_batch(const G2Job* jobs, int nprob, int64_t rows, int N, float* ws, cudaStream_t st) {
+static int tc_wgrad_batch(const G2Job* jobs, int nprob, int64_t rows, int N, float* ws, cudaStream_t st,
+                          int single = 0) {
   if (N < 1 || N > 128 || nprob < 1 || nprob > kMaxProb) { set_error("tc_wgrad: unsupported N=%d nprob=%d", N, nprob); return X2_EINVAL; }
   const int N_pad = ceil_to(N, 32);
   const int cpp = wgrad_ctas(rows, nprob);                              // CTAs per problem
   const int64_t rpc = cdiv(cdiv(rows > 0 ? rows : 1, cpp), kChunkK) * kChunkK;
-  const uint32_t stage_bytes = 2 * (uint32_t)(N_pad / 32) * 4096;      // X hi | X lo (Y^T lives in tensor memory)
-  const int stages = 4;                                                 // <= 128 KB smem, 4 x 64 TMEM columns
+  // producer path (see k_tc_wgrad): every job of the batch must qualify
+  int xmode = cp_async_enabled() ? (N == 128 ? 1 : ((N <= 64 && (N & 1) == 0) ? 2 : 0)) : 0;
+  for (int i = 0; i < nprob; ++i) {
+    const uintptr_t xa = reinterpret_cast<uintptr_t>(jobs[i].X), ya = reinterpret_cast<uintptr_t>(jobs[i].Y);
+    if ((ya & 15) || (jobs[i].ldy & 3)) xmode = 0;
+    if (xmode == 1 && ((xa & 15) || (jobs[i].ldx & 3))) xmode = 0;
+    if (xmode == 2 && ((xa & 7) || jobs[i].ldx != N)) xmode = 0;
+  }
+  // stage: X hi | X lo (| raw Y block, cp.async paths); Y^T hi / lo live in tensor memory
+  const uint32_t stage_bytes = 2 * (uint32_t)(N_pad / 32) * 4096 + (xmode ? 16384u : 0u);
+  const int stages = 4;                                                 // <= 192 KB smem, 4 x 64 TMEM columns
   const size_t smem = 1024 + (size_t)stages * stage_bytes + 256 + 4 * 128 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    X2_CUDA_OK(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    X2_CUDA_OK(cudaFuncSetAttribute(k_tc_wgrad<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    X2_CUDA_OK(cudaFuncSetAttribute(k_tc_wgrad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    X2_CUDA_OK(cudaFuncSetAttribute(k_tc_wgrad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     attr_set = true;
   }
   G2Params p{};
@@ -857,7 +1143,10 @@ static int tc_wgrad_batch(const G2Job* jobs, int nprob, int64_t rows, int N, flo
     any_bias |= jobs[i].db != nullptr;
   }
   p.nprob = nprob; p.N = N; p.N_pad = N_pad; p.rows = rows; p.rows_per_cta = rpc; p.stages = stages;
-  k_tc_wgrad<<<cpp * nprob, kG2Threads, smem, st>>>(p);
+  p.single = single;
+  if (xmode == 1) k_tc_wgrad<1><<<cpp * nprob, kG2Threads, smem, st>>>(p);
+  else if (xmode == 2) k_tc_wgrad<2><<<cpp * nprob, kG2Threads, smem, st>>>(p);
+  else k_tc_wgrad<0><<<cpp * nprob, kG2Threads, smem, st>>>(p);
   X2_LAUNCH_OK();
   const unsigned nblk = (unsigned)((128 * (int64_t)N + 31) / 32 + (any_bias ? 4 : 0));
   k_splitk_reduce_batch<<<dim3(nblk, (unsigned)nprob), 256, 0, st>>>(rb, cpp, 128, N);
@@ -867,9 +1156,9 @@ static int tc_wgrad_batch(const G2Job* jobs, int nprob, int64_t rows, int N, flo
 
 // dW[128,N] = Y[rows,128]^T X[rows,N] ; db[128] = colsum(Y)  (db may be NULL).  ws: tc_wgrad_workspace_floats
 static int tc_wgrad(const float* Y, int64_t ldy, const float* X, int64_t ldx, int64_t rows, int N, float* dW,
-                    int64_t lddw, float* db, float* ws, cudaStream_t st) {
+                    int64_t lddw, float* db, float* ws, cudaStream_t st, int single = 0) {
   const G2Job job{Y, ldy, X, ldx, dW, lddw, db};
-  return tc_wgrad_batch(&job, 1, rows, N, ws, st);
+  return tc_wgrad_batch(&job, 1, rows, N, ws, st, single);
 }
 
 }  // namespace tc

@@ -1,5 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t10.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t10.log
-timeout 300 python bench.py --no-cpu-baseline --no-train-step > gpurun_out/b10.json 2> gpurun_out/b10.err
-timeout 300 python bench.py --no-cpu-baseline --no-train-step --mode tf32 > gpurun_out/b10_tf32.json 2> gpurun_out/b10_tf32.err
-X2GNN_CPASYNC=0 timeout 300 python bench.py --no-cpu-baseline --no-train-step > gpurun_out/b10_old.json 2> gpurun_out/b10_old.err
-tail -3 gpurun_out/t10.log
+timeout 600 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_v3.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train-step > gpurun_out/ncu_ll.log 2>&1

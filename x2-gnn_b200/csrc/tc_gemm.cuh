@@ -6,12 +6,11 @@
 //
 // Two persistent, warp-specialised kernels (1 CTA / SM, 800 threads):
 //   warp 0      : TMEM allocation + single-thread tcgen05.mma issue
-//   warps 1..16 : producers -- coalesced 128-bit global loads of fp32 activations, hi/lo split in
-//                 registers, 128-bit stores into the UMMA canonical SWIZZLE_128B smem layout
-//                 (the split has to touch every element anyway, so LDG->STS replaces TMA here).
-//                 Two producer warps per SM sub-partition and two chunks of loads in flight per
-//                 thread: with one warp per sub-partition the kernel was issue-latency bound
-//                 (ncu: 13.7 cycles per issued instruction, profiles/r1_notes.md).
+//   warps 1..16 : producers.  Aligned operands (the conv path): every thread copies its 16-byte (8-byte
+//                 for 168-byte sbf rows) pieces of raw fp32 with cp.async straight into the hi half of
+//                 the UMMA canonical smem layout, several chunks ahead and without holding registers,
+//                 then reads its own pieces back and derives the lo half (see "Split precision" below).
+//                 Unaligned operands: LDG.128 -> hi/lo split in registers -> STS.128.
 //   warps 17..24: epilogue -- tcgen05.ld of the fp32 accumulator (one output row per thread),
 //                 transposed through a padded smem tile so that every global store instruction
 //                 writes whole 128-byte lines, bias / accumulate fused
@@ -29,7 +28,10 @@
 //       CTAs, partial tiles summed in fixed order by k_splitk_reduce => deterministic wgrad).
 //
 // Split precision: the tensor core TRUNCATES fp32 operand bits to tf32 (verified with
-// tools/umma_ts_probe.cu), so hi and lo are rounded to nearest tf32 in software before they are stored.
+// tools/umma_ts_probe.cu).  Register-staged operands and the weights are split in software into
+// hi = rn_tf32(x), lo = rn_tf32(x - hi).  cp.async-staged activations keep the RAW word as the hi operand
+// (hardware truncation) and lo = rn_tf32(x - trunc_tf32(x)): the difference is exact, |x - hi - lo| <=
+// 2^-21 |x| with either scheme.
 #pragma once
 #include "common.cuh"
 

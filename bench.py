@@ -42,14 +42,16 @@ def algorithmic_bytes(E, T, D, S, R, A):
     return fwd, bwd
 
 
-def host_workload(seed: int, nmol: int = NMOL):
+def host_workload(rank: int = 0, world: int = 1, nmol: int = NMOL):
+    """The rank's graphs of a global batch of nmol * world molecules (seed 0), whole molecules dealt to
+    ranks balanced by triplet count (x2gnn_b200.ddp.shard_graphs); world == 1 is the seed-0 batch."""
     from x2gnn_b200 import synth
-    b = synth.qm9_batch(nmol, seed=seed)
+    b, mine = synth.qm9_shard(nmol, world, rank, seed=0)
     tri = synth.triplets_host(b["edge_index"], len(b["x"]))[0]
     E = b["edge_index"].shape[1]
-    ci = synth.conv_inputs(E, tri, DIMS["D"], DIMS["S"], DIMS["R"], DIMS["A"], seed=seed)
+    ci = synth.conv_inputs(E, tri, DIMS["D"], DIMS["S"], DIMS["R"], DIMS["A"], seed=rank)
     # central atom j of every directed bond (i -> j): all triplets of a target bond share it (xgnn.py:57-58)
-    return dict(N=len(b["x"]), E=E, T=tri.shape[1], center=b["edge_index"][1].copy(), **ci)
+    return dict(N=len(b["x"]), E=E, T=tri.shape[1], center=b["edge_index"][1].copy(), nmol=len(mine), **ci)
 
 
 # ---------------------------------------------------------------------------------- clocks
@@ -145,13 +147,13 @@ def run_reference(args):
     ncores = os.cpu_count() or 1
     steps, warmup = args.steps, args.warmup
     # bounded sample: pick the number of molecules so that (steps + warmup) steps fit ~150 s
-    probe = host_workload(0, 16)
+    probe = host_workload(0, 1, 16)
     t_probe = time_cpu(oracle_step_fn(probe, ncores), 1, warmup=1)
     rate = probe["T"] / t_probe
-    full = host_workload(0, NMOL)
+    full = host_workload(0, 1, NMOL)
     budget_T = rate * 150.0 / max(steps + warmup, 1)
     nmol = NMOL if budget_T >= full["T"] else max(4, min(NMOL, int(NMOL * budget_T / full["T"])))
-    w = full if nmol == NMOL else host_workload(0, nmol)
+    w = full if nmol == NMOL else host_workload(0, 1, nmol)
     sec = time_cpu(oracle_step_fn(w, ncores), steps, warmup=warmup)
     value = w["T"] / sec
     sample = (f"{nmol} of {NMOL} molecules of the seed-0 batch (E={w['E']}, T={w['T']}), "
@@ -186,9 +188,10 @@ def train_step_bench(dev, world, rank, steps, warmup, with_cpu):
     model = XGNNPoly(**HPARAMS).to(dev)
     ema = torch.optim.swa_utils.AveragedModel(model, multi_avg_fn=torch.optim.swa_utils.get_ema_multi_avg_fn(0.95))
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)    # same update rule, one kernel
-    b = synth.qm9_batch(NMOL, seed=rank)
+    b, mine = synth.qm9_shard(NMOL, world, rank, seed=0)     # balanced share of the global batch of NMOL * world
+    nmine = len(mine)
     data = {k: (torch.from_numpy(v).to(dev) if hasattr(v, "shape") else v) for k, v in b.items()}
-    y = torch.zeros(NMOL, device=dev)
+    y = torch.zeros(nmine, device=dev)
     bucket = ddp.FlatGradBucket(model.parameters())
 
     def step():
@@ -226,7 +229,9 @@ def train_step_bench(dev, world, rank, steps, warmup, with_cpu):
     # the step is bound by host-side launch overhead (~800 launches), so host jitter shows: mean and median
     res = {"molecules_per_sec": world * NMOL / (ms * 1e-3), "ms_per_step": ms, "steps": steps,
            "ms_per_step_median": per_step[len(per_step) // 2], "ms_per_step_min": per_step[0],
-           "molecules_per_gpu": NMOL, "loss": float(loss.detach()), "N": len(b["x"]), "E": int(b["edge_index"].shape[1])}
+           "molecules_per_gpu": NMOL, "molecules_this_rank": nmine, "loss": float(loss.detach()), "N": len(b["x"]),
+           "E": int(b["edge_index"].shape[1]),
+           "sharding": "global batch of 128 x N molecules (seed 0), whole molecules dealt to ranks balanced by triplet count"}
     if with_cpu and rank == 0:
         from oracle import model as omodel
         ncores = os.cpu_count() or 1
@@ -267,7 +272,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     steps, warmup = args.steps, max(args.warmup, 3)
 
-    w = host_workload(seed=rank)
+    w = host_workload(rank, world)
     E, T = w["E"], w["T"]
     D, H, S, R, A = (DIMS[k] for k in "DHSRA")
     torch.manual_seed(0)
@@ -481,7 +486,8 @@ def run_ours(args):
                    "molecules_per_gpu": NMOL, "E": E, "T": T, "precision_mode": ("fp32 SIMT (1e-5 parity)" if args.mode == "fp32" else
                                       "REDUCED PRECISION: one tf32 pass in the Linear layers (2e-2 class)" if args.mode == "tf32" else
                                       "fp32 I/O, Linear layers on tcgen05 in 3xTF32 split precision (1e-5 parity)"),
-                   "parallelism": f"dp{world} (graph batches sharded per GPU, NCCL grad all-reduce)",
+                   "parallelism": f"dp{world} (global batch of {NMOL} x {world} molecules, whole molecules dealt to ranks "
+                                  f"balanced by triplet count; NCCL all-reduce of the flat parameter gradient)",
                    "l2": f"no flush: per-step T-row inputs {680 * T / 1e6:.0f} MB > 126 MB L2"},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

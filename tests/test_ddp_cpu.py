@@ -57,6 +57,28 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def test_qm9_shard_partitions_the_global_batch():
+    """bench.py's multi-GPU workload: every rank generates the same global list and keeps whole molecules;
+    world == 1 is the plain seed-0 batch; the shares are disjoint, complete and balanced by triplets."""
+    from x2gnn_b200 import synth
+    one, ids = synth.qm9_shard(12, 1, 0, seed=3)
+    ref = synth.qm9_batch(12, seed=3)
+    assert ids == list(range(12))
+    for k, v in ref.items():
+        if hasattr(v, "shape"):
+            assert np.array_equal(one[k], v), k
+    world = 3
+    seen, loads = [], []
+    for r in range(world):
+        b, mine = synth.qm9_shard(12, world, r, seed=3)
+        seen += mine
+        assert b["num_graphs"] == len(mine) and int(b["edge_num"].sum()) == b["edge_index"].shape[1]
+        assert int(b["edge_index"].max()) < len(b["x"])          # node ids are local to the rank's batch
+        loads.append(synth.triplets_host(b["edge_index"], len(b["x"]))[0].shape[1])
+    assert sorted(seen) == list(range(12 * world))
+    assert max(loads) - min(loads) < 0.15 * max(loads), loads
+
+
 def test_flat_bucket_allreduce_gloo_world2(tmp_path):
     world, port, out = 2, _free_port(), str(tmp_path / "res.pt")
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)

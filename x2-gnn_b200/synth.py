@@ -89,6 +89,24 @@ def qm9_batch(num_mols: int, seed: int = 0, nmin: int = 9, nmax: int = 29, **kw)
     return collate(mols, seed=seed, **kw)
 
 
+def qm9_shard(mols_per_rank: int, world: int, rank: int, seed: int = 0, nmin: int = 9, nmax: int = 29, **kw):
+    """BASELINE.json configs[4]: the rank's share of a global batch of `mols_per_rank * world` QM9-sized
+    molecules.  Whole molecules are dealt to ranks by `ddp.shard_graphs`, balanced by their triplet
+    counts (conv cost ~ T), so every rank generates the same global list and keeps its own
+    part.  world == 1 reproduces `qm9_batch(mols_per_rank, seed)` exactly.  Returns (batch, graph ids)."""
+    from .ddp import shard_graphs
+    rng = np.random.default_rng(seed)
+    mols = [synth_mol(int(rng.integers(nmin, nmax + 1)), rng) for _ in range(mols_per_rank * world)]
+    if world == 1:
+        return collate(mols, seed=seed, **kw), list(range(len(mols)))
+    costs = []
+    for pos, _ in mols:
+        deg = np.bincount(radius_edges(pos, kw.get("cutoff", CUTOFF))[1], minlength=len(pos))
+        costs.append(int((deg * (deg - 1)).sum()))          # triplets centred on every atom
+    mine = shard_graphs(costs, world)[rank]
+    return collate([mols[g] for g in mine], seed=seed + 104729 * rank, **kw), mine
+
+
 def ball_batch(num_mols: int, n_atoms: int = 500, seed: int = 0, **kw):
     """BASELINE.json configs[3]: ball-packed `n_atoms`-atom graphs."""
     rng = np.random.default_rng(seed)

@@ -209,6 +209,8 @@ typedef struct {
   float* lse;    /* [E, H]   log-sum-exp of the logits per (target, head) */
   float* ea;     /* [T, D]   lin_edge(edge_attr)  (NULL if A == 0) */
   float* sg;     /* [T, D]   lin_sbf(sbf) */
+  float* xs;     /* [E, D]   x * lin_rbf(rbf), the filtered source features (sbftransformer_conv.py:100); optional:
+                    NULL => fwd keeps it in its workspace and bwd recomputes it (one more E-scale kernel) */
 } x2_conv_saved;
 
 typedef struct {

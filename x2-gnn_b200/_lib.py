@@ -44,7 +44,8 @@ class ConvDesc(C.Structure):
 
 
 class ConvSaved(C.Structure):
-    _fields_ = [("qkvs", c_f32p), ("attn", c_f32p), ("lse", c_f32p), ("ea", c_f32p), ("sg", c_f32p)]
+    _fields_ = [("qkvs", c_f32p), ("attn", c_f32p), ("lse", c_f32p), ("ea", c_f32p), ("sg", c_f32p),
+                ("xs", c_f32p)]
 
 
 class ConvGrads(C.Structure):

@@ -184,7 +184,7 @@ int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* ws, siz
 
 extern "C" {
 
-int x2_version(void) { return 100; }  // 0.1.0
+int x2_version(void) { return 101; }  // 0.1.1: x2_conv_saved.xs, X2_MODE_TF32
 
 int64_t x2_launch_count(void) { return (int64_t)x2::g_launches.load(); }
 

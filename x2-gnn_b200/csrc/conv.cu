@@ -947,6 +947,7 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
   if (E == 0) return X2_OK;
 
   phase_begin(st);
+  if (s->xs) w.xs = s->xs;          // kept for the backward (saved.xs) instead of living in the workspace
   // (1) x_src = x * lin_rbf(rbf)                                             :99-100
   k_rbf_filter<<<filter_grid(E), kFilterRows * 32, (size_t)D * d->R * sizeof(float), st>>>(
       d->x, d->rbf, d->w_rbf, E, D, d->R, w.xs, nullptr);
@@ -1075,9 +1076,13 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
   const bool batched = L.mode == X2_MODE_TF32X3 && D == kTcBlock &&
                        ((reinterpret_cast<uintptr_t>(d->x) | reinterpret_cast<uintptr_t>(g->dx)) & 15) == 0;
   const bool fused_tail = batched && R <= 16;        // k_filter_bwd_full recomputes F itself
-  k_rbf_filter<<<filter_grid(E), kFilterRows * 32, (size_t)D * R * sizeof(float), st>>>(
-      d->x, d->rbf, d->w_rbf, E, D, R, w.xs, fused_tail ? nullptr : w.F);
-  X2_LAUNCH_OK();
+  if (s->xs && fused_tail) {
+    w.xs = s->xs;                                    // the forward kept x * lin_rbf(rbf): nothing to recompute
+  } else {
+    k_rbf_filter<<<filter_grid(E), kFilterRows * 32, (size_t)D * R * sizeof(float), st>>>(
+        d->x, d->rbf, d->w_rbf, E, D, R, w.xs, fused_tail ? nullptr : w.F);
+    X2_LAUNCH_OK();
+  }
   // (6) node-level weight gradients
   if (batched) {          // the four weight gradients as problems of ONE launch (+ one reduction)
     const tc::G2Job jobs[4] = {

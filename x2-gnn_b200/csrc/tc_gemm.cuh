@@ -1089,8 +1089,17 @@ k_splitk_reduce_batch(const ReduceBatch b, int splits, int64_t M, int N) {
   const float* src = is_bias ? b.colsum[pi] : b.partial[pi];
   const bool live = idx < lim && src != nullptr;
   float s = 0.f;
-  if (live)
-    for (int z = g; z < splits; z += 8) s += src[(int64_t)z * lim + idx];
+  if (live) {
+    int z = g;                                     // loads eight at a time, additions in the original order
+    for (; z + 56 < splits; z += 64) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = src[(int64_t)(z + 8 * u) * lim + idx];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; z < splits; z += 8) s += src[(int64_t)z * lim + idx];
+  }
   red[g][lane] = s;
   __syncthreads();
   if (g == 0 && live) {

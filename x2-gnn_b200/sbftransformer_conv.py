@@ -111,9 +111,11 @@ class _SBFConvFn(torch.autograd.Function):
         lse = torch.empty((E, H), **f32)
         ea = torch.empty((max(n_ea, 1), D), **f32) if A else None
         sg = torch.empty((max(T, 1), D), **f32)
+        xs = torch.empty((E, D), **f32)          # x * lin_rbf(rbf): kept so the backward does not recompute it
         out = torch.empty((E, D), **f32) if fuse else attn
         alpha = torch.empty((T, H), **f32) if cfg["want_alpha"] else None
-        saved = _lib.ConvSaved(_lib.ptr(qkvs), _lib.ptr(attn), _lib.ptr(lse), _lib.ptr(ea), _lib.ptr(sg))
+        saved = _lib.ConvSaved(_lib.ptr(qkvs), _lib.ptr(attn), _lib.ptr(lse), _lib.ptr(ea), _lib.ptr(sg),
+                               _lib.ptr(xs))
         L = _lib.lib()
         ws = _lib.workspace(L.x2_sbfconv_fwd_workspace_bytes(C.byref(desc)), dev)
         _lib.check(L.x2_sbfconv_fwd(C.byref(desc), C.byref(saved), _lib.ptr(out), _lib.ptr(alpha),
@@ -121,7 +123,7 @@ class _SBFConvFn(torch.autograd.Function):
         ctx.cfg, ctx.meta, ctx.dims = cfg, meta, (E, T, D, H, Cc, S, R, A, fuse)
         ctx.groups = groups
         ctx.tensors = t            # inputs + weights (kept alive; plain references, no graph)
-        ctx.saved_bufs = (qkvs, attn, lse, ea, sg)
+        ctx.saved_bufs = (qkvs, attn, lse, ea, sg, xs)
         if alpha is not None:
             ctx.mark_non_differentiable(alpha)
             return out, alpha
@@ -131,7 +133,7 @@ class _SBFConvFn(torch.autograd.Function):
     def backward(ctx, gout, _galpha):
         t, meta = ctx.tensors, ctx.meta
         E, T, D, H, Cc, S, R, A, fuse = ctx.dims
-        qkvs, attn, lse, ea, sg = ctx.saved_bufs
+        qkvs, attn, lse, ea, sg, xs = ctx.saved_bufs
         gout = _lib.f32(gout, "SBFTransformerConv.backward")
         dev = gout.device
         cfg = ctx.cfg
@@ -151,7 +153,8 @@ class _SBFConvFn(torch.autograd.Function):
             setattr(desc, n, _lib.ptr(getattr(meta, n)))
         _set_groups(desc, ctx.groups)
         n_ea = ctx.groups.rows if ctx.groups is not None else T
-        saved = _lib.ConvSaved(_lib.ptr(qkvs), _lib.ptr(attn), _lib.ptr(lse), _lib.ptr(ea), _lib.ptr(sg))
+        saved = _lib.ConvSaved(_lib.ptr(qkvs), _lib.ptr(attn), _lib.ptr(lse), _lib.ptr(ea), _lib.ptr(sg),
+                               _lib.ptr(xs))
 
         f32 = dict(dtype=torch.float32, device=dev)
         need = ctx.needs_input_grad     # (cfg, meta, x, rbf, sbf, edge_attr, ...)

@@ -1,3 +1,5 @@
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t13.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t13.log
-timeout 300 python bench.py --no-cpu-baseline --no-train-step > gpurun_out/b13.json 2> gpurun_out/b13.err
-tail -3 gpurun_out/t13.log
+python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t_final.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t_final.log
+timeout 600 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+tail -2 gpurun_out/smoke.log; tail -2 gpurun_out/t_final.log

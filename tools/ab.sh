@@ -1,5 +1,4 @@
-python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t_final.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t_final.log
-timeout 600 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
-tail -2 gpurun_out/smoke.log; tail -2 gpurun_out/t_final.log
+timeout 600 python -m pytest tests/test_gpu_tc_gemm.py tests/test_gpu_model.py -m gpu -x -q > gpurun_out/t14.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t14.log
+python tools/prof_train.py > gpurun_out/prof_train2.txt 2>&1
+git stash -q 2>/dev/null
+tail -3 gpurun_out/t14.log; tail -1 gpurun_out/prof_train2.txt

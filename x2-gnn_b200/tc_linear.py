@@ -23,38 +23,69 @@ _BLK = 128
 _ws_cache: dict = {}
 
 
-def _scratch(nbytes: int, dev):
-    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+def _scratch(nbytes: int, dev, stream_id: int):
+    key = (dev.index, stream_id)
     ws = _ws_cache.get(key)
-    if ws is None or ws[0].numel() < nbytes:
+    if ws is None or ws[2] < nbytes:
         t = _lib.workspace(nbytes, dev)
-        ws = (t, _lib.ptr(t), t.numel())
+        ws = (t, t.data_ptr(), t.numel())
         _ws_cache[key] = ws
     return ws
 
 
+_ws_need: dict = {}          # workspace sizes are functions of the (fixed) block shape / row count: ask once
+
+
+def _need_fwd(L):
+    n = _ws_need.get("g")
+    if n is None:
+        n = _ws_need["g"] = int(L.x2_tc_gemm_workspace_bytes(_BLK, _BLK))
+    return n
+
+
+def _need_bwd(L, M):
+    n = _ws_need.get(M)
+    if n is None:
+        n = _ws_need[M] = max(_need_fwd(L), int(L.x2_tc_wgrad_workspace_bytes(M, _BLK)))
+    return n
+
+
+def _f32c(t, what):
+    if t.dtype is not torch.float32:
+        raise TypeError(f"{what}: expected float32, got {t.dtype} (the sm_100a kernels are fp32-I/O)")
+    return t if t.is_contiguous() else t.contiguous()
+
+
 class _TCLinearFn(torch.autograd.Function):
+    # The harness model makes ~100 of these calls per training step and the step is bound by host time, so
+    # the Python around the two C calls is kept minimal: one current_stream() lookup, cached workspace
+    # sizes, raw integer pointers, the error path only when a call fails.
     @staticmethod
     def forward(ctx, x, weight, bias):
-        x2 = _lib.f32(x.reshape(-1, x.size(-1)), "TCLinear.x")
-        w = _lib.f32(weight, "TCLinear.weight")
-        b = _lib.f32(bias, "TCLinear.bias") if bias is not None else None
-        dev = _lib.require_cuda(x2, w, b, what="TCLinear")
+        x2 = _f32c(x.reshape(-1, x.size(-1)), "TCLinear.x")
+        w = _f32c(weight, "TCLinear.weight")
+        b = _f32c(bias, "TCLinear.bias") if bias is not None else None
+        dev = x2.device
+        if (dev.index not in _lib._checked_devices or not w.is_cuda or w.device != dev
+                or (b is not None and b.device != dev)):
+            _lib.require_cuda(x2, w, b, what="TCLinear")      # full check (incl. sm_100) on first use / mismatch
         M, K = x2.shape
         N = w.size(0)
         L = _lib.lib()
         y = torch.empty((M, N), dtype=torch.float32, device=dev)
-        _, ws_p, ws_n = _scratch(L.x2_tc_gemm_workspace_bytes(_BLK, _BLK), dev)
-        st = _lib.stream()
-        esz = 4
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _, ws_p, ws_n = _scratch(_need_fwd(L), dev, st)
+        xp, wp, yp = x2.data_ptr(), w.data_ptr(), y.data_ptr()
+        bp = b.data_ptr() if b is not None else 0
         for n0 in range(0, N, _BLK):
             nb = min(_BLK, N - n0)
             for k0 in range(0, K, _BLK):
                 kb = min(_BLK, K - k0)
-                _lib.check(L.x2_tc_gemm(
-                    x2.data_ptr() + k0 * esz, K, M, kb, w.data_ptr() + (n0 * K + k0) * esz, 1, K, nb,
-                    (b.data_ptr() + n0 * esz) if (b is not None and k0 == 0) else None,
-                    y.data_ptr() + n0 * esz, N, 1 if k0 > 0 else 0, ws_p, ws_n, st), "x2_tc_gemm")
+                rc = L.x2_tc_gemm(xp + k0 * 4, K, M, kb, wp + (n0 * K + k0) * 4, 1, K, nb,
+                                  (bp + n0 * 4) if (bp and k0 == 0) else None,
+                                  yp + n0 * 4, N, 1 if k0 > 0 else 0, ws_p, ws_n, st)
+                if rc:
+                    _lib.check(rc, "x2_tc_gemm")
         ctx.save_for_backward(x2, w)
         ctx.has_bias = b is not None
         ctx.x_shape = x.shape
@@ -65,34 +96,38 @@ class _TCLinearFn(torch.autograd.Function):
         x2, w = ctx.saved_tensors
         M, K = x2.shape
         N = w.size(0)
-        gy2 = _lib.f32(gy.reshape(M, N), "TCLinear.grad")
+        gy2 = _f32c(gy.reshape(M, N), "TCLinear.grad")
         dev = gy2.device
         L = _lib.lib()
-        st = _lib.stream()
-        esz = 4
+        st = torch.cuda.current_stream(dev).cuda_stream
         gx = gw = gb = None
-        _, ws_p, ws_n = _scratch(max(L.x2_tc_gemm_workspace_bytes(_BLK, _BLK), L.x2_tc_wgrad_workspace_bytes(M, _BLK)), dev)
-        if ctx.needs_input_grad[0]:
+        _, ws_p, ws_n = _scratch(_need_bwd(L, M), dev, st)
+        gp, wp, xp = gy2.data_ptr(), w.data_ptr(), x2.data_ptr()
+        need = ctx.needs_input_grad
+        if need[0]:
             gx = torch.empty((M, K), dtype=torch.float32, device=dev)
+            gxp = gx.data_ptr()
             for k0 in range(0, K, _BLK):          # output columns (in_features)
                 kb = min(_BLK, K - k0)
                 for n0 in range(0, N, _BLK):      # reduction over out_features
                     nb = min(_BLK, N - n0)
-                    _lib.check(L.x2_tc_gemm(
-                        gy2.data_ptr() + n0 * esz, N, M, nb, w.data_ptr() + (n0 * K + k0) * esz, K, 1, kb, None,
-                        gx.data_ptr() + k0 * esz, K, 1 if n0 > 0 else 0, ws_p, ws_n, st), "x2_tc_gemm")
+                    rc = L.x2_tc_gemm(gp + n0 * 4, N, M, nb, wp + (n0 * K + k0) * 4, K, 1, kb, None,
+                                      gxp + k0 * 4, K, 1 if n0 > 0 else 0, ws_p, ws_n, st)
+                    if rc:
+                        _lib.check(rc, "x2_tc_gemm")
             gx = gx.view(ctx.x_shape)
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        if need[1] or (ctx.has_bias and need[2]):
             gw = torch.empty((N, K), dtype=torch.float32, device=dev)
             gb = torch.empty(N, dtype=torch.float32, device=dev) if ctx.has_bias else None
+            gwp = gw.data_ptr()
+            gbp = gb.data_ptr() if gb is not None else 0
             for n0 in range(0, N, _BLK):
                 for k0 in range(0, K, _BLK):
                     kb = min(_BLK, K - k0)
-                    _lib.check(L.x2_tc_wgrad(
-                        gy2.data_ptr() + n0 * esz, N, x2.data_ptr() + k0 * esz, K, M, kb,
-                        gw.data_ptr() + (n0 * K + k0) * esz, K,
-                        (gb.data_ptr() + n0 * esz) if (gb is not None and k0 == 0) else None,
-                        ws_p, ws_n, st), "x2_tc_wgrad")
+                    rc = L.x2_tc_wgrad(gp + n0 * 4, N, xp + k0 * 4, K, M, kb, gwp + (n0 * K + k0) * 4, K,
+                                       (gbp + n0 * 4) if (gbp and k0 == 0) else None, ws_p, ws_n, st)
+                    if rc:
+                        _lib.check(rc, "x2_tc_wgrad")
         return gx, gw, gb
 
 

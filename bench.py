@@ -449,25 +449,35 @@ def run_ours(args):
     # ------------------------------------------------ roofline of the layer's kernels (rank 0)
     fwd_b, bwd_b = algorithmic_bytes(E, T, D, S, R, A)
     kernel_ms = sum(v[0] for v in phases.values()) / max(steps, 1)
+    phase_ms = {k: round(v[0] / max(steps, 1), 4) for k, v in phases.items()}
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = (fwd_b + bwd_b) / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
-    phase_ms = {k: round(v[0] / max(steps, 1), 4) for k, v in phases.items()}
     # DRAM traffic of the same step from the committed ncu capture (only valid for the same workload / mode)
-    traffic, traffic_src = None, None
+    traffic, traffic_src, phase_rates = None, None, None
     tpath = os.path.join(ROOT, "profiles", "r1_step_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         if tj.get("E") == E and tj.get("T") == T and tj.get("mode") == args.mode:
             traffic, traffic_src = tj["dram_bytes_per_step"], tj["source"]
+            # per phase: DRAM bytes of the committed ncu launch list / event time measured in THIS run
+            if "phase_dram_MB" in tj:
+                phase_rates = {k: {"dram_MB": round(mb, 1), "ms": phase_ms[k],
+                                   "dram_GBs": round(mb / phase_ms[k], 1) if phase_ms.get(k) else None,
+                                   "frac_of_peak": round(mb / phase_ms[k] / peak, 3) if phase_ms.get(k) else None}
+                               for k, mb in tj["phase_dram_MB"].items() if k in phase_ms}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel": "all launches of x2_sbfconv_fwd + x2_sbfconv_bwd (one layer step)",
                 "algorithmic_bytes_per_step": fwd_b + bwd_b, "kernel_ms_per_step": kernel_ms,
-                "phase_ms_per_step": phase_ms}
+                "phase_ms_per_step": phase_ms,
+                # how close each phase runs to the memory system with the bytes it actually moves (the gap
+                # between `achieved` and these rates is traffic that is not algorithmic: materialised
+                # per-triplet intermediates)
+                "phase_dram_rates": phase_rates}
 
     # ------------------------------------------------ CPU baseline (N = 1 only, bounded)
     cpu = None

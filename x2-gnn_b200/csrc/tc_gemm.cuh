@@ -173,6 +173,46 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-collective forms: EVERY lane of a converged warp executes the call with the same operands and one
+// elected lane issues the instruction.  Keeping the MMA warp's loops warp-uniform lets the compiler hold
+// descriptors and tensor-memory addresses in uniform registers; with the loops under `if (lane == 0)` it
+// wrapped every UTCHMMA in a vote / elect / 4 x R2UR.BROADCAST waterfall (~14 dependent instructions per
+// MMA): the single issuing thread then needed ~1 650 cycles per 32-row chunk whatever the number of
+// MMAs, and that -- not HBM, not the tensor pipe -- was the period of the whole pipeline (ablation in
+// profiles/r1_notes.md: MMA path alone 0.152 ms of gemm_e's 0.181 ms, one pass instead of three: same).
+__device__ __forceinline__ uint32_t elect_one() {        // 1 in exactly one lane of the (converged) warp
+  uint32_t is_leader;
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, q;\n"
+      "}\n" : "=r"(is_leader));
+  return is_leader;
+}
+// `leader` comes from ONE elect_one() call per role, so the same thread issues the MMAs and the commits
+// that track them.
+__device__ __forceinline__ void umma_tf32_ts_w(uint32_t leader, uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint32_t leader, uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.b32 q, %1, 0;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
                "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
@@ -349,38 +389,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
     // =============================== MMA issuer ===============================
     const uint32_t idesc = make_idesc(kTileM, 0, 0);     // M = 128 channels, N = 128 rows of the tile
     const uint32_t sA_u = smem_u32(sA);
+    const uint32_t leader = elect_one();
     uint32_t st = 0, ph = 0;   // smem ring position / phase
     uint32_t tcount = 0;       // tile counter (TMEM accumulator buffer)
     for (int pi = pi_beg; pi < pi_end; ++pi) {
     asm volatile("bar.sync 2, 160;" ::: "memory");        // this problem's weights are in tensor memory
     tc_fence_after();
-    if (lane == 0) {
-      for (int64_t tile = cta; tile < ntiles; tile += ncta, ++tcount) {
-        const uint32_t buf = tcount & 1;
-        mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1);
+    // the whole warp walks the loops (uniform control flow); one elected lane issues each MMA / commit
+    for (int64_t tile = cta; tile < ntiles; tile += ncta, ++tcount) {
+      const uint32_t buf = tcount & 1;
+      mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * 128;
+      for (int kc = 0; kc < KC; ++kc) {
+        mbar_wait(&full[st], ph);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + buf * 128;
-        for (int kc = 0; kc < KC; ++kc) {
-          mbar_wait(&full[st], ph);
-          tc_fence_after();
-          const int kvalid = min(kChunkK, p.K - kc * kChunkK);
-          const int ksteps = (kvalid + 7) >> 3;
-          const uint64_t dxh = make_desc(sA_u + st * 2 * kChunkBytes, 16, 1024);
-          const uint64_t dxl = make_desc(sA_u + st * 2 * kChunkBytes + kChunkBytes, 16, 1024);
-          const uint32_t w_hi = tmem_base + kTmemWHi + kc * kChunkK, w_lo = tmem_base + kTmemWLo + kc * kChunkK;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t adv = (uint64_t)(ks * 2);      // +32 bytes (>>4) along K inside the swizzle row
-            umma_tf32_ts(taddr, w_hi + ks * 8, dxh + adv, idesc, (kc | ks) != 0);
-            if (!p.single) {
-              umma_tf32_ts(taddr, w_lo + ks * 8, dxh + adv, idesc, 1);
-              umma_tf32_ts(taddr, w_hi + ks * 8, dxl + adv, idesc, 1);
-            }
+        const int kvalid = min(kChunkK, p.K - kc * kChunkK);
+        const int ksteps = (kvalid + 7) >> 3;
+        uint64_t dxh = make_desc(sA_u + st * 2 * kChunkBytes, 16, 1024);
+        uint64_t dxl = make_desc(sA_u + st * 2 * kChunkBytes + kChunkBytes, 16, 1024);
+        uint32_t w_hi = tmem_base + kTmemWHi + kc * kChunkK, w_lo = tmem_base + kTmemWLo + kc * kChunkK;
+        if (p.single) {
+          for (int ks = 0; ks < ksteps; ++ks, dxh += 2, w_hi += 8)
+            umma_tf32_ts_w(leader, taddr, w_hi, dxh, idesc, (kc | ks) != 0);
+        } else {
+          for (int ks = 0; ks < ksteps; ++ks, dxh += 2, dxl += 2, w_hi += 8, w_lo += 8) {   // +32 bytes (>>4) along K
+            umma_tf32_ts_w(leader, taddr, w_hi, dxh, idesc, (kc | ks) != 0);
+            umma_tf32_ts_w(leader, taddr, w_lo, dxh, idesc, 1);
+            umma_tf32_ts_w(leader, taddr, w_hi, dxl, idesc, 1);
           }
-          umma_commit(&empty[st]);          // smem slot reusable once these MMAs retire
-          if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[buf]);           // accumulator complete
+        umma_commit_w(leader, &empty[st]);  // smem slot reusable once these MMAs retire
+        if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
       }
+      umma_commit_w(leader, &tfull[buf]);   // accumulator complete
     }
     __syncwarp();
     }
@@ -700,31 +742,35 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
   const int64_t nchunks = rend > rbeg ? (rend - rbeg + kChunkK - 1) / kChunkK : 0;
 
   if (warp == 0) {
-    if (lane == 0 && nchunks > 0) {
+    if (nchunks > 0) {                                            // whole warp, uniform control flow (see umma_tf32_ts_w)
       const uint32_t idesc = make_idesc(p.N_pad, 0, 1);          // A from TMEM, B MN-major
       const uint32_t s_u = smem_u32(sS);
+      const uint32_t leader = elect_one();
       uint32_t st = 0, ph = 0;
       for (int64_t c = 0; c < nchunks; ++c) {
         mbar_wait(&full[st], ph);
         tc_fence_after();
         const uint32_t x_hi = s_u + st * stage_bytes, x_lo = x_hi + xbytes;
-        const uint32_t y_hi = tmem_base + kG2YCol + st * 64, y_lo = y_hi + 32;
+        uint32_t y_hi = tmem_base + kG2YCol + st * 64, y_lo = y_hi + 32;
         const int kvalid = (int)min((int64_t)kChunkK, rend - rbeg - c * kChunkK);
         const int ksteps = (kvalid + 7) >> 3;
-        const uint64_t dxh = make_desc(x_hi, 4096, 512, kLayoutSW128Base32);
-        const uint64_t dxl = make_desc(x_lo, 4096, 512, kLayoutSW128Base32);
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t adv = (uint64_t)(ks * 64);       // one K=8 step = two 4-row k-groups = 1024 B (>>4)
-          umma_tf32_ts(tmem_base, y_hi + ks * 8, dxh + adv, idesc, (c | ks) != 0);
-          if (!p.single) {
-            umma_tf32_ts(tmem_base, y_lo + ks * 8, dxh + adv, idesc, 1);
-            umma_tf32_ts(tmem_base, y_hi + ks * 8, dxl + adv, idesc, 1);
+        uint64_t dxh = make_desc(x_hi, 4096, 512, kLayoutSW128Base32);
+        uint64_t dxl = make_desc(x_lo, 4096, 512, kLayoutSW128Base32);
+        // one K=8 step = two 4-row k-groups = 1024 B (>>4 = 64)
+        if (p.single) {
+          for (int ks = 0; ks < ksteps; ++ks, dxh += 64, y_hi += 8)
+            umma_tf32_ts_w(leader, tmem_base, y_hi, dxh, idesc, (c | ks) != 0);
+        } else {
+          for (int ks = 0; ks < ksteps; ++ks, dxh += 64, dxl += 64, y_hi += 8, y_lo += 8) {
+            umma_tf32_ts_w(leader, tmem_base, y_hi, dxh, idesc, (c | ks) != 0);
+            umma_tf32_ts_w(leader, tmem_base, y_lo, dxh, idesc, 1);
+            umma_tf32_ts_w(leader, tmem_base, y_hi, dxl, idesc, 1);
           }
         }
-        umma_commit(&empty[st]);
+        umma_commit_w(leader, &empty[st]);
         if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
       }
-      umma_commit(tfull);
+      umma_commit_w(leader, tfull);
     }
     __syncwarp();
   } else if (warp <= kProducerWarps) {

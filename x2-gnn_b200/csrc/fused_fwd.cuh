@@ -176,7 +176,9 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_fwd(const F1Params p) {
 
   if (warp == kFMmaWarp) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // whole warp, uniform control flow; one elected lane issues (see umma_tf32_ts_w in tc_gemm.cuh)
+    {
+      const uint32_t leader = elect_one();
       const uint32_t idesc = make_idesc(kFT, 0, 0);          // M = 128 channels, N = 64 triplets
       const uint32_t sR_u = smem_u32(sR), sW_u = smem_u32(sW);
       uint32_t st = 0, ph = 0;
@@ -198,36 +200,34 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused_fwd(const F1Params p) {
               mbar_wait(&full[st], ph);
               tc_fence_after();
               const int ksteps = (min(kChunkK, p.A - kc * kChunkK) + 7) >> 3;
-              const uint64_t dh = make_desc(sR_u + st * 2 * kFChunkBytes, 16, 1024);
-              const uint64_t dl = make_desc(sR_u + st * 2 * kFChunkBytes + kFChunkBytes, 16, 1024);
-              const uint32_t w_hi = tmem_base + kTmemWHi + kc * kChunkK, w_lo = tmem_base + kTmemWLo + kc * kChunkK;
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint64_t adv = (uint64_t)(ks * 2);
-                umma_tf32_ts(t_ea, w_hi + ks * 8, dh + adv, idesc, (kc | ks) != 0);
-                umma_tf32_ts(t_ea, w_lo + ks * 8, dh + adv, idesc, 1);
-                umma_tf32_ts(t_ea, w_hi + ks * 8, dl + adv, idesc, 1);
+              uint64_t dh = make_desc(sR_u + st * 2 * kFChunkBytes, 16, 1024);
+              uint64_t dl = make_desc(sR_u + st * 2 * kFChunkBytes + kFChunkBytes, 16, 1024);
+              uint32_t w_hi = tmem_base + kTmemWHi + kc * kChunkK, w_lo = tmem_base + kTmemWLo + kc * kChunkK;
+              for (int ks = 0; ks < ksteps; ++ks, dh += 2, dl += 2, w_hi += 8, w_lo += 8) {
+                umma_tf32_ts_w(leader, t_ea, w_hi, dh, idesc, (kc | ks) != 0);
+                umma_tf32_ts_w(leader, t_ea, w_lo, dh, idesc, 1);
+                umma_tf32_ts_w(leader, t_ea, w_hi, dl, idesc, 1);
               }
-              umma_commit(&empty[st]);
+              umma_commit_w(leader, &empty[st]);
               if (++st == kFStages) { st = 0; ph ^= 1; }
             }
             for (int kc = 0; kc < KC_S; ++kc) {               // Sg^T += W_s . sbf^T   (A operand in smem)
               mbar_wait(&full[st], ph);
               tc_fence_after();
               const int ksteps = (min(kChunkK, p.S - kc * kChunkK) + 7) >> 3;
-              const uint64_t dh = make_desc(sR_u + st * 2 * kFChunkBytes, 16, 1024);
-              const uint64_t dl = make_desc(sR_u + st * 2 * kFChunkBytes + kFChunkBytes, 16, 1024);
-              const uint64_t wh = make_desc(sW_u + kc * kChunkBytes, 16, 1024);
-              const uint64_t wl = make_desc(sW_u + kWsKC * kChunkBytes + kc * kChunkBytes, 16, 1024);
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint64_t adv = (uint64_t)(ks * 2);
-                umma_tf32(t_sg, wh + adv, dh + adv, idesc, (kc | ks) != 0);
-                umma_tf32(t_sg, wl + adv, dh + adv, idesc, 1);
-                umma_tf32(t_sg, wh + adv, dl + adv, idesc, 1);
+              uint64_t dh = make_desc(sR_u + st * 2 * kFChunkBytes, 16, 1024);
+              uint64_t dl = make_desc(sR_u + st * 2 * kFChunkBytes + kFChunkBytes, 16, 1024);
+              uint64_t wh = make_desc(sW_u + kc * kChunkBytes, 16, 1024);
+              uint64_t wl = make_desc(sW_u + kWsKC * kChunkBytes + kc * kChunkBytes, 16, 1024);
+              for (int ks = 0; ks < ksteps; ++ks, dh += 2, dl += 2, wh += 2, wl += 2) {
+                umma_tf32_w(leader, t_sg, wh, dh, idesc, (kc | ks) != 0);
+                umma_tf32_w(leader, t_sg, wl, dh, idesc, 1);
+                umma_tf32_w(leader, t_sg, wh, dl, idesc, 1);
               }
-              umma_commit(&empty[st]);
+              umma_commit_w(leader, &empty[st]);
               if (++st == kFStages) { st = 0; ph ^= 1; }
             }
-            umma_commit(&tfull[set]);
+            umma_commit_w(leader, &tfull[set]);
           }
         }
       }

@@ -204,6 +204,18 @@ __device__ __forceinline__ void umma_tf32_ts_w(uint32_t leader, uint32_t d_tmem,
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
+__device__ __forceinline__ void umma_tf32_w(uint32_t leader, uint32_t taddr, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {      // A and B from smem
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(taddr),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_w(uint32_t leader, uint64_t* bar) {
   asm volatile(
       "{\n"

@@ -306,8 +306,6 @@ def run_ours(args):
         step()
     barrier()
     n0 = _lib.launch_count()
-    _lib.timing_read()
-    _lib.timing_enable(rank == 0)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         barrier()
@@ -316,10 +314,18 @@ def run_ours(args):
             step()
         ev1.record()
         barrier()
-    _lib.timing_enable(False)
     launches = (_lib.launch_count() - n0) // max(steps, 1)
-    phases = _lib.timing_read() if rank == 0 else {}
     ms = ev0.elapsed_time(ev1)
+    # per-phase CUDA-event times of the library in a SEPARATE pass: the event records sit between the
+    # launches (they would cost the timed region ~2 us each and keep a launch from overlapping the tail
+    # of its predecessor)
+    _lib.timing_read()
+    _lib.timing_enable(rank == 0)
+    for _ in range(steps):           # every rank steps (the step holds a collective when N > 1)
+        step()
+    barrier()
+    _lib.timing_enable(False)
+    phases = _lib.timing_read() if rank == 0 else {}
     t_all = torch.tensor([ms, float(T)], device=dev, dtype=torch.float64)
     if world > 1:
         tmax = t_all.clone()
@@ -347,16 +353,19 @@ def run_ours(args):
         for _ in range(warmup):
             seg_step()
         torch.cuda.synchronize()
-        _lib.timing_read()
-        _lib.timing_enable(True)
         ev0.record()
         for _ in range(steps):
             seg_step()
         ev1.record()
         torch.cuda.synchronize()
+        seg_ms = ev0.elapsed_time(ev1) / steps
+        _lib.timing_read()
+        _lib.timing_enable(True)             # phases in a separate pass, as for the headline
+        for _ in range(steps):
+            seg_step()
+        torch.cuda.synchronize()
         _lib.timing_enable(False)
         seg_phases = {k: round(v[0] / steps, 4) for k, v in _lib.timing_read().items()}
-        seg_ms = ev0.elapsed_time(ev1) / steps
         seg_bytes = (4 * (E * (D + R) + T * S + N * A + E * D) + 16 * T + 8 * E            # fwd
                      + 4 * (E * D + E * (D + R) + T * S + N * A) + 16 * T + 8 * E           # bwd reads
                      + 4 * (E * (D + R) + N * A))                                           # bwd writes

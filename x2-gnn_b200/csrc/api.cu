@@ -10,6 +10,11 @@ namespace x2 {
 
 // ------------------------------------------------------------------ instrumentation
 static std::atomic<long long> g_launches{0};
+bool pdl_enabled() {
+  static const int on = [] { const char* v = getenv("X2GNN_PDL"); return (v && v[0] == '0') ? 0 : 1; }();
+  return on != 0;
+}
+
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static std::atomic<int> g_timing{0};
@@ -184,7 +189,7 @@ int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* ws, siz
 
 extern "C" {
 
-int x2_version(void) { return 101; }  // 0.1.1: x2_conv_saved.xs, X2_MODE_TF32
+int x2_version(void) { return 102; }  // 0.1.1: x2_conv_saved.xs, X2_MODE_TF32
 
 int64_t x2_launch_count(void) { return (int64_t)x2::g_launches.load(); }
 

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(kFilterRows * 32)
 k_rbf_filter(const float* __restrict__ x, const float* __restrict__ rbf, const float* __restrict__ w_rbf,
              int64_t E, int D, int R, float* __restrict__ xs, float* __restrict__ F) {
   extern __shared__ __align__(16) float s_w[];     // W_r transposed to [R][D]: lanes read consecutive words
+  pdl_sync();
   for (int i = threadIdx.x; i < D * R; i += blockDim.x) s_w[(i % R) * D + i / R] = w_rbf[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -153,6 +154,7 @@ k_filter_bwd_full(const float* __restrict__ x, const float* __restrict__ rbf, co
                   float* __restrict__ partial) {
   constexpr int D = 128;
   extern __shared__ __align__(16) float s_w[];     // [R][D] transposed W_r, then [warps][RMAX][D] for the reduction
+  pdl_sync();
   for (int i = threadIdx.x; i < D * R; i += blockDim.x) s_w[(i % R) * D + i / R] = w_rbf[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -232,6 +234,7 @@ k_attn_fwd(const float* __restrict__ qkvs, int ldq, const float* __restrict__ ea
            int C, float scale, int fuse_skip, float dropout_p, uint64_t seed,
            float* __restrict__ attn, float* __restrict__ out, float* __restrict__ lse,
            float* __restrict__ alpha) {
+  pdl_sync();
   constexpr int D = 32 * VEC;
   const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (e >= E) return;
@@ -358,6 +361,7 @@ k_attn_fwd_stage(const float* __restrict__ qkvs, int ldq, const float* __restric
                  const int32_t* __restrict__ src, const int32_t* __restrict__ rowptr, int64_t E, int H, int C,
                  float scale, int fuse_skip, float* __restrict__ attn, float* __restrict__ out,
                  float* __restrict__ lse) {
+  pdl_sync();
   constexpr int D = 32 * VEC;
   constexpr int NARR = EA == kEaTriplet ? 2 : 1;
   constexpr int STAGE = NARR * kStRows * D;            // floats per stage
@@ -470,6 +474,7 @@ k_attn_bwd_tgt(const float* __restrict__ qkvs, int ldq, const float* __restrict_
                float scale, float dropout_p, uint64_t seed, float* __restrict__ dqkv, int ldg,
                float* __restrict__ dea, float* __restrict__ dsg, float* __restrict__ al,
                float* __restrict__ da_out) {
+  pdl_sync();
   constexpr int D = 32 * VEC;
   const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (e >= E) return;
@@ -592,6 +597,7 @@ template <int VEC>
 __global__ void __launch_bounds__(128)
 k_rows_segsum(const float* __restrict__ in, const int32_t* __restrict__ rowptr,
               const int32_t* __restrict__ order, int64_t M, float* __restrict__ out) {
+  pdl_sync();
   constexpr int D = 32 * VEC;
   const int64_t m = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (m >= M) return;
@@ -618,6 +624,7 @@ k_attn_bwd_src(const float* __restrict__ qkvs, int ldq, const float* __restrict_
                const float* __restrict__ da_in, const int32_t* __restrict__ tgt,
                const int32_t* __restrict__ rowptr_src, const int32_t* __restrict__ order_src,
                int64_t E, int H, int C, float scale, float* __restrict__ dqkv, int ldg) {
+  pdl_sync();
   constexpr int D = 32 * VEC;
   const int64_t f = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (f >= E) return;
@@ -805,18 +812,18 @@ static void launch_attn_fwd_inst(const x2_conv_desc* d, const x2_conv_saved* s, 
       constexpr int DEPTH = EA == kEaTriplet ? 2 : 3;
       constexpr int NARR = EA == kEaTriplet ? 2 : 1;
       const size_t smem = (size_t)4 * DEPTH * NARR * kStRows * 32 * VEC * sizeof(float) + 4 * DEPTH * sizeof(uint64_t);
-      k_attn_fwd_stage<VEC, EA, 2, DEPTH><<<grid, 128, smem, st>>>(
+      launch_k(k_attn_fwd_stage<VEC, EA, 2, DEPTH>, dim3(grid), dim3(128), smem, st, 
           s->qkvs, 4 * d->D, s->ea, d->ea_index, s->sg, d->src, d->rowptr_tgt, d->E, d->H, d->C, scale,
           d->fuse_skip, s->attn, out, s->lse);
       return;
     }
   }
   if (d->C == 2 * VEC)     // config.json: C = 8, 4 channels per lane => 2 lanes per head
-    k_attn_fwd<VEC, EA, GENERAL, 2><<<grid, 128, 0, st>>>(
+    launch_k(k_attn_fwd<VEC, EA, GENERAL, 2>, dim3(grid), dim3(128), 0, st, 
         s->qkvs, 4 * d->D, s->ea, d->ea_index, s->sg, d->src, d->rowptr_tgt, order, d->E,
         d->H, d->C, scale, d->fuse_skip, d->dropout_p, d->seed, s->attn, out, s->lse, alpha);
   else
-    k_attn_fwd<VEC, EA, GENERAL, 0><<<grid, 128, 0, st>>>(
+    launch_k(k_attn_fwd<VEC, EA, GENERAL, 0>, dim3(grid), dim3(128), 0, st, 
         s->qkvs, 4 * d->D, s->ea, d->ea_index, s->sg, d->src, d->rowptr_tgt, order, d->E,
         d->H, d->C, scale, d->fuse_skip, d->dropout_p, d->seed, s->attn, out, s->lse, alpha);
 }
@@ -844,11 +851,11 @@ static void launch_attn_bwd_tgt_inst(const x2_conv_desc* d, const x2_conv_saved*
   const unsigned grid = (unsigned)cdiv(d->E * 32, 128);
   const int32_t* order = d->tgt_sorted ? nullptr : d->order_tgt;     // sorted: order_tgt is the identity
   if (d->C == 2 * VEC)
-    k_attn_bwd_tgt<VEC, EA, DROP, 2><<<grid, 128, 0, st>>>(
+    launch_k(k_attn_bwd_tgt<VEC, EA, DROP, 2>, dim3(grid), dim3(128), 0, st, 
         s->qkvs, 4 * d->D, s->ea, d->ea_index, s->sg, s->attn, s->lse, gout, d->src, d->rowptr_tgt, order, d->E,
         d->H, d->C, scale, d->dropout_p, d->seed, w.dqkv, 3 * d->D, w.dea, w.dsg, w.al, w.da);
   else
-    k_attn_bwd_tgt<VEC, EA, DROP, 0><<<grid, 128, 0, st>>>(
+    launch_k(k_attn_bwd_tgt<VEC, EA, DROP, 0>, dim3(grid), dim3(128), 0, st, 
         s->qkvs, 4 * d->D, s->ea, d->ea_index, s->sg, s->attn, s->lse, gout, d->src, d->rowptr_tgt, order, d->E,
         d->H, d->C, scale, d->dropout_p, d->seed, w.dqkv, 3 * d->D, w.dea, w.dsg, w.al, w.da);
 }
@@ -871,12 +878,12 @@ static int launch_attn_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const 
   }
   X2_LAUNCH_OK();
   if (d->ea_index) {       // per-target rows -> per-table-row sums (fixed order)
-    k_rows_segsum<VEC><<<(unsigned)cdiv(d->ea_rows * 32, 128), 128, 0, st>>>(w.dea, d->ea_rowptr, d->ea_order,
+    launch_k(k_rows_segsum<VEC>, dim3((unsigned)cdiv(d->ea_rows * 32, 128)), dim3(128), 0, st, w.dea, d->ea_rowptr, d->ea_order,
                                                                              d->ea_rows, w.dea_tab);
     X2_LAUNCH_OK();
   }
   phase_end(X2_PHASE_ATTN_BWD_TGT, st);
-  k_attn_bwd_src<VEC><<<grid, 128, 0, st>>>(s->qkvs, 4 * d->D, s->sg, gout, w.al, w.da, d->tgt,
+  launch_k(k_attn_bwd_src<VEC>, dim3(grid), dim3(128), 0, st, s->qkvs, 4 * d->D, s->sg, gout, w.al, w.da, d->tgt,
                                             d->rowptr_src, d->order_src, d->E, d->H, d->C, scale, w.dqkv,
                                             3 * d->D);
   X2_LAUNCH_OK();
@@ -949,7 +956,7 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
   phase_begin(st);
   if (s->xs) w.xs = s->xs;          // kept for the backward (saved.xs) instead of living in the workspace
   // (1) x_src = x * lin_rbf(rbf)                                             :99-100
-  k_rbf_filter<<<filter_grid(E), kFilterRows * 32, (size_t)D * d->R * sizeof(float), st>>>(
+  launch_k(k_rbf_filter, dim3(filter_grid(E)), dim3(kFilterRows * 32), (size_t)D * d->R * sizeof(float), st, 
       d->x, d->rbf, d->w_rbf, E, D, d->R, w.xs, nullptr);
   X2_LAUNCH_OK();
   const Lin L{lin_mode(d->mode), w.img, nullptr, st, d->mode == X2_MODE_TF32};
@@ -1079,7 +1086,7 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
   if (s->xs && fused_tail) {
     w.xs = s->xs;                                    // the forward kept x * lin_rbf(rbf): nothing to recompute
   } else {
-    k_rbf_filter<<<filter_grid(E), kFilterRows * 32, (size_t)D * R * sizeof(float), st>>>(
+    launch_k(k_rbf_filter, dim3(filter_grid(E)), dim3(kFilterRows * 32), (size_t)D * R * sizeof(float), st, 
         d->x, d->rbf, d->w_rbf, E, D, R, w.xs, fused_tail ? nullptr : w.F);
     X2_LAUNCH_OK();
   }
@@ -1119,13 +1126,13 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
         attr_set = true;
       }
       if (RM == 8)
-        k_filter_bwd_full<8><<<fgrid, kFilterRows * 32, fsmem, st>>>(d->x, d->rbf, d->w_rbf, w.dxs, w.dxs2, g->dx,
+        launch_k(k_filter_bwd_full<8>, dim3(fgrid), dim3(kFilterRows * 32), fsmem, st, d->x, d->rbf, d->w_rbf, w.dxs, w.dxs2, g->dx,
             d->fuse_skip ? w.dx2 : nullptr, E, R, g->drbf, w.wg);
       else
-        k_filter_bwd_full<16><<<fgrid, kFilterRows * 32, fsmem, st>>>(d->x, d->rbf, d->w_rbf, w.dxs, w.dxs2, g->dx,
+        launch_k(k_filter_bwd_full<16>, dim3(fgrid), dim3(kFilterRows * 32), fsmem, st, d->x, d->rbf, d->w_rbf, w.dxs, w.dxs2, g->dx,
             d->fuse_skip ? w.dx2 : nullptr, E, R, g->drbf, w.wg);
       X2_LAUNCH_OK();
-      k_splitk_reduce<<<splitk_reduce_blocks(D, R, false), 256, 0, st>>>(w.wg, nullptr, (int)fgrid, D, R, g->dw_rbf, R,
+      launch_k(k_splitk_reduce, dim3(splitk_reduce_blocks(D, R, false)), dim3(256), 0, st, w.wg, nullptr, (int)fgrid, D, R, g->dw_rbf, R,
                                                                          nullptr);
       X2_LAUNCH_OK();
       phase_end(X2_PHASE_NODE_BWD, st);

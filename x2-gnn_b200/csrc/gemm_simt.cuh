@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(256)
 k_splitk_reduce(const float* __restrict__ partial, const float* __restrict__ colsum, int splits, int64_t M,
                 int N, float* __restrict__ out, int64_t ldo, float* __restrict__ bias) {
   __shared__ float red[8][33];
+  pdl_sync();
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int64_t MN = M * N;
   const int64_t nblk_out = (MN + 31) / 32;

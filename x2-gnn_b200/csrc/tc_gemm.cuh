@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();        // everything above overlapped the previous launch's tail; global memory from here on
 
   // ---- weights -> tensor memory (first epilogue warp of each lane quarter): lane = output channel n.
   // Loads are issued 32 at a time; only the MMA warp waits for the weights (named barrier 2), the
@@ -760,6 +761,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();        // global memory from here on
 
   const int64_t rbeg = cta * p.rows_per_cta;
   const int64_t rend = min(p.rows, rbeg + p.rows_per_cta);
@@ -1097,9 +1099,9 @@ static int tc_gemm_batch(const G1Prob* probs, int nprob, int ngroups, int64_t M,
   const int64_t ntiles = cdiv(M, kTileM);
   const int64_t per_group = kNumSM / ngroups;
   const int grid = (int)(ntiles < per_group ? ntiles : per_group) * ngroups;
-  if (piece == 16) k_tc_gemm<16><<<grid, kThreads, smem, st>>>(p);
-  else if (piece == 8) k_tc_gemm<8><<<grid, kThreads, smem, st>>>(p);
-  else k_tc_gemm<0><<<grid, kThreads, smem, st>>>(p);
+  if (piece == 16) launch_k(k_tc_gemm<16>, dim3(grid), dim3(kThreads), smem, st, p);
+  else if (piece == 8) launch_k(k_tc_gemm<8>, dim3(grid), dim3(kThreads), smem, st, p);
+  else launch_k(k_tc_gemm<0>, dim3(grid), dim3(kThreads), smem, st, p);
   X2_LAUNCH_OK();
   return X2_OK;
 }
@@ -1149,6 +1151,7 @@ struct ReduceBatch {
 __global__ void __launch_bounds__(256)
 k_splitk_reduce_batch(const ReduceBatch b, int splits, int64_t M, int N) {
   __shared__ float red[8][33];
+  pdl_sync();
   const int pi = blockIdx.y;
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int64_t MN = M * N;
@@ -1225,12 +1228,12 @@ static int tc_wgrad_batch(const G2Job* jobs, int nprob, int64_t rows, int N, flo
   }
   p.nprob = nprob; p.N = N; p.N_pad = N_pad; p.rows = rows; p.rows_per_cta = rpc; p.stages = stages;
   p.single = single;
-  if (xmode == 1) k_tc_wgrad<1><<<cpp * nprob, kG2Threads, smem, st>>>(p);
-  else if (xmode == 2) k_tc_wgrad<2><<<cpp * nprob, kG2Threads, smem, st>>>(p);
-  else k_tc_wgrad<0><<<cpp * nprob, kG2Threads, smem, st>>>(p);
+  if (xmode == 1) launch_k(k_tc_wgrad<1>, dim3(cpp * nprob), dim3(kG2Threads), smem, st, p);
+  else if (xmode == 2) launch_k(k_tc_wgrad<2>, dim3(cpp * nprob), dim3(kG2Threads), smem, st, p);
+  else launch_k(k_tc_wgrad<0>, dim3(cpp * nprob), dim3(kG2Threads), smem, st, p);
   X2_LAUNCH_OK();
   const unsigned nblk = (unsigned)((128 * (int64_t)N + 31) / 32 + (any_bias ? 4 : 0));
-  k_splitk_reduce_batch<<<dim3(nblk, (unsigned)nprob), 256, 0, st>>>(rb, cpp, 128, N);
+  launch_k(k_splitk_reduce_batch, dim3(nblk, (unsigned)nprob), dim3(256), 0, st, rb, cpp, (int64_t)128, N);
   X2_LAUNCH_OK();
   return X2_OK;
 }

@@ -446,7 +446,7 @@ def run_ours(args):
     train = None
     if not args.no_train_step:
         try:
-            train = train_step_bench(dev, world, rank, max(3, min(steps, 10)), 3,
+            train = train_step_bench(dev, world, rank, max(3, min(steps, 10)), 5,
                                      with_cpu=(world == 1 and not args.no_cpu_baseline))
         except Exception as exc:  # keep the headline line even if the secondary metric fails
             train = {"error": f"{type(exc).__name__}: {exc}"}

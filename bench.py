@@ -232,6 +232,15 @@ def train_step_bench(dev, world, rank, steps, warmup, with_cpu):
            "molecules_per_gpu": NMOL, "molecules_this_rank": nmine, "loss": float(loss.detach()), "N": len(b["x"]),
            "E": int(b["edge_index"].shape[1]),
            "sharding": "global batch of 128 x N molecules (seed 0), whole molecules dealt to ranks balanced by triplet count"}
+    # ---- the same step with its dense part replayed as ONE CUDA graph (the eager step above is bound by the
+    # host: ~800 launches from Python).  Every replayed step still runs the whole path: `prepare` (the integer
+    # kernels building triplets + CSR metadata, eager, with their size read-backs) is inside the timed region,
+    # then forward, loss, backward, gradient all-reduce, clip, Adam and EMA replay from the graph.  A graph is
+    # tied to the batch's (N, E, T): a loader would keep one per padded shape bucket; the bench batch is fixed.
+    try:
+        res["cuda_graph"] = _train_step_graph(dev, world, rank, steps, data, y, nmine)
+    except Exception as exc:
+        res["cuda_graph"] = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
     if with_cpu and rank == 0:
         from oracle import model as omodel
         ncores = os.cpu_count() or 1
@@ -252,6 +261,74 @@ def train_step_bench(dev, world, rank, steps, warmup, with_cpu):
         res["cpu_baseline"] = {"molecules_per_sec": nm / sec, "cores": ncores, "kind": "port",
                                "sample": f"{nm}-molecule batch, 1 warm-up + 2 timed training steps of the oracle model"}
     return res
+
+
+def _train_step_graph(dev, world, rank, steps, data, y, nmine):
+    """The training step with forward + loss + backward + all-reduce + clip + Adam + EMA replayed from one
+    CUDA graph (x2gnn_b200.train_graph).  Checks the replayed loss against an identical model stepped eagerly."""
+    import torch
+    import torch.distributed as dist
+    from x2gnn_b200 import ddp
+    from x2gnn_b200.train_graph import GraphedTrainStep, dense_step
+    from x2gnn_b200.xgnn_model import XGNNPoly
+
+    torch.manual_seed(0)
+    model = XGNNPoly(**HPARAMS).to(dev)
+    bucket = ddp.FlatGradBucket(model.parameters()) if world > 1 else None
+    gs = GraphedTrainStep(model, data, y, lr=1e-3, bucket=bucket)
+    prep_stream = torch.cuda.Stream(device=dev)
+    prep_stream.wait_stream(torch.cuda.current_stream(dev))
+
+    def step():
+        # the per-batch integer work, every step (results identical to gs.prep), on its own stream so that its
+        # size read-backs do not drain the replay in flight -- as a loader thread preparing the next batch does
+        with torch.cuda.stream(prep_stream):
+            p2 = model.prepare(data)
+        gs.replay()
+        return p2
+
+    for _ in range(3):
+        p2 = step()
+    torch.cuda.synchronize(dev)
+    same_idx = bool(torch.equal(p2["tri"], gs.prep["tri"]))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 2)]
+    marks[0].record()
+    for i in range(steps):
+        step()
+        marks[i + 1].record()
+    torch.cuda.current_stream(dev).wait_stream(prep_stream)    # the last step's index work is inside the timing
+    marks[-1].record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = marks[0].elapsed_time(marks[-1]) / steps
+    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(steps))
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    out = {"molecules_per_sec": world * NMOL / (ms * 1e-3), "ms_per_step": ms,
+           "ms_per_step_median": per_step[len(per_step) // 2], "steps": steps,
+           "graph_loss": float(gs.loss.detach()), "indices_rebuilt_each_step_identical": same_idx,
+           "what": "per step: prepare() (triplet / CSR integer kernels, eager, own stream) + one graph replay of "
+                   "forward, loss, backward, all-reduce, clip, Adam, EMA"}
+    if world == 1:
+        # parity of the replayed arithmetic: an identical model stepped eagerly as many times lands on the same
+        # loss (the k-th loss is computed before the k-th update)
+        torch.manual_seed(0)
+        m2 = XGNNPoly(**HPARAMS).to(dev)
+        ps2 = [p for p in m2.parameters() if p.requires_grad]
+        o2 = torch.optim.Adam(ps2, lr=1e-3, fused=True)
+        pr2 = m2.prepare(data)
+        n_updates = gs.warmup_updates + 3 + steps
+        for _ in range(n_updates):
+            l2 = dense_step(m2, o2, ps2, data, pr2, y)
+        out["eager_loss_after_same_updates"] = float(l2.detach())
+        out["updates"] = n_updates
+    return out
 
 
 # ---------------------------------------------------------------------------------- our arm

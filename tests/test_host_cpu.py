@@ -142,3 +142,30 @@ def test_dropin_install():
     sys.path.remove(x2gnn_b200.DROPIN_DIR)
     for m in x2gnn_b200.DROPIN_MODULES:
         sys.modules.pop(m, None)
+
+
+def test_sync_free_embedding_matches_nn_embedding():
+    """EmbeddingBlock's graph-capturable lookup (distinct ids + histogram from XGNNPoly.prepare) against the
+    stock nn.Embedding(max_norm, scale_grad_by_freq, padding_idx) it replaces: same renormalised table,
+    same output, same gradients (atom_embedding.py of the reference; pure PyTorch, runs on the CPU)."""
+    from x2gnn_b200.xgnn_model import EmbeddingBlock, graph_layer_norm
+    torch.manual_seed(0)
+    a = EmbeddingBlock(32)
+    with torch.no_grad():
+        a.embedding.weight.mul_(3.0)              # some rows above max_norm = 3, some below
+        a.embedding.weight[6].mul_(0.05)
+    b = copy.deepcopy(a)
+    z = torch.tensor([1, 6, 6, 8, 1, 1, 7, 0, 6, 1])
+    g = torch.randn(z.numel(), 32)
+    ya = a(z)
+    (ya * g).sum().backward()
+    yb = b(z, torch.unique(z), torch.bincount(z, minlength=10))
+    (yb * g).sum().backward()
+    assert torch.allclose(a.embedding.weight, b.embedding.weight, rtol=1e-6, atol=0)   # in-place max_norm renorm
+    assert float(a.embedding.weight[1].detach().norm()) < 3.001 < 4 < float(a.embedding.weight[9].detach().norm())   # row 9 is not in z
+    assert torch.allclose(ya, yb, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(a.embedding.weight.grad, b.embedding.weight.grad, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(a.lin.weight.grad, b.lin.weight.grad, rtol=1e-5, atol=1e-6)
+    x = torch.randn(7, 4)
+    batch = torch.tensor([0, 0, 1, 1, 1, 3, 3])
+    assert torch.equal(graph_layer_norm(x, batch, 4), graph_layer_norm(x, batch, 4, counts=torch.tensor([2, 3, 0, 2])))

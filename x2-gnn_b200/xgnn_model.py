@@ -34,14 +34,46 @@ def _lin(i, o):
     return l
 
 
+class _EmbedByFreq(torch.autograd.Function):
+    """weight[z] whose weight gradient is scaled by the inverse frequency of every id in the batch -- the
+    arithmetic of nn.Embedding(scale_grad_by_freq=True, padding_idx=0) written with gather / index_add only,
+    so that it neither synchronises nor sorts (F.embedding's backward does) and can sit inside a CUDA graph.
+    `counts` [rows] is the batch histogram of `z`, built once per batch by `XGNNPoly.prepare`."""
+
+    @staticmethod
+    def forward(ctx, weight, z, counts):
+        ctx.save_for_backward(z, counts)
+        ctx.rows = weight.size(0)
+        return weight.index_select(0, z)
+
+    @staticmethod
+    def backward(ctx, g):
+        z, counts = ctx.saved_tensors
+        gw = torch.zeros(ctx.rows, g.size(1), dtype=g.dtype, device=g.device).index_add_(0, z, g)
+        gw = gw / counts.clamp(min=1).to(g.dtype).unsqueeze(1)
+        gw[0].zero_()                                     # padding_idx = 0
+        return gw, None, None
+
+
 class EmbeddingBlock(nn.Module):
     def __init__(self, embedding_size=128):
         super().__init__()
         self.embedding = nn.Embedding(10, embedding_size, padding_idx=0, max_norm=3.0, scale_grad_by_freq=True)
         self.lin = _lin(embedding_size, embedding_size)
 
-    def forward(self, z):
-        return F.silu(self.lin(self.embedding(z)))
+    def forward(self, z, z_rows=None, z_counts=None):
+        """With the batch's distinct ids `z_rows` and histogram `z_counts` (from `XGNNPoly.prepare`) the
+        lookup is sync-free: max_norm renormalises exactly the rows nn.Embedding would (those present in
+        the batch), in place, then gathers; otherwise it is the stock nn.Embedding call."""
+        if z_rows is None:
+            return F.silu(self.lin(self.embedding(z)))
+        emb = self.embedding
+        with torch.no_grad():
+            sub = emb.weight.index_select(0, z_rows)
+            nrm = sub.norm(p=emb.norm_type, dim=1, keepdim=True)
+            scale = torch.where(nrm > emb.max_norm, emb.max_norm / (nrm + 1e-7), torch.ones_like(nrm))
+            emb.weight.index_copy_(0, z_rows, sub * scale)
+        return F.silu(self.lin(_EmbedByFreq.apply(emb.weight, z, z_counts)))
 
 
 class ResidualLayer(nn.Module):
@@ -71,9 +103,10 @@ class AtomWise(nn.Module):
         return out
 
 
-def graph_layer_norm(x, batch, num_graphs, eps=1e-8):
-    """PyG 2.1.0 LayerNorm(affine=False) with `batch`: statistics over all rows AND channels of a graph."""
-    cnt = torch.bincount(batch, minlength=num_graphs).clamp(min=1).to(x.dtype)
+def graph_layer_norm(x, batch, num_graphs, eps=1e-8, counts=None):
+    """PyG 2.1.0 LayerNorm(affine=False) with `batch`: statistics over all rows AND channels of a graph.
+    `counts` [num_graphs] = rows per graph when the caller already has them (torch.bincount synchronises)."""
+    cnt = (torch.bincount(batch, minlength=num_graphs) if counts is None else counts).clamp(min=1).to(x.dtype)
     norm = (cnt * x.size(-1)).view(-1, 1)
     acc = torch.zeros(num_graphs, x.size(1), dtype=x.dtype, device=x.device)
     mean = acc.index_add(0, batch, x).sum(-1, keepdim=True) / norm
@@ -98,7 +131,7 @@ class SBFTransformer(nn.Module):
         self.conv_layers = conv_layers
 
     def forward(self, x, edge_index, edge_attr, batch, edge_sbf, node_rbf, edge_index_0, atom_batch, num_graphs,
-                edge_attr_index=None, edge_attr_target_index=None):
+                edge_attr_index=None, edge_attr_target_index=None, batch_counts=None):
         """`edge_attr` is [T, A] as in the reference; or a per-atom table [N, A] with either
         `edge_attr_index` [T] (rows gathered per triplet AFTER edgenn) or `edge_attr_target_index` [E] (the
         conv layers take the table itself: the row is constant over the triplets of a target bond, so
@@ -116,7 +149,7 @@ class SBFTransformer(nn.Module):
             res0 = out
             out = self.convs[i](sbf=edge_sbf, rbf=node_rbf, x=out, edge_index=edge_index, edge_attr=edge_attr,
                                 **conv_kw)
-            out = graph_layer_norm(out, batch, num_graphs)
+            out = graph_layer_norm(out, batch, num_graphs, counts=batch_counts)
             out = self.bf_skip[i](out)
             out = F.silu(self.dense_bf_skip[i](out)) + res0
             out = self.af_skip[i](out)
@@ -143,25 +176,51 @@ class XGNNPoly(nn.Module):
         # values as the reference's [T, A] gather, xgnn.py:57-58); False: gather per triplet as the reference
         self.segment_edge_attr = True
 
-    def forward(self, data: dict):
+    def prepare(self, data: dict) -> dict:
+        """The integer part of a forward pass, which depends on the batch only and not on the parameters:
+        triplets of the line graph (xgnn.py:52-53), the bond -> molecule map and its histogram
+        (model.py:46), the distinct atomic numbers of the batch (nn.Embedding's max_norm / frequency
+        bookkeeping) and the CSR metadata the conv layers cache per `edge_index` tensor.  `forward` calls it
+        itself; a caller that replays the dense part of the step as a CUDA graph calls it once per batch,
+        outside the capture (it reads output sizes back from the device), and passes the result in."""
+        from . import graph_meta
+        ei, z = data["edge_index"], data["x"]
+        B, E, N = int(data["num_graphs"]), int(ei.size(1)), int(z.size(0))
+        tri, a_j, a_i, a_k = vertex_to_edge_2(ei, N)
+        batch = torch.repeat_interleave(torch.arange(B, device=ei.device), data["edge_num"], output_size=E)
+        prep = {"tri": tri, "src_bond": tri[0].contiguous(), "a_j": a_j, "a_i": a_i, "a_k": a_k,
+                "batch": batch, "batch_counts": data["edge_num"].to(torch.int64),
+                "ei0": ei[0].contiguous(), "ei1": ei[1].contiguous(),
+                "z_rows": torch.unique(z), "z_counts": torch.bincount(z, minlength=self.emb_block.embedding.num_embeddings)}
+        # built here, found in the cache by the 4 layers (same tensor objects); referenced from `prep` so the
+        # device buffers outlive the cache's eviction for as long as a captured graph points at them
+        prep["line_graph_meta"] = graph_meta.get(tri, E)
+        if self.segment_edge_attr:
+            prep["edge_attr_groups"] = graph_meta.get_groups(prep["ei1"], N)
+        return prep
+
+    def forward(self, data: dict, prep: dict = None):
         """data: x[N] i64, atom_pos[N,3], edge_index[2,E] i64, edge_attr[E,338], edge_num[B], batch[N],
-        num_graphs -- the PyG-collated record layout of the reference dataset (qm9_allprop.py:18)."""
-        pos, ei = data["atom_pos"], data["edge_index"]
+        num_graphs -- the PyG-collated record layout of the reference dataset (qm9_allprop.py:18).
+        `prep` = `self.prepare(data)` when the caller has already built the index tensors of this batch."""
+        if prep is None:
+            prep = self.prepare(data)
+        pos = data["atom_pos"]
         B = int(data["num_graphs"])
-        d = torch.norm(pos[ei[0]] - pos[ei[1]], dim=1)
-        batch = torch.repeat_interleave(torch.arange(B, device=d.device), data["edge_num"],
-                                        output_size=ei.size(1))
+        tri, a_j, a_i, a_k = prep["tri"], prep["a_j"], prep["a_i"], prep["a_k"]
+        d = torch.norm(pos[prep["ei0"]] - pos[prep["ei1"]], dim=1)
         env = self.envelop_function(d)[:, None]
-        tri, a_j, a_i, a_k = vertex_to_edge_2(ei, data["x"].size(0))
         neo_x = F.silu(self.mat_trans(data["edge_attr"] * env))
-        atom_emb = self.emb_block(data["x"])            # [N, A]; the reference gathers [a_j] here (xgnn.py:58)
+        # [N, A]; the reference gathers [a_j] here (xgnn.py:58)
+        atom_emb = self.emb_block(data["x"], prep["z_rows"], prep["z_counts"])
         ji, jk = pos[a_i] - pos[a_j], pos[a_k] - pos[a_j]
         ang = torch.atan2(torch.linalg.cross(ji, jk).norm(dim=1), (ji * jk).sum(1))
-        edge_sbf = self.sbf_layer(d, ang, tri[0])
+        edge_sbf = self.sbf_layer(d, ang, prep["src_bond"])
         node_rbf = self.rbf_layer(d) * env
         neo_x = F.silu(self.emb_trans(neo_x))
+        kw = dict(batch_counts=prep["batch_counts"])
         if self.segment_edge_attr:      # a_j[t] == ei[1][tri[1][t]]: the atom shared by both bonds of the triplet
-            return self.fin_model(neo_x, tri, atom_emb, batch, edge_sbf, node_rbf, ei[0], data["batch"], B,
-                                  edge_attr_target_index=ei[1])
-        return self.fin_model(neo_x, tri, atom_emb, batch, edge_sbf, node_rbf, ei[0], data["batch"], B,
-                              edge_attr_index=a_j)
+            return self.fin_model(neo_x, tri, atom_emb, prep["batch"], edge_sbf, node_rbf, prep["ei0"],
+                                  data["batch"], B, edge_attr_target_index=prep["ei1"], **kw)
+        return self.fin_model(neo_x, tri, atom_emb, prep["batch"], edge_sbf, node_rbf, prep["ei0"],
+                              data["batch"], B, edge_attr_index=a_j, **kw)

@@ -229,6 +229,18 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* saved, float* out
 int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* saved, const float* grad_out,
                    const x2_conv_grads* g, void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------- post-conv block
+ * Graph-wise LayerNorm without affine parameters: model.py:24,46 `LayerNorm(in_channels, eps=1e-8,
+ * affine=False)(x=out, batch=data.batch)` (torch_geometric 2.1.0: mean and variance over all rows AND
+ * channels of a molecule).  The rows of molecule g are rowptr[g] .. rowptr[g+1] of x[rowptr[B], D] (PyG
+ * collates graph after graph, so they are contiguous); rowptr is int32 [B+1], D % 4 == 0, buffers 16-byte
+ * aligned.  fwd writes y[.,D] and stats[B,2] = (mean, 1/sqrt(var+eps)) per molecule; bwd takes the forward's
+ * y and stats and grad_y, writes grad_x.  One CTA per molecule, fixed-order reductions (deterministic). */
+int x2_graph_layernorm_fwd(const float* x, const int32_t* rowptr, int64_t B, int32_t D, float eps, float* y,
+                           float* stats, void* stream);
+int x2_graph_layernorm_bwd(const float* y, const float* grad_y, const int32_t* rowptr, int64_t B, int32_t D,
+                           const float* stats, float* grad_x, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

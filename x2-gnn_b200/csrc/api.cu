@@ -189,7 +189,7 @@ int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* ws, siz
 
 extern "C" {
 
-int x2_version(void) { return 102; }  // 0.1.1: x2_conv_saved.xs, X2_MODE_TF32
+int x2_version(void) { return 103; }  // 0.1.2: x2_graph_layernorm_*
 
 int64_t x2_launch_count(void) { return (int64_t)x2::g_launches.load(); }
 

@@ -22,6 +22,7 @@ from torch import nn
 from .angular_basis_layer import F_B_2D
 from .edge_graph import vertex_to_edge_2
 from .envelop import poly_envelop
+from .graph_norm import graph_layer_norm_rows, rowptr_from_counts
 from .radial_basis_layer import RadialBasis
 from .sbftransformer_conv import Glorot_Ortho_, SBFTransformerConv
 from .tc_linear import TCLinear
@@ -103,9 +104,13 @@ class AtomWise(nn.Module):
         return out
 
 
-def graph_layer_norm(x, batch, num_graphs, eps=1e-8, counts=None):
+def graph_layer_norm(x, batch, num_graphs, eps=1e-8, counts=None, rowptr=None):
     """PyG 2.1.0 LayerNorm(affine=False) with `batch`: statistics over all rows AND channels of a graph.
-    `counts` [num_graphs] = rows per graph when the caller already has them (torch.bincount synchronises)."""
+    `rowptr` [num_graphs+1] int32 (rows grouped graph after graph, as PyG collates them): one sm_100a kernel
+    each way (graph_norm.py).  Otherwise the composite of CUDA PyTorch ops, for any `batch`; `counts`
+    [num_graphs] = rows per graph when the caller already has them (torch.bincount synchronises)."""
+    if rowptr is not None:
+        return graph_layer_norm_rows(x, rowptr, eps)
     cnt = (torch.bincount(batch, minlength=num_graphs) if counts is None else counts).clamp(min=1).to(x.dtype)
     norm = (cnt * x.size(-1)).view(-1, 1)
     acc = torch.zeros(num_graphs, x.size(1), dtype=x.dtype, device=x.device)
@@ -131,7 +136,7 @@ class SBFTransformer(nn.Module):
         self.conv_layers = conv_layers
 
     def forward(self, x, edge_index, edge_attr, batch, edge_sbf, node_rbf, edge_index_0, atom_batch, num_graphs,
-                edge_attr_index=None, edge_attr_target_index=None, batch_counts=None):
+                edge_attr_index=None, edge_attr_target_index=None, batch_counts=None, batch_rowptr=None):
         """`edge_attr` is [T, A] as in the reference; or a per-atom table [N, A] with either
         `edge_attr_index` [T] (rows gathered per triplet AFTER edgenn) or `edge_attr_target_index` [E] (the
         conv layers take the table itself: the row is constant over the triplets of a target bond, so
@@ -149,7 +154,7 @@ class SBFTransformer(nn.Module):
             res0 = out
             out = self.convs[i](sbf=edge_sbf, rbf=node_rbf, x=out, edge_index=edge_index, edge_attr=edge_attr,
                                 **conv_kw)
-            out = graph_layer_norm(out, batch, num_graphs, counts=batch_counts)
+            out = graph_layer_norm(out, batch, num_graphs, counts=batch_counts, rowptr=batch_rowptr)
             out = self.bf_skip[i](out)
             out = F.silu(self.dense_bf_skip[i](out)) + res0
             out = self.af_skip[i](out)
@@ -192,6 +197,9 @@ class XGNNPoly(nn.Module):
                 "batch": batch, "batch_counts": data["edge_num"].to(torch.int64),
                 "ei0": ei[0].contiguous(), "ei1": ei[1].contiguous(),
                 "z_rows": torch.unique(z), "z_counts": torch.bincount(z, minlength=self.emb_block.embedding.num_embeddings)}
+        if data["edge_num"].numel() != B or int(prep["batch_counts"].sum()) != E:
+            raise ValueError("edge_num must list the bonds of each of the num_graphs molecules (sum = E)")
+        prep["batch_rowptr"] = rowptr_from_counts(prep["batch_counts"])     # bonds are collated graph after graph
         # built here, found in the cache by the 4 layers (same tensor objects); referenced from `prep` so the
         # device buffers outlive the cache's eviction for as long as a captured graph points at them
         prep["line_graph_meta"] = graph_meta.get(tri, E)
@@ -218,7 +226,7 @@ class XGNNPoly(nn.Module):
         edge_sbf = self.sbf_layer(d, ang, prep["src_bond"])
         node_rbf = self.rbf_layer(d) * env
         neo_x = F.silu(self.emb_trans(neo_x))
-        kw = dict(batch_counts=prep["batch_counts"])
+        kw = dict(batch_counts=prep["batch_counts"], batch_rowptr=prep["batch_rowptr"])
         if self.segment_edge_attr:      # a_j[t] == ei[1][tri[1][t]]: the atom shared by both bonds of the triplet
             return self.fin_model(neo_x, tri, atom_emb, prep["batch"], edge_sbf, node_rbf, prep["ei0"],
                                   data["batch"], B, edge_attr_target_index=prep["ei1"], **kw)

@@ -241,6 +241,19 @@ int x2_graph_layernorm_fwd(const float* x, const int32_t* rowptr, int64_t B, int
 int x2_graph_layernorm_bwd(const float* y, const float* grad_y, const int32_t* rowptr, int64_t B, int32_t D,
                            const float* stats, float* grad_x, void* stream);
 
+/* rbf-gated bond -> atom readout sum: readout.py:34-43 (AtomWise.forward)
+ *   out[n,:] = sum over bonds e = rowptr[n] .. rowptr[n+1]-1 of (w rbf[e] + b) * x[e]
+ * for bonds sorted by their first atom (edge_index is lexicographic, atom_graph.py:42-45): rowptr int32 [N+1],
+ * rowptr[N] = E; x[E,D], rbf[E,R], w[D,R] (nn.Linear layout), b[D] or NULL; D in {128, 256}, R <= 16.
+ * bwd: grad_out[N,D] -> dx[E,D], drbf[E,R], dw[D,R], db[D] (NULL iff b is NULL).  Warp per atom, no atomics,
+ * fixed-order reductions (deterministic). */
+int x2_rbf_readout_fwd(const float* x, const float* rbf, const float* w, const float* b, const int32_t* rowptr,
+                       int64_t N, int64_t E, int32_t D, int32_t R, float* out, void* stream);
+size_t x2_rbf_readout_bwd_workspace_bytes(int64_t N, int64_t E, int32_t D, int32_t R);
+int x2_rbf_readout_bwd(const float* x, const float* rbf, const float* w, const float* b, const int32_t* rowptr,
+                       const float* grad_out, int64_t N, int64_t E, int32_t D, int32_t R, float* dx, float* drbf,
+                       float* dw, float* db, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

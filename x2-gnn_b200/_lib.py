@@ -93,6 +93,9 @@ SIGNATURES = {
                                  _P, _SZ, _P]),
     "x2_graph_layernorm_fwd": (C.c_int, [_P, _P, _I64, _I32, _F, _P, _P, _P]),
     "x2_graph_layernorm_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P, _P]),
+    "x2_rbf_readout_fwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P]),
+    "x2_rbf_readout_bwd_workspace_bytes": (_SZ, [_I64, _I64, _I32, _I32]),
+    "x2_rbf_readout_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _P, _SZ, _P]),
 }
 
 

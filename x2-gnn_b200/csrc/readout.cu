@@ -1,0 +1,228 @@
+// readout.cu -- rbf-gated bond -> atom readout sum of the post-conv block.
+//
+// Reference: readout.py:34-43 `AtomWise.forward`: out[n,:] = sum over bonds e leaving atom n of
+// (lin_rbf(rbf[e]) * x[e]), executed there as a Linear, an elementwise product and a torch_scatter sum
+// (atomics), and in the backward as a gather, two products, a GEMM and a weight-gradient GEMM.
+//
+// Here: bonds are sorted by their first atom (edge_index is lexicographic, atom_graph.py:42-45), so the bonds
+// of atom n are the contiguous rows rowptr[n] .. rowptr[n+1].  One warp per atom, lane owns 4 channels of
+// every 128: F = W rbf_e + b is recomputed from the R <= 31 radial values (lane r holds rbf[e, r]; W sits in
+// shared memory transposed), no [E, D] intermediate exists and nothing is atomic.
+//   fwd:  out[n] = sum_e F_e * x_e
+//   bwd:  dx_e = g_n * F_e ;  dF_e = g_n * x_e ;  drbf[e, r] = sum_c dF_e[c] W[c, r] ;
+//         dW[c, r] = sum_e dF_e[c] rbf[e, r] ;  db[c] = sum_e dF_e[c]
+//         (register accumulators per warp, fixed-order block partials, one fixed-order reduction kernel).
+#include "common.cuh"
+
+namespace x2 {
+namespace {
+
+constexpr int kRoWarps = 8;
+
+// s_w: [R + 1][D] = W transposed, then the bias row
+__device__ __forceinline__ void load_wt(float* s_w, const float* __restrict__ w, const float* __restrict__ b, int D,
+                                        int R) {
+  for (int i = threadIdx.x; i < D * R; i += blockDim.x) s_w[(i % R) * D + i / R] = w[i];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) s_w[R * D + i] = b ? b[i] : 0.f;
+  __syncthreads();
+}
+
+template <int DV>     // D = 128 * DV
+__global__ void __launch_bounds__(kRoWarps * 32)
+k_readout_fwd(const float* __restrict__ x, const float* __restrict__ rbf, const float* __restrict__ w,
+              const float* __restrict__ b, const int32_t* __restrict__ rowptr, int64_t N, int R,
+              float* __restrict__ out) {
+  constexpr int D = 128 * DV;
+  extern __shared__ __align__(16) float s_w[];
+  load_wt(s_w, w, b, D, R);
+  const int lane = threadIdx.x & 31;
+  for (int64_t n = (int64_t)blockIdx.x * kRoWarps + (threadIdx.x >> 5); n < N; n += (int64_t)gridDim.x * kRoWarps) {
+    float4 acc[DV];
+#pragma unroll
+    for (int v = 0; v < DV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int beg = rowptr[n], end = rowptr[n + 1];
+    for (int e = beg; e < end; ++e) {
+      const float rv = lane < R ? rbf[(int64_t)e * R + lane] : 0.f;
+#pragma unroll
+      for (int v = 0; v < DV; ++v) {
+        const int d0 = v * 128 + lane * 4;
+        float4 f = *reinterpret_cast<const float4*>(s_w + R * D + d0);
+        for (int r = 0; r < R; ++r) {
+          const float br = __shfl_sync(0xffffffffu, rv, r);
+          const float4 wv = *reinterpret_cast<const float4*>(s_w + r * D + d0);
+          f.x = fmaf(br, wv.x, f.x); f.y = fmaf(br, wv.y, f.y); f.z = fmaf(br, wv.z, f.z); f.w = fmaf(br, wv.w, f.w);
+        }
+        const float4 xv = *reinterpret_cast<const float4*>(x + (int64_t)e * D + d0);
+        acc[v].x = fmaf(f.x, xv.x, acc[v].x); acc[v].y = fmaf(f.y, xv.y, acc[v].y);
+        acc[v].z = fmaf(f.z, xv.z, acc[v].z); acc[v].w = fmaf(f.w, xv.w, acc[v].w);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < DV; ++v) *reinterpret_cast<float4*>(out + n * D + v * 128 + lane * 4) = acc[v];
+  }
+}
+
+// One 128-channel slab (blockIdx.y) per block row: the dW accumulators (RMAX + 1 float4 per lane) stay in registers.
+template <int RMAX>
+__global__ void __launch_bounds__(kRoWarps * 32)
+k_readout_bwd(const float* __restrict__ x, const float* __restrict__ rbf, const float* __restrict__ w,
+              const float* __restrict__ b, const int32_t* __restrict__ rowptr, const float* __restrict__ g,
+              int64_t N, int64_t E, int D, int R, float* __restrict__ dx, float* __restrict__ drbf_part,
+              float* __restrict__ partial) {
+  extern __shared__ __align__(16) float s_w[];     // [R + 1][D], reused as [warps][RMAX + 1][128] for the reduction
+  load_wt(s_w, w, b, D, R);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d0 = blockIdx.y * 128 + lane * 4;
+  float4 wv[RMAX + 1];
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r)
+    wv[r] = r < R ? *reinterpret_cast<const float4*>(s_w + r * D + d0) : make_float4(0.f, 0.f, 0.f, 0.f);
+  wv[RMAX] = *reinterpret_cast<const float4*>(s_w + R * D + d0);      // bias
+  float4 acc[RMAX + 1];
+#pragma unroll
+  for (int r = 0; r <= RMAX; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int64_t n = (int64_t)blockIdx.x * kRoWarps + warp; n < N; n += (int64_t)gridDim.x * kRoWarps) {
+    const float4 gv = *reinterpret_cast<const float4*>(g + n * D + d0);
+    const int beg = rowptr[n], end = rowptr[n + 1];
+    for (int e = beg; e < end; ++e) {
+      const float rv = lane < R ? rbf[(int64_t)e * R + lane] : 0.f;
+      const float4 xv = *reinterpret_cast<const float4*>(x + (int64_t)e * D + d0);
+      float4 f = wv[RMAX];
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        const float br = __shfl_sync(0xffffffffu, rv, r);
+        f.x = fmaf(br, wv[r].x, f.x); f.y = fmaf(br, wv[r].y, f.y); f.z = fmaf(br, wv[r].z, f.z); f.w = fmaf(br, wv[r].w, f.w);
+      }
+      *reinterpret_cast<float4*>(dx + (int64_t)e * D + d0) = make_float4(gv.x * f.x, gv.y * f.y, gv.z * f.z, gv.w * f.w);
+      const float4 dF = make_float4(gv.x * xv.x, gv.y * xv.y, gv.z * xv.z, gv.w * xv.w);
+      acc[RMAX].x += dF.x; acc[RMAX].y += dF.y; acc[RMAX].z += dF.z; acc[RMAX].w += dF.w;
+      float mine = 0.f;                                           // lane r ends up with this slab's drbf[e, r]
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        const float br = __shfl_sync(0xffffffffu, rv, r);
+        acc[r].x = fmaf(dF.x, br, acc[r].x); acc[r].y = fmaf(dF.y, br, acc[r].y);
+        acc[r].z = fmaf(dF.z, br, acc[r].z); acc[r].w = fmaf(dF.w, br, acc[r].w);
+        float p = dF.x * wv[r].x + dF.y * wv[r].y + dF.z * wv[r].z + dF.w * wv[r].w;
+#pragma unroll
+        for (int o_ = 16; o_ > 0; o_ >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o_);
+        if (lane == r) mine = p;
+      }
+      // [slab][E][R]: summed over the D / 128 slabs by k_readout_reduce (a single slab writes drbf itself)
+      if (lane < R) drbf_part[((int64_t)blockIdx.y * E + e) * R + lane] = mine;
+    }
+  }
+  __syncthreads();                                   // everyone is done with the W copy
+  float* red = s_w;                                  // [warps][RMAX + 1][128]
+#pragma unroll
+  for (int r = 0; r <= RMAX; ++r) *reinterpret_cast<float4*>(red + (warp * (RMAX + 1) + r) * 128 + lane * 4) = acc[r];
+  __syncthreads();
+  // partial[block][D][R + 1]: columns 0..R-1 = dW rows, column R = db
+  for (int i = threadIdx.x; i < 128 * (R + 1); i += blockDim.x) {
+    const int c = i / (R + 1), r = i - c * (R + 1);
+    const int rr = r < R ? r : RMAX;
+    float t = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < kRoWarps; ++wq) t += red[(wq * (RMAX + 1) + rr) * 128 + c];
+    partial[((int64_t)blockIdx.x * D + blockIdx.y * 128 + c) * (R + 1) + r] = t;
+  }
+}
+
+// dW[D, R], db[D] = fixed-order sums of the block partials; drbf[E, R] = sum of the slab partials (slabs > 1).
+__global__ void k_readout_reduce(const float* __restrict__ partial, int nblocks, int D, int R, float* __restrict__ dw,
+                                 float* __restrict__ db, const float* __restrict__ drbf_part, int slabs, int64_t ER,
+                                 float* __restrict__ drbf) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nw = (int64_t)D * (R + 1);
+  if (i < nw) {
+    float t = 0.f;
+    for (int k = 0; k < nblocks; ++k) t += partial[(int64_t)k * nw + i];
+    const int c = (int)(i / (R + 1)), r = (int)(i - (int64_t)c * (R + 1));
+    if (r < R) dw[(int64_t)c * R + r] = t;
+    else if (db) db[c] = t;
+  }
+  if (slabs > 1) {
+    for (int64_t j = i; j < ER; j += (int64_t)gridDim.x * blockDim.x) {
+      float t = 0.f;
+      for (int s = 0; s < slabs; ++s) t += drbf_part[(int64_t)s * ER + j];
+      drbf[j] = t;
+    }
+  }
+}
+
+inline int ro_blocks(int64_t N) {
+  const int64_t need = cdiv(N, kRoWarps), cap = (int64_t)kNumSM * 4;
+  return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+}  // namespace
+}  // namespace x2
+
+using namespace x2;
+
+extern "C" {
+
+size_t x2_rbf_readout_bwd_workspace_bytes(int64_t N, int64_t E, int32_t D, int32_t R) {
+  if (N < 0 || E < 0 || D <= 0 || R <= 0) return 0;
+  const size_t part = (size_t)ro_blocks(N) * (size_t)D * (size_t)(R + 1) * sizeof(float);
+  const size_t slabs = (size_t)(D / 128);
+  return part + (slabs > 1 ? slabs * (size_t)E * (size_t)R * sizeof(float) : 0) + 256;
+}
+
+int x2_rbf_readout_fwd(const float* x, const float* rbf, const float* w, const float* b, const int32_t* rowptr,
+                       int64_t N, int64_t E, int32_t D, int32_t R, float* out, void* stream) {
+  X2_CHECK_ARG(N >= 0 && E >= 0 && (D == 128 || D == 256) && R >= 1 && R <= 16,
+               "x2_rbf_readout_fwd: need D in {128, 256} and 1 <= R <= 16 (got D=%d R=%d)", (int)D, (int)R);
+  if (N == 0) return X2_OK;
+  X2_CHECK_ARG(w && rowptr && out && (E == 0 || (x && rbf)), "x2_rbf_readout_fwd: null pointer");
+  const size_t smem = (size_t)(R + 1) * D * sizeof(float);
+  const dim3 grid(ro_blocks(N)), block(kRoWarps * 32);
+  if (D == 128) k_readout_fwd<1><<<grid, block, smem, (cudaStream_t)stream>>>(x, rbf, w, b, rowptr, N, R, out);
+  else k_readout_fwd<2><<<grid, block, smem, (cudaStream_t)stream>>>(x, rbf, w, b, rowptr, N, R, out);
+  X2_LAUNCH_OK();
+  return X2_OK;
+}
+
+int x2_rbf_readout_bwd(const float* x, const float* rbf, const float* w, const float* b, const int32_t* rowptr,
+                       const float* grad_out, int64_t N, int64_t E, int32_t D, int32_t R, float* dx, float* drbf,
+                       float* dw, float* db, void* ws, size_t ws_bytes, void* stream) {
+  X2_CHECK_ARG(N >= 0 && E >= 0 && (D == 128 || D == 256) && R >= 1 && R <= 16,
+               "x2_rbf_readout_bwd: need D in {128, 256} and 1 <= R <= 16 (got D=%d R=%d)", (int)D, (int)R);
+  X2_CHECK_ARG(dw, "x2_rbf_readout_bwd: dw is required");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0 || E == 0) {
+    X2_CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)D * R * sizeof(float), st));
+    if (db) X2_CUDA_OK(cudaMemsetAsync(db, 0, (size_t)D * sizeof(float), st));
+    return X2_OK;
+  }
+  X2_CHECK_ARG(x && rbf && w && rowptr && grad_out && dx && drbf, "x2_rbf_readout_bwd: null pointer");
+  X2_CHECK_ARG(ws && ws_bytes >= x2_rbf_readout_bwd_workspace_bytes(N, E, D, R), "x2_rbf_readout_bwd: workspace too small");
+  const int nb = ro_blocks(N), slabs = D / 128;
+  float* partial = reinterpret_cast<float*>(ws);
+  float* drbf_part = slabs > 1 ? partial + (size_t)nb * D * (R + 1) : drbf;
+  const int RM = R <= 8 ? 8 : 16;
+  // the reduction scratch [warps][RMAX + 1][128] reuses the W image [R + 1][D]
+  const size_t smem = sizeof(float) * (size_t)((RM + 1) * 128 * kRoWarps > (R + 1) * D ? (RM + 1) * 128 * kRoWarps : (R + 1) * D);
+  const dim3 grid(nb, slabs), block(kRoWarps * 32);
+  if (RM == 8) {
+    k_readout_bwd<8><<<grid, block, smem, st>>>(x, rbf, w, b, rowptr, grad_out, N, E, D, R, dx, drbf_part, partial);
+  } else {
+    static bool once = false;
+    if (!once) {
+      X2_CUDA_OK(cudaFuncSetAttribute(k_readout_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+      once = true;
+    }
+    k_readout_bwd<16><<<grid, block, smem, st>>>(x, rbf, w, b, rowptr, grad_out, N, E, D, R, dx, drbf_part, partial);
+  }
+  X2_LAUNCH_OK();
+  const int64_t nw = (int64_t)D * (R + 1);
+  const int64_t work = slabs > 1 ? (nw > E * R ? nw : E * R) : nw;
+  int64_t rb = cdiv(work, 256);
+  if (rb > kNumSM * 8) rb = kNumSM * 8;
+  if (rb < cdiv(nw, 256)) rb = cdiv(nw, 256);
+  k_readout_reduce<<<(unsigned)rb, 256, 0, st>>>(partial, nb, D, R, dw, db, drbf_part, slabs, E * (int64_t)R, drbf);
+  X2_LAUNCH_OK();
+  return X2_OK;
+}
+
+}  // extern "C"

@@ -24,6 +24,7 @@ from .edge_graph import vertex_to_edge_2
 from .envelop import poly_envelop
 from .graph_norm import graph_layer_norm_rows, rowptr_from_counts
 from .radial_basis_layer import RadialBasis
+from . import readout_sum
 from .sbftransformer_conv import Glorot_Ortho_, SBFTransformerConv
 from .tc_linear import TCLinear
 
@@ -96,9 +97,14 @@ class AtomWise(nn.Module):
         self.mlp = nn.ModuleList(mods)
         self.lin_rbf = _lin(rbf_dim, in_channels)
 
-    def forward(self, x, rbf, num_atoms, edge_index_0):
-        out = torch.zeros(num_atoms, x.size(1), dtype=x.dtype, device=x.device)
-        out.index_add_(0, edge_index_0, self.lin_rbf(rbf) * x)
+    def forward(self, x, rbf, num_atoms, edge_index_0, atom_rowptr=None):
+        """`atom_rowptr` [num_atoms+1] int32 (bonds sorted by first atom): the gated sum runs as one sm_100a
+        kernel each way (readout_sum.py); otherwise Linear + product + index_add as in the reference."""
+        if atom_rowptr is not None and x.is_cuda and readout_sum.supported(x.size(1), rbf.size(1)):
+            out = readout_sum.rbf_readout(x, rbf, self.lin_rbf.weight, self.lin_rbf.bias, atom_rowptr)
+        else:
+            out = torch.zeros(num_atoms, x.size(1), dtype=x.dtype, device=x.device)
+            out.index_add_(0, edge_index_0, self.lin_rbf(rbf) * x)
         for m in self.mlp:
             out = m(out)
         return out
@@ -136,7 +142,8 @@ class SBFTransformer(nn.Module):
         self.conv_layers = conv_layers
 
     def forward(self, x, edge_index, edge_attr, batch, edge_sbf, node_rbf, edge_index_0, atom_batch, num_graphs,
-                edge_attr_index=None, edge_attr_target_index=None, batch_counts=None, batch_rowptr=None):
+                edge_attr_index=None, edge_attr_target_index=None, batch_counts=None, batch_rowptr=None,
+                atom_rowptr=None):
         """`edge_attr` is [T, A] as in the reference; or a per-atom table [N, A] with either
         `edge_attr_index` [T] (rows gathered per triplet AFTER edgenn) or `edge_attr_target_index` [E] (the
         conv layers take the table itself: the row is constant over the triplets of a target bond, so
@@ -149,7 +156,7 @@ class SBFTransformer(nn.Module):
             edge_attr = edge_attr[edge_attr_index]
         out = x
         n_atoms = atom_batch.size(0)
-        results = self.readouts[0](out, node_rbf, n_atoms, edge_index_0)
+        results = self.readouts[0](out, node_rbf, n_atoms, edge_index_0, atom_rowptr)
         for i in range(self.conv_layers):
             res0 = out
             out = self.convs[i](sbf=edge_sbf, rbf=node_rbf, x=out, edge_index=edge_index, edge_attr=edge_attr,
@@ -158,7 +165,7 @@ class SBFTransformer(nn.Module):
             out = self.bf_skip[i](out)
             out = F.silu(self.dense_bf_skip[i](out)) + res0
             out = self.af_skip[i](out)
-            results = results + self.readouts[i + 1](out, node_rbf, n_atoms, edge_index_0)
+            results = results + self.readouts[i + 1](out, node_rbf, n_atoms, edge_index_0, atom_rowptr)
         mol = torch.zeros(num_graphs, results.size(1), dtype=results.dtype, device=results.device)
         return mol.index_add(0, atom_batch, results).view(-1)
 
@@ -200,6 +207,10 @@ class XGNNPoly(nn.Module):
         if data["edge_num"].numel() != B or int(prep["batch_counts"].sum()) != E:
             raise ValueError("edge_num must list the bonds of each of the num_graphs molecules (sum = E)")
         prep["batch_rowptr"] = rowptr_from_counts(prep["batch_counts"])     # bonds are collated graph after graph
+        # bonds leaving one atom are contiguous when edge_index is lexicographic (atom_graph.py:42-45): readout CSR
+        ei0 = prep["ei0"]
+        prep["atom_rowptr"] = (rowptr_from_counts(torch.bincount(ei0, minlength=N))
+                               if E == 0 or bool((ei0[1:] >= ei0[:-1]).all()) else None)
         # built here, found in the cache by the 4 layers (same tensor objects); referenced from `prep` so the
         # device buffers outlive the cache's eviction for as long as a captured graph points at them
         prep["line_graph_meta"] = graph_meta.get(tri, E)
@@ -226,7 +237,7 @@ class XGNNPoly(nn.Module):
         edge_sbf = self.sbf_layer(d, ang, prep["src_bond"])
         node_rbf = self.rbf_layer(d) * env
         neo_x = F.silu(self.emb_trans(neo_x))
-        kw = dict(batch_counts=prep["batch_counts"], batch_rowptr=prep["batch_rowptr"])
+        kw = dict(batch_counts=prep["batch_counts"], batch_rowptr=prep["batch_rowptr"], atom_rowptr=prep["atom_rowptr"])
         if self.segment_edge_attr:      # a_j[t] == ei[1][tri[1][t]]: the atom shared by both bonds of the triplet
             return self.fin_model(neo_x, tri, atom_emb, prep["batch"], edge_sbf, node_rbf, prep["ei0"],
                                   data["batch"], B, edge_attr_target_index=prep["ei1"], **kw)

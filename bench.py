@@ -19,6 +19,7 @@ PyTorch ops -- the reference has no native code to compile) on the host cores.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import sys
@@ -213,15 +214,19 @@ def train_step_bench(dev, world, rank, steps, warmup, with_cpu):
         dist.barrier()
     torch.cuda.synchronize()
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    gc.collect()
+    gc.disable()          # a generation-2 collection inside a host-bound step shows up as a 0.1-1 s outlier
     marks[0].record()
     for i in range(steps):
         loss = step()
         marks[i + 1].record()
+    gc.enable()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     ms = marks[0].elapsed_time(marks[-1]) / steps
-    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(steps))
+    in_order = [round(marks[i].elapsed_time(marks[i + 1]), 3) for i in range(steps)]
+    per_step = sorted(in_order)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -229,6 +234,7 @@ def train_step_bench(dev, world, rank, steps, warmup, with_cpu):
     # the step is bound by host-side launch overhead (~800 launches), so host jitter shows: mean and median
     res = {"molecules_per_sec": world * NMOL / (ms * 1e-3), "ms_per_step": ms, "steps": steps,
            "ms_per_step_median": per_step[len(per_step) // 2], "ms_per_step_min": per_step[0],
+           "ms_each_step": in_order,
            "molecules_per_gpu": NMOL, "molecules_this_rank": nmine, "loss": float(loss.detach()), "N": len(b["x"]),
            "E": int(b["edge_index"].shape[1]),
            "sharding": "global batch of 128 x N molecules (seed 0), whole molecules dealt to ranks balanced by triplet count"}
@@ -241,12 +247,13 @@ def train_step_bench(dev, world, rank, steps, warmup, with_cpu):
     try:
         g = _train_step_graph(dev, world, rank, steps, data, y, nmine)
         # the graphed step is the implementation's training step: it leads, the eager numbers stay beside it
-        eager = {k: res[k] for k in ("molecules_per_sec", "ms_per_step", "ms_per_step_median", "ms_per_step_min",
-                                     "steps", "loss")}
+        eager = {k: res.pop(k) if k == "ms_each_step" else res[k]
+                 for k in ("molecules_per_sec", "ms_per_step", "ms_per_step_median", "ms_per_step_min", "steps",
+                           "loss", "ms_each_step")}
         eager["what"] = "the same step issued launch by launch from Python (~560 kernels; bound by the host)"
         res.update({"mode": "cuda_graph", "molecules_per_sec": g.pop("molecules_per_sec"),
                     "ms_per_step": g.pop("ms_per_step"), "ms_per_step_median": g.pop("ms_per_step_median"),
-                    "steps": g.pop("steps")})
+                    "steps": g.pop("steps"), "ms_each_step": g.pop("ms_each_step")})
         res.pop("ms_per_step_min", None)
         res["loss"] = g.get("graph_loss")
         res["cuda_graph"] = g
@@ -307,23 +314,27 @@ def _train_step_graph(dev, world, rank, steps, data, y, nmine):
         dist.barrier()
     torch.cuda.synchronize(dev)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 2)]
+    gc.collect()
+    gc.disable()
     marks[0].record()
     for i in range(steps):
         step()
         marks[i + 1].record()
+    gc.enable()
     torch.cuda.current_stream(dev).wait_stream(prep_stream)    # the last step's index work is inside the timing
     marks[-1].record()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     ms = marks[0].elapsed_time(marks[-1]) / steps
-    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(steps))
+    in_order = [round(marks[i].elapsed_time(marks[i + 1]), 3) for i in range(steps)]
+    per_step = sorted(in_order)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
     out = {"molecules_per_sec": world * NMOL / (ms * 1e-3), "ms_per_step": ms,
-           "ms_per_step_median": per_step[len(per_step) // 2], "steps": steps,
+           "ms_per_step_median": per_step[len(per_step) // 2], "steps": steps, "ms_each_step": in_order,
            "graph_loss": float(gs.loss.detach()), "indices_rebuilt_each_step_identical": same_idx,
            "what": "per step: prepare() (triplet / CSR integer kernels, eager, own stream) + one graph replay of "
                    "forward, loss, backward, all-reduce, clip, Adam, EMA"}

@@ -169,3 +169,31 @@ def test_sync_free_embedding_matches_nn_embedding():
     x = torch.randn(7, 4)
     batch = torch.tensor([0, 0, 1, 1, 1, 3, 3])
     assert torch.equal(graph_layer_norm(x, batch, 4), graph_layer_norm(x, batch, 4, counts=torch.tensor([2, 3, 0, 2])))
+
+
+def test_post_conv_entry_points_validate_and_refuse_cpu():
+    """x2_graph_layernorm_* / x2_rbf_readout_*: argument errors are reported through the return code and
+    x2_last_error before anything is launched (so they can be checked without a GPU); the Python bindings
+    have no CPU path."""
+    from x2gnn_b200 import _lib, graph_norm, readout_sum
+    L = _lib.lib()
+    assert L.x2_graph_layernorm_fwd(None, None, 1, 6, 1e-8, None, None, None) != 0      # D % 4 != 0
+    assert b"multiple of 4" in L.x2_last_error()
+    assert L.x2_graph_layernorm_fwd(None, None, 0, 128, 1e-8, None, None, None) == 0    # no graphs: nothing to do
+    assert L.x2_graph_layernorm_bwd(None, None, None, 2, 128, None, None, None) != 0    # null pointers
+    assert L.x2_rbf_readout_fwd(None, None, None, None, None, 4, 9, 64, 6, None, None) != 0   # D not 128 / 256
+    assert b"D in {128, 256}" in L.x2_last_error()
+    assert L.x2_rbf_readout_fwd(None, None, None, None, None, 4, 9, 128, 17, None, None) != 0  # R > 16
+    assert L.x2_rbf_readout_bwd_workspace_bytes(2367, 43048, 128, 6) >= 128 * 7 * 4
+    assert (L.x2_rbf_readout_bwd_workspace_bytes(2367, 43048, 256, 6)
+            > L.x2_rbf_readout_bwd_workspace_bytes(2367, 43048, 128, 6) + 2 * 43048 * 6 * 4 - 1)
+    assert readout_sum.supported(128, 6) and readout_sum.supported(256, 16)
+    assert not readout_sum.supported(64, 6) and not readout_sum.supported(128, 17)
+    rp = graph_norm.rowptr_from_counts(torch.tensor([3, 0, 2]))
+    assert rp.dtype == torch.int32 and rp.tolist() == [0, 3, 3, 5]
+    if torch.cuda.is_available():
+        return
+    with pytest.raises(_lib.X2Error):
+        graph_norm.graph_layer_norm_rows(torch.zeros(5, 8), rp)
+    with pytest.raises(_lib.X2Error):
+        readout_sum.rbf_readout(torch.zeros(5, 128), torch.zeros(5, 6), torch.zeros(128, 6), None, rp)

@@ -213,17 +213,23 @@ def train_step_bench(dev, world, rank, steps, warmup, with_cpu):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    # The first iterations of a loop that starts from an idle device run slow on every box seen (10-100 ms
+    # outliers at fixed positions 1 and 3, whatever the warm-up before the synchronize): LEAD more untimed
+    # iterations run inside the loop itself and the K timed steps follow them without a pause (ranks stay in
+    # step through the all-reduce of every iteration; barrier + synchronize bracket the whole loop).
+    LEAD = 4
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(LEAD + steps + 1)]
     gc.collect()
-    gc.disable()          # a generation-2 collection inside a host-bound step shows up as a 0.1-1 s outlier
-    marks[0].record()
-    for i in range(steps):
+    gc.disable()
+    for i in range(LEAD + steps):
+        marks[i].record()
         loss = step()
-        marks[i + 1].record()
+    marks[-1].record()
     gc.enable()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    marks = marks[LEAD:]
     ms = marks[0].elapsed_time(marks[-1]) / steps
     in_order = [round(marks[i].elapsed_time(marks[i + 1]), 3) for i in range(steps)]
     per_step = sorted(in_order)
@@ -313,19 +319,20 @@ def _train_step_graph(dev, world, rank, steps, data, y, nmine):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 2)]
+    LEAD = 4              # untimed iterations inside the loop (pipeline fill from an idle device), see the eager loop
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(LEAD + steps + 1)]
     gc.collect()
     gc.disable()
-    marks[0].record()
-    for i in range(steps):
+    for i in range(LEAD + steps):
+        marks[i].record()
         step()
-        marks[i + 1].record()
     gc.enable()
     torch.cuda.current_stream(dev).wait_stream(prep_stream)    # the last step's index work is inside the timing
     marks[-1].record()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
+    marks = marks[LEAD:]
     ms = marks[0].elapsed_time(marks[-1]) / steps
     in_order = [round(marks[i].elapsed_time(marks[i + 1]), 3) for i in range(steps)]
     per_step = sorted(in_order)

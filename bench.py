@@ -353,7 +353,7 @@ def _train_step_graph(dev, world, rank, steps, data, y, nmine):
         ps2 = [p for p in m2.parameters() if p.requires_grad]
         o2 = torch.optim.Adam(ps2, lr=1e-3, fused=True)
         pr2 = m2.prepare(data)
-        n_updates = gs.warmup_updates + 3 + steps
+        n_updates = gs.warmup_updates + 3 + LEAD + steps
         for _ in range(n_updates):
             l2 = dense_step(m2, o2, ps2, data, pr2, y)
         out["eager_loss_after_same_updates"] = float(l2.detach())

@@ -536,7 +536,7 @@ def run_ours(args):
 
     h2d = sum(pin[k].numel() * pin[k].element_size() for k in pin)
     d2h = sum(t.numel() * t.element_size() for t in (h_out, h_dx, h_drbf, h_flat))
-    e2e_steps = max(3, min(steps, 10))
+    e2e_steps = max(3, min(steps, 30))
     for _ in range(2):
         e2e_step()
     barrier()
@@ -556,7 +556,7 @@ def run_ours(args):
     train = None
     if not args.no_train_step:
         try:
-            train = train_step_bench(dev, world, rank, max(3, min(steps, 10)), 5,
+            train = train_step_bench(dev, world, rank, max(3, min(steps, 30)), 5,
                                      with_cpu=(world == 1 and not args.no_cpu_baseline))
         except Exception as exc:  # keep the headline line even if the secondary metric fails
             train = {"error": f"{type(exc).__name__}: {exc}"}

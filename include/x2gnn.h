@@ -107,12 +107,29 @@ int x2_triplets_fill(const int64_t* edge_index, int64_t E, int64_t N, const int3
  * edge_index[2,T] int64 (row 0 = source line-node, row 1 = target line-node), E line-nodes.
  * Outputs (int32): src[T], tgt[T]; rowptr_tgt[E+1] + order_tgt[T] (triplet ids grouped by target,
  * ascending inside a group; identity when edge_index[1] is already sorted); rowptr_src[E+1] +
- * order_src[T] (grouped by source, ascending).  flags[0]=1 if target-sorted, flags[1]=number of
- * out-of-range ids. */
+ * order_src[T] (grouped by source, ascending).  flags is int32 [4]: flags[0]=1 if target-sorted,
+ * flags[1]=number of out-of-range ids, flags[2]=length of the longest target segment, flags[3]=0. */
 size_t x2_meta_workspace_bytes(int64_t T, int64_t E);
 int x2_meta_build(const int64_t* edge_index, int64_t T, int64_t E, int32_t* src, int32_t* tgt,
                   int32_t* rowptr_tgt, int32_t* order_tgt, int32_t* rowptr_src,
                   int32_t* order_src, int32_t* flags, void* ws, size_t ws_bytes, void* stream);
+
+/* Tiles of the fused forward / backward-by-target kernels (csrc/tile_attn.cuh): the target-sorted triplet
+ * list cut into runs of whole segments with at most X2_TILE_ROWS triplets, and every segment cut (relative to
+ * its own start) into ITEMS of at most X2_TILE_ITEM_ROWS rows, the work units of the attention warps.
+ * x2_tiles_count gives the number of tiles for T triplets whose longest segment is max_seg (flags[2] of
+ * x2_meta_build), or 0 when the segments are too long for the tile (the conv then takes the unfused kernels).
+ * x2_tiles_build fills tile[4 * (ntiles + 1)] int32: (first target, first triplet, first item, 0) of every
+ * tile, last entry (E, T, number of items, 0); and items[2 * x2_tile_items_bound(T, E)] int32: (first
+ * triplet, (target << 4) | (rows - 1)) of every item, in row order.  Needs E < 2^27.
+ * ws >= x2_tiles_workspace_bytes(E). */
+#define X2_TILE_ROWS 120
+#define X2_TILE_ITEM_ROWS 8
+int64_t x2_tiles_count(int64_t T, int32_t max_seg);
+int64_t x2_tile_items_bound(int64_t T, int64_t E);
+size_t x2_tiles_workspace_bytes(int64_t E);
+int x2_tiles_build(const int32_t* rowptr_tgt, int64_t E, int64_t T, int32_t max_seg, int32_t* tile,
+                   int64_t ntiles, int32_t* items, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------- basis expansions
  * envelop.py:16-21: out = 1/x + a x^(p-1) + b x^p + c x^(p+1), x = d * inv_cutoff. */
@@ -166,7 +183,7 @@ typedef struct {
   int32_t mode;        /* X2_MODE_* */
   float dropout_p;     /* attention dropout (training); 0 disables */
   int32_t tgt_sorted;  /* 1 iff edge_index[1] is non-decreasing (order_tgt is the identity): enables the fused
-                          forward kernel; x2_meta_build reports it in flags[0] */
+                          tile kernels; x2_meta_build reports it in flags[0] */
   uint64_t seed;       /* dropout RNG seed */
   /* inputs */
   const float *x, *rbf, *sbf, *edge_attr;
@@ -189,18 +206,26 @@ typedef struct {
    * order_src).  Then saved.ea is [ea_rows, D] and grads.dedge_attr is [ea_rows, A]. */
   int64_t ea_rows;
   const int32_t *ea_index, *ea_rowptr, *ea_order;
+  /* Optional tiling of the target-sorted triplet list (x2_tiles_build); NULL / 0 => unfused kernels.  With it
+   * (and tgt_sorted, D == 128, A in {0, 128} or the edge_attr table, S even <= 64, no dropout, no alpha
+   * output) lin_edge, lin_sbf and the segmented attention run as ONE kernel that reads edge_attr / sbf once. */
+  const int32_t* tiles;
+  const int32_t* tile_items;
+  int64_t n_tiles;
 } x2_conv_desc;
 
 #define X2_MODE_FP32 0    /* fp32 SIMT arithmetic everywhere (1e-5 parity) */
 #define X2_MODE_TF32X3 1  /* Linear layers on tcgen05 tensor cores in 3xTF32 split precision (fp32-accurate,
-                             1e-5 parity); needs D % 128 == 0.  Attention arithmetic stays fp32 SIMT. */
+                             1e-5 parity); needs D % 128 == 0.  Attention arithmetic stays fp32 SIMT.  When the
+                             caller supplies `tiles` the T-scale forward runs as one fused kernel. */
 #define X2_MODE_TF32 3    /* reduced precision: as TF32X3 but ONE tf32 pass per product (operands truncated to
                              10 mantissa bits by the tensor core, fp32 accumulation): ~5e-4 relative error on
                              layer outputs and gradients, inside the 2e-2 tolerance class of the bf16-projection
                              mode; the lo-half passes of the producers and two of three MMAs are skipped */
-#define X2_MODE_TF32X3_FUSED 2  /* experimental: as TF32X3, with lin_edge / lin_sbf and the forward attention
-                                   fused into one tcgen05 kernel (csrc/fused_fwd.cuh) when edge_index is
-                                   target-sorted, D == 128, A <= 128, S <= 64, no dropout / alpha request */
+#define X2_MODE_TF32X3_UNFUSED 2  /* as TF32X3 but never the fused tile kernels (csrc/tile_attn.cuh): lin_edge /
+                                     lin_sbf as separate tensor-core GEMMs that materialise EA / Sg, then the
+                                     warp-per-target attention kernels (the round-1 decomposition; A/B and
+                                     coverage of the generic kernels) */
 
 /* Tensors written by fwd and consumed by bwd (caller-owned, kept alive by autograd). */
 typedef struct {

@@ -40,6 +40,7 @@ class ConvDesc(C.Structure):
         ("w_v", c_f32p), ("b_v", c_f32p), ("w_edge", c_f32p), ("w_sbf", c_f32p), ("b_sbf", c_f32p),
         ("w_skip", c_f32p), ("b_skip", c_f32p),
         ("ea_rows", C.c_int64), ("ea_index", c_i32p), ("ea_rowptr", c_i32p), ("ea_order", c_i32p),
+        ("tiles", c_i32p), ("tile_items", c_i32p), ("n_tiles", C.c_int64),
     ]
 
 
@@ -75,6 +76,10 @@ SIGNATURES = {
     "x2_triplets_fill": (C.c_int, [_P, _I64, _I64, _P, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
     "x2_meta_workspace_bytes": (_SZ, [_I64, _I64]),
     "x2_meta_build": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "x2_tiles_count": (C.c_int64, [_I64, _I32]),
+    "x2_tile_items_bound": (C.c_int64, [_I64, _I64]),
+    "x2_tiles_workspace_bytes": (_SZ, [_I64]),
+    "x2_tiles_build": (C.c_int, [_P, _I64, _I64, _I32, _P, _I64, _P, _P, _SZ, _P]),
     "x2_envelope_fwd": (C.c_int, [_P, _I64, _F, _I32, _F, _F, _F, _P, _P]),
     "x2_radial_fwd": (C.c_int, [_P, _P, _P, _I64, _I32, _F, _P, _P]),
     "x2_radial_bwd_workspace_bytes": (_SZ, [_I64, _I32]),

@@ -15,6 +15,21 @@ bool pdl_enabled() {
   return on != 0;
 }
 
+int ensure_dyn_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> done;      // (kernel, device) pairs already set
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { set_error("cudaGetDevice -> %s", cudaGetErrorString(e)); return X2_ECUDA; }
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& d : done)
+    if (d.first == func && d.second == dev) return X2_OK;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%d bytes) -> %s", bytes, cudaGetErrorString(e)); return X2_ECUDA; }
+  done.emplace_back(func, dev);
+  return X2_OK;
+}
+
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static std::atomic<int> g_timing{0};

@@ -30,6 +30,17 @@ void set_error(const char* fmt, ...);
     }                                                                             \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: ensure_dyn_smem sets it once
+// per (kernel, current device) under a mutex (a process-global `static bool` would leave every device but
+// the first without the opt-in size, and races between host threads).
+int ensure_dyn_smem(const void* func, int bytes);
+#define X2_DYN_SMEM(kernel, bytes) X2_CUDA_OK_RC(x2::ensure_dyn_smem(reinterpret_cast<const void*>(kernel), (int)(bytes)))
+#define X2_CUDA_OK_RC(expr)               \
+  do {                                    \
+    int _rc = (expr);                     \
+    if (_rc != X2_OK) return _rc;         \
+  } while (0)
+
 void count_launch();
 #define X2_LAUNCH_OK()                 \
   do {                                 \

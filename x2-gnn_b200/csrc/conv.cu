@@ -14,7 +14,6 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "tc_gemm.cuh"
-#include "fused_fwd.cuh"
 
 namespace x2 {
 
@@ -64,6 +63,10 @@ __device__ __forceinline__ float head_sum_t(float v, int lph) {
     return head_sum(v, lph);
   }
 }
+
+}  // namespace x2
+#include "tile_attn.cuh"     // fused T-scale forward (uses head_sum_t)
+namespace x2 {
 
 // Attention-dropout keep factor for (triplet, head): 0 or 1/(1-p); counter-based so forward and
 // backward regenerate the same mask.
@@ -666,7 +669,7 @@ k_attn_bwd_src(const float* __restrict__ qkvs, int ldq, const float* __restrict_
 
 // ------------------------------------------------------------------ Linear dispatch (SIMT / tensor core)
 static inline int lin_mode(int mode) {
-  return (mode == X2_MODE_TF32X3_FUSED || mode == X2_MODE_TF32) ? X2_MODE_TF32X3 : mode;
+  return (mode == X2_MODE_TF32X3_UNFUSED || mode == X2_MODE_TF32) ? X2_MODE_TF32X3 : mode;
 }
 
 struct Lin {
@@ -727,7 +730,7 @@ static int lin_wgrad(const Lin& L, const float* dy, int64_t lddy, const float* x
 static int check_desc(const x2_conv_desc* d) {
   X2_CHECK_ARG(d != nullptr, "conv: null descriptor");
   X2_CHECK_ARG(d->E >= 0 && d->T >= 0 && d->E < 2147483647LL && d->T < 2147483647LL, "conv: bad E/T");
-  X2_CHECK_ARG(d->mode == X2_MODE_FP32 || d->mode == X2_MODE_TF32X3 || d->mode == X2_MODE_TF32X3_FUSED ||
+  X2_CHECK_ARG(d->mode == X2_MODE_FP32 || d->mode == X2_MODE_TF32X3 || d->mode == X2_MODE_TF32X3_UNFUSED ||
                    d->mode == X2_MODE_TF32, "conv: unknown mode %d", d->mode);
   X2_CHECK_ARG(d->mode == X2_MODE_FP32 || d->D % 128 == 0,
                "conv: X2_MODE_TF32X3 needs heads*out_channels to be a multiple of 128 (got %d)", d->D);
@@ -749,12 +752,11 @@ static int check_desc(const x2_conv_desc* d) {
   return X2_OK;
 }
 
-struct FwdWs { float* xs; void* img; void* fused; };
+struct FwdWs { float* xs; void* img; };
 static size_t fwd_layout(const x2_conv_desc* d, void* ws, FwdWs* w) {
   Arena a(ws, (size_t)-1);
   w->xs = a.take<float>((size_t)d->E * d->D + 4);
   w->img = a.take<char>(tc::bimage_bytes(kTcBlock, kTcBlock) + 256);
-  w->fused = a.take<char>(tc::fused_fwd_workspace_bytes(d->T));
   return align_up(a.off, 256) + 256;
 }
 
@@ -842,6 +844,58 @@ static int launch_attn_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float*
   }
   X2_LAUNCH_OK();
   return X2_OK;
+}
+
+static bool tile_fwd_enabled() {
+  static const int on = [] { const char* v = getenv("X2GNN_FUSED"); return (v && v[0] == '0') ? 0 : 1; }();
+  return on != 0;
+}
+// the fused forward needs: tensor-core mode, the tiling of a target-sorted list, D = 128, edge_attr [T,128]
+// (or the table form / no lin_edge), S even <= 64, no dropout, no alpha output, 16-byte aligned rows
+static bool tile_fwd_usable(const x2_conv_desc* d, const float* alpha) {
+  if (!(d->mode == X2_MODE_TF32X3 || d->mode == X2_MODE_TF32) || !tile_fwd_enabled()) return false;
+  if (d->mode == X2_MODE_TF32) return false;                      // the one-pass mode keeps the unfused kernels
+  if (!d->tiles || !d->tile_items || d->n_tiles <= 0 || !d->tgt_sorted || d->T <= 0 || alpha || d->dropout_p > 0.f) return false;
+  if (!tc::tile_fwd_supported(d->D, d->H, d->C, d->A, d->S, d->ea_index != nullptr)) return false;
+  if ((reinterpret_cast<uintptr_t>(d->sbf) & 7) != 0) return false;
+  if (d->A > 0 && !d->ea_index && (reinterpret_cast<uintptr_t>(d->edge_attr) & 15) != 0) return false;
+  return true;
+}
+template <int LPH>
+static int launch_tile_fwd_lph(const tc::TaParams& p, int ea_mode, int grid, cudaStream_t st) {
+  auto go = [&](auto kern) -> int {
+    X2_DYN_SMEM(kern, tc::kTaSmem);
+    launch_k(kern, dim3(grid), dim3(tc::kTaThreads), tc::kTaSmem, st, p);
+    X2_LAUNCH_OK();
+    return X2_OK;
+  };
+  switch (ea_mode) {
+    case tc::kTaEaTriplet: return go(tc::k_tile_fwd<LPH, tc::kTaEaTriplet>);
+    case tc::kTaEaSegment: return go(tc::k_tile_fwd<LPH, tc::kTaEaSegment>);
+    default: return go(tc::k_tile_fwd<LPH, tc::kTaEaNone>);
+  }
+}
+static int launch_tile_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, cudaStream_t st) {
+  tc::TaParams p{};
+  const int ea_mode = d->A == 0 ? tc::kTaEaNone : (d->ea_index ? tc::kTaEaSegment : tc::kTaEaTriplet);
+  p.ea = ea_mode == tc::kTaEaSegment ? s->ea : d->edge_attr;
+  p.ea_index = d->ea_index;
+  p.sbf = d->sbf; p.S = d->S;
+  p.w_edge = d->w_edge; p.w_sbf = d->w_sbf; p.b_sbf = d->b_sbf;
+  p.qkvs = s->qkvs; p.ldq = 4 * d->D;
+  p.src = d->src; p.tgt = d->tgt; p.rowptr = d->rowptr_tgt;
+  p.tile = d->tiles; p.items = d->tile_items; p.ntiles = (int)d->n_tiles;
+  p.H = d->H; p.C = d->C; p.scale = 1.0f / sqrtf((float)d->C); p.fuse_skip = d->fuse_skip;
+  p.out = out; p.attn = s->attn; p.lse = s->lse;
+  p.ea_out = ea_mode == tc::kTaEaTriplet ? s->ea : nullptr;      // still consumed by the backward kernels
+  p.sg_out = s->sg;
+  const int grid = (int)(d->n_tiles < kNumSM ? d->n_tiles : kNumSM);
+  switch (d->C / 4) {
+    case 1: return launch_tile_fwd_lph<1>(p, ea_mode, grid, st);
+    case 2: return launch_tile_fwd_lph<2>(p, ea_mode, grid, st);
+    case 4: return launch_tile_fwd_lph<4>(p, ea_mode, grid, st);
+    default: return launch_tile_fwd_lph<0>(p, ea_mode, grid, st);
+  }
 }
 
 template <int VEC, int EA, bool DROP>
@@ -956,6 +1010,7 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
   phase_begin(st);
   if (s->xs) w.xs = s->xs;          // kept for the backward (saved.xs) instead of living in the workspace
   // (1) x_src = x * lin_rbf(rbf)                                             :99-100
+  if ((size_t)D * d->R * sizeof(float) > 48 * 1024) X2_DYN_SMEM(k_rbf_filter, 64 * 1024);     // D = 256, R > 48
   launch_k(k_rbf_filter, dim3(filter_grid(E)), dim3(kFilterRows * 32), (size_t)D * d->R * sizeof(float), st, 
       d->x, d->rbf, d->w_rbf, E, D, d->R, w.xs, nullptr);
   X2_LAUNCH_OK();
@@ -986,26 +1041,13 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
     X2_TRY((launch_gemm<true, true>(p, nb, E, D, D, D, D, 4 * D, 0, st)));
   }
   phase_end(X2_PHASE_NODE_PROJ, st);
-  // (3+4 fused) tensor-core projections + segmented attention in one kernel, when the triplet list is
-  // target-sorted (what vertex_to_edge_2 produces): edge_attr / sbf are streamed once, EA / Sg stay in
-  // tensor memory for the forward result.
-  // EXPERIMENTAL, opt-in (X2_MODE_TF32X3_FUSED): correct (same parity tests) but ~2x slower than the
-  // unfused pair today -- with lane = channel the four epilogue warps of a stream each execute the whole
-  // per-triplet instruction sequence (profiles/r1_notes.md).
-  if (d->mode == X2_MODE_TF32X3_FUSED && d->tgt_sorted && T > 0 && d->dropout_p == 0.f && alpha == nullptr &&
-      d->ea_index == nullptr &&
-      tc::fused_fwd_supported(D, d->H, d->C, d->A, d->S)) {
-    tc::F1Params f{};
-    f.ea = d->edge_attr; f.ld_ea = d->A; f.A = d->A;
-    f.sbf = d->sbf; f.ld_s = d->S; f.S = d->S;
-    f.w_edge = d->w_edge; f.b_sbf = d->b_sbf;
-    f.qkvs = s->qkvs; f.ldq = 4 * D;
-    f.src = d->src; f.tgt = d->tgt; f.rowptr = d->rowptr_tgt;
-    f.E = E; f.T = T; f.H = d->H; f.C = d->C; f.scale = 1.0f / sqrtf((float)d->C); f.fuse_skip = d->fuse_skip;
-    f.out = out; f.attn = s->attn; f.lse = s->lse;
-    f.ea_out = s->ea; f.sg_out = s->sg;        // still consumed by the backward kernels
+  // (3+4 fused) lin_edge + lin_sbf + segmented attention as ONE tcgen05 kernel over segment-aligned tiles
+  // (csrc/tile_attn.cuh): edge_attr / sbf are streamed once, EA / Sg go from tensor memory through a
+  // shared-memory tile straight into the attention warps.  Default whenever the caller supplies the tiling.
+  if (tile_fwd_usable(d, alpha)) {
+    if (d->ea_index) X2_TRY(lin_fwd(L, d->edge_attr, d->A, d->w_edge, d->A, nullptr, s->ea, D, d->ea_rows, D, d->A));
     phase_end(X2_PHASE_TROW_PROJ, st);
-    X2_TRY(tc::fused_fwd(f, d->w_sbf, w.fused, st));
+    X2_TRY(launch_tile_fwd(d, s, out, st));
     phase_end(X2_PHASE_ATTN_FWD, st);
     return X2_OK;
   }
@@ -1086,6 +1128,7 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
   if (s->xs && fused_tail) {
     w.xs = s->xs;                                    // the forward kept x * lin_rbf(rbf): nothing to recompute
   } else {
+    if ((size_t)D * R * sizeof(float) > 48 * 1024) X2_DYN_SMEM(k_rbf_filter, 64 * 1024);
     launch_k(k_rbf_filter, dim3(filter_grid(E)), dim3(kFilterRows * 32), (size_t)D * R * sizeof(float), st, 
         d->x, d->rbf, d->w_rbf, E, D, R, w.xs, fused_tail ? nullptr : w.F);
     X2_LAUNCH_OK();
@@ -1120,11 +1163,7 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
       const int64_t fneed = cdiv(E, kFilterRows);
       const unsigned fgrid = (unsigned)(fneed < kNumSM * 4 ? fneed : kNumSM * 4);
       const size_t fsmem = (size_t)kFilterRows * RM * D * sizeof(float);
-      static bool attr_set = false;
-      if (!attr_set) {
-        X2_CUDA_OK(cudaFuncSetAttribute(k_filter_bwd_full<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        attr_set = true;
-      }
+      X2_DYN_SMEM(k_filter_bwd_full<16>, 65536);
       if (RM == 8)
         launch_k(k_filter_bwd_full<8>, dim3(fgrid), dim3(kFilterRows * 32), fsmem, st, d->x, d->rbf, d->w_rbf, w.dxs, w.dxs2, g->dx,
             d->fuse_skip ? w.dx2 : nullptr, E, R, g->drbf, w.wg);

@@ -207,11 +207,7 @@ int x2_rbf_readout_bwd(const float* x, const float* rbf, const float* w, const f
   if (RM == 8) {
     k_readout_bwd<8><<<grid, block, smem, st>>>(x, rbf, w, b, rowptr, grad_out, N, E, D, R, dx, drbf_part, partial);
   } else {
-    static bool once = false;
-    if (!once) {
-      X2_CUDA_OK(cudaFuncSetAttribute(k_readout_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-      once = true;
-    }
+    X2_DYN_SMEM(k_readout_bwd<16>, 80 * 1024);
     k_readout_bwd<16><<<grid, block, smem, st>>>(x, rbf, w, b, rowptr, grad_out, N, E, D, R, dx, drbf_part, partial);
   }
   X2_LAUNCH_OK();

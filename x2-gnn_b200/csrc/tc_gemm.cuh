@@ -1077,13 +1077,9 @@ static int tc_gemm_batch(const G1Prob* probs, int nprob, int ngroups, int64_t M,
   }
   const int stages = 5;                                   // 5 x 32 KB = 160 KB (6 and 7 stages measured the same)
   const size_t smem = 1024 + (size_t)stages * 2 * kChunkBytes + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    X2_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    X2_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    X2_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    attr_set = true;
-  }
+  X2_DYN_SMEM(k_tc_gemm<0>, kMaxSmem);
+  X2_DYN_SMEM(k_tc_gemm<8>, kMaxSmem);
+  X2_DYN_SMEM(k_tc_gemm<16>, kMaxSmem);
   // producer path: the widest cp.async piece every problem's rows are aligned to (0 = register staging)
   int piece = cp_async_enabled() ? 16 : 0;
   for (int i = 0; i < nprob && piece; ++i) {
@@ -1207,13 +1203,9 @@ static int tc_wgrad_batch(const G2Job* jobs, int nprob, int64_t rows, int N, flo
   const uint32_t stage_bytes = 2 * (uint32_t)(N_pad / 32) * 4096 + (xmode ? 16384u : 0u);
   const int stages = 4;                                                 // <= 192 KB smem, 4 x 64 TMEM columns
   const size_t smem = 1024 + (size_t)stages * stage_bytes + 256 + 4 * 128 * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    X2_CUDA_OK(cudaFuncSetAttribute(k_tc_wgrad<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    X2_CUDA_OK(cudaFuncSetAttribute(k_tc_wgrad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    X2_CUDA_OK(cudaFuncSetAttribute(k_tc_wgrad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    attr_set = true;
-  }
+  X2_DYN_SMEM(k_tc_wgrad<0>, kMaxSmem);
+  X2_DYN_SMEM(k_tc_wgrad<1>, kMaxSmem);
+  X2_DYN_SMEM(k_tc_wgrad<2>, kMaxSmem);
   G2Params p{};
   ReduceBatch rb{};
   bool any_bias = false;

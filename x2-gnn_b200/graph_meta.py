@@ -25,6 +25,10 @@ class LineGraphMeta:
     rowptr_src: torch.Tensor   # [E+1] int32
     order_src: torch.Tensor    # [T] int32
     target_sorted: bool
+    max_seg: int = 0           # longest target segment
+    tiles: torch.Tensor = None # [n_tiles + 1, 4] int32 or None: tiling of the target-sorted list for the fused
+    tile_items: torch.Tensor = None   # kernels and its work items [., 2] int32 (x2_tiles_build)
+    n_tiles: int = 0
 
 
 def build(edge_index: torch.Tensor, num_nodes: int) -> LineGraphMeta:
@@ -43,7 +47,7 @@ def build(edge_index: torch.Tensor, num_nodes: int) -> LineGraphMeta:
     rp_s = torch.empty(E + 1, **i32)
     od_t = torch.empty(max(T, 1), **i32)
     od_s = torch.empty(max(T, 1), **i32)
-    flags = torch.zeros(2, **i32)
+    flags = torch.zeros(4, **i32)
     ws = _lib.workspace(L.x2_meta_workspace_bytes(T, E), dev)
     _lib.check(L.x2_meta_build(_lib.ptr(ei), T, E, _lib.ptr(src), _lib.ptr(tgt), _lib.ptr(rp_t),
                                _lib.ptr(od_t), _lib.ptr(rp_s), _lib.ptr(od_s), _lib.ptr(flags),
@@ -51,7 +55,19 @@ def build(edge_index: torch.Tensor, num_nodes: int) -> LineGraphMeta:
     f = flags.tolist()          # one host sync per batch; also surfaces async kernel errors
     if f[1] != 0:
         raise IndexError(f"edge_index has {f[1]} entries outside [0, {E})")
-    return LineGraphMeta(T, E, src, tgt, rp_t, od_t, rp_s, od_s, bool(f[0]))
+    meta = LineGraphMeta(T, E, src, tgt, rp_t, od_t, rp_s, od_s, bool(f[0]), int(f[2]))
+    if meta.target_sorted and T > 0:
+        # segment-aligned tiles for the fused tcgen05 kernels; 0 tiles: a segment is too long for the tile
+        n = int(L.x2_tiles_count(T, meta.max_seg))
+        if n > 0 and E < (1 << 27):
+            meta.tiles = torch.empty((n + 1, 4), **i32)
+            meta.tile_items = torch.empty((int(L.x2_tile_items_bound(T, E)), 2), **i32)
+            meta.n_tiles = n
+            ws2 = _lib.workspace(L.x2_tiles_workspace_bytes(E), dev)
+            _lib.check(L.x2_tiles_build(_lib.ptr(rp_t), E, T, meta.max_seg, _lib.ptr(meta.tiles), n,
+                                        _lib.ptr(meta.tile_items), _lib.ptr(ws2), ws2.numel(), _lib.stream()),
+                       "x2_tiles_build")
+    return meta
 
 
 _cache: list = []   # [(weakref(edge_index), version, num_nodes, meta)], most recent first

@@ -22,13 +22,13 @@ from . import _lib, graph_meta
 
 MODE_FP32 = 0      # X2_MODE_FP32: SIMT fp32 everywhere
 MODE_TF32X3 = 1    # X2_MODE_TF32X3: Linear layers on tcgen05 tensor cores, 3xTF32 (fp32-accurate)
-MODE_TF32X3_FUSED = 2   # experimental: + fused tcgen05 projection/attention forward kernel
+MODE_TF32X3_UNFUSED = 2   # same numerics, never the fused tile kernels (A/B, coverage of the generic kernels)
 MODE_TF32 = 3      # X2_MODE_TF32: reduced precision, one tf32 pass per product (the 2e-2 tolerance class)
 
 
 def default_mode(hc: int) -> int:
     """Tensor-core Linear layers (fp32-accurate 3xTF32) whenever the shape allows; override with
-    X2GNN_MODE=fp32|tf32x3|tf32 (tf32 = reduced precision, opt-in only)."""
+    X2GNN_MODE=fp32|tf32x3|tf32x3_unfused|tf32 (tf32 = reduced precision, opt-in only)."""
     env = os.environ.get("X2GNN_MODE", "").lower()
     if env == "fp32":
         return MODE_FP32
@@ -36,8 +36,8 @@ def default_mode(hc: int) -> int:
         return MODE_TF32X3
     if env == "tf32":
         return MODE_TF32 if hc % 128 == 0 else MODE_FP32
-    if env == "tf32x3_fused":
-        return MODE_TF32X3_FUSED if hc == 128 else MODE_TF32X3
+    if env == "tf32x3_unfused":
+        return MODE_TF32X3_UNFUSED if hc % 128 == 0 else MODE_FP32
     return MODE_TF32X3 if hc % 128 == 0 else MODE_FP32
 
 
@@ -79,6 +79,17 @@ class _SBFConvFn(torch.autograd.Function):
         A = t["edge_attr"].size(1) if t["w_edge"] is not None else 0
         if meta.E != E:
             raise ValueError(f"edge_index was indexed for {meta.E} nodes but x has {E} rows")
+        # the kernels index the weights with D, S, R, A taken from the inputs: a basis of the wrong width
+        # must raise here (the reference fails inside F.linear), not read out of bounds on the device
+        HC = H * Cc
+        want = {"w_rbf": (D, R), "w_sbf": (HC, S), "b_sbf": (HC,), "w_q": (HC, D), "b_q": (HC,), "w_k": (HC, D),
+                "b_k": (HC,), "w_v": (HC, D), "b_v": (HC,), "w_edge": (HC, A), "w_skip": (HC, D), "b_skip": (HC,)}
+        for n, shp in want.items():
+            if t[n] is not None and tuple(t[n].shape) != shp:
+                raise ValueError(f"SBFTransformerConv: {n} has shape {tuple(t[n].shape)}, the inputs need {shp} "
+                                 f"(x [{E},{D}], rbf [.,{R}], sbf [.,{S}], edge_attr [.,{A}], heads*out_channels {HC})")
+        if D != HC:
+            raise ValueError(f"SBFTransformerConv: x has {D} channels, heads*out_channels = {HC}")
         groups = cfg.get("ea_groups") if A else None     # segment-constant edge_attr table (opt-in)
         n_ea = groups.rows if groups is not None else T
         if t["sbf"].size(0) != T or (A and t["edge_attr"].size(0) != n_ea) or t["rbf"].size(0) != E:
@@ -104,6 +115,7 @@ class _SBFConvFn(torch.autograd.Function):
         for n in ("src", "tgt", "rowptr_tgt", "order_tgt", "rowptr_src", "order_src"):
             setattr(desc, n, _lib.ptr(getattr(meta, n)))
         _set_groups(desc, groups)
+        desc.tiles, desc.tile_items, desc.n_tiles = _lib.ptr(meta.tiles), _lib.ptr(meta.tile_items), meta.n_tiles
 
         f32 = dict(dtype=torch.float32, device=dev)
         qkvs = torch.empty((E, 4 * D), **f32)
@@ -152,6 +164,7 @@ class _SBFConvFn(torch.autograd.Function):
         for n in ("src", "tgt", "rowptr_tgt", "order_tgt", "rowptr_src", "order_src"):
             setattr(desc, n, _lib.ptr(getattr(meta, n)))
         _set_groups(desc, ctx.groups)
+        desc.tiles, desc.tile_items, desc.n_tiles = _lib.ptr(meta.tiles), _lib.ptr(meta.tile_items), meta.n_tiles
         n_ea = ctx.groups.rows if ctx.groups is not None else T
         saved = _lib.ConvSaved(_lib.ptr(qkvs), _lib.ptr(attn), _lib.ptr(lse), _lib.ptr(ea), _lib.ptr(sg),
                                _lib.ptr(xs))

@@ -114,22 +114,18 @@ int x2_meta_build(const int64_t* edge_index, int64_t T, int64_t E, int32_t* src,
                   int32_t* rowptr_tgt, int32_t* order_tgt, int32_t* rowptr_src,
                   int32_t* order_src, int32_t* flags, void* ws, size_t ws_bytes, void* stream);
 
-/* Tiles of the fused forward / backward-by-target kernels (csrc/tile_attn.cuh): the target-sorted triplet
- * list cut into runs of whole segments with at most X2_TILE_ROWS triplets, and every segment cut (relative to
- * its own start) into ITEMS of at most X2_TILE_ITEM_ROWS rows, the work units of the attention warps.
- * x2_tiles_count gives the number of tiles for T triplets whose longest segment is max_seg (flags[2] of
- * x2_meta_build), or 0 when the segments are too long for the tile (the conv then takes the unfused kernels).
- * x2_tiles_build fills tile[4 * (ntiles + 1)] int32: (first target, first triplet, first item, 0) of every
- * tile, last entry (E, T, number of items, 0); and items[2 * x2_tile_items_bound(T, E)] int32: (first
- * triplet, (target << 4) | (rows - 1)) of every item, in row order.  Needs E < 2^27.
- * ws >= x2_tiles_workspace_bytes(E). */
-#define X2_TILE_ROWS 120
-#define X2_TILE_ITEM_ROWS 8
-int64_t x2_tiles_count(int64_t T, int32_t max_seg);
-int64_t x2_tile_items_bound(int64_t T, int64_t E);
-size_t x2_tiles_workspace_bytes(int64_t E);
-int x2_tiles_build(const int32_t* rowptr_tgt, int64_t E, int64_t T, int32_t max_seg, int32_t* tile,
-                   int64_t ntiles, int32_t* items, void* ws, size_t ws_bytes, void* stream);
+/* Work items of the fused tile kernels (csrc/tile_attn.cuh): every target segment of the target-sorted
+ * triplet list is cut, from its own start, into ITEMS of at most X2_ITEM_ROWS rows -- the unit of work of an
+ * attention warp; X2_UNIT_ITEMS consecutive items form the contiguous row range a CTA streams at a time.
+ * x2_items_build fills itemptr[E + 1] (items of target e are itemptr[e] .. itemptr[e+1]) and items[2 * n]
+ * int32, n <= x2_items_bound(T, E): (first triplet, (target << 4) | (rows - 1)) in row order, followed by the
+ * sentinel (T, 0).  Needs E < 2^27.  ws >= x2_items_workspace_bytes(E). */
+#define X2_ITEM_ROWS 8
+#define X2_UNIT_ITEMS 15
+int64_t x2_items_bound(int64_t T, int64_t E);
+size_t x2_items_workspace_bytes(int64_t E);
+int x2_items_build(const int32_t* rowptr_tgt, int64_t E, int64_t T, int32_t* itemptr, int32_t* items, void* ws,
+                   size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------- basis expansions
  * envelop.py:16-21: out = 1/x + a x^(p-1) + b x^p + c x^(p+1), x = d * inv_cutoff. */
@@ -206,12 +202,12 @@ typedef struct {
    * order_src).  Then saved.ea is [ea_rows, D] and grads.dedge_attr is [ea_rows, A]. */
   int64_t ea_rows;
   const int32_t *ea_index, *ea_rowptr, *ea_order;
-  /* Optional tiling of the target-sorted triplet list (x2_tiles_build); NULL / 0 => unfused kernels.  With it
+  /* Optional work items of the target-sorted triplet list (x2_items_build); NULL => unfused kernels.  With them
    * (and tgt_sorted, D == 128, A in {0, 128} or the edge_attr table, S even <= 64, no dropout, no alpha
    * output) lin_edge, lin_sbf and the segmented attention run as ONE kernel that reads edge_attr / sbf once. */
-  const int32_t* tiles;
-  const int32_t* tile_items;
-  int64_t n_tiles;
+  const int32_t* items;
+  const int32_t* itemptr;
+  int64_t items_bound;   /* capacity of `items` in entries (>= number of items + 1): sizes the partial-state scratch */
 } x2_conv_desc;
 
 #define X2_MODE_FP32 0    /* fp32 SIMT arithmetic everywhere (1e-5 parity) */

@@ -14,7 +14,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libx2gnn.so")
+LIB_PATH = os.environ.get("X2GNN_LIB") or os.path.join(_HERE, "lib", "libx2gnn.so")   # X2GNN_LIB: A/B builds
 
 _lock = threading.Lock()
 _lib = None
@@ -40,7 +40,7 @@ class ConvDesc(C.Structure):
         ("w_v", c_f32p), ("b_v", c_f32p), ("w_edge", c_f32p), ("w_sbf", c_f32p), ("b_sbf", c_f32p),
         ("w_skip", c_f32p), ("b_skip", c_f32p),
         ("ea_rows", C.c_int64), ("ea_index", c_i32p), ("ea_rowptr", c_i32p), ("ea_order", c_i32p),
-        ("tiles", c_i32p), ("tile_items", c_i32p), ("n_tiles", C.c_int64),
+        ("items", c_i32p), ("itemptr", c_i32p), ("items_bound", C.c_int64),
     ]
 
 
@@ -76,10 +76,9 @@ SIGNATURES = {
     "x2_triplets_fill": (C.c_int, [_P, _I64, _I64, _P, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
     "x2_meta_workspace_bytes": (_SZ, [_I64, _I64]),
     "x2_meta_build": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
-    "x2_tiles_count": (C.c_int64, [_I64, _I32]),
-    "x2_tile_items_bound": (C.c_int64, [_I64, _I64]),
-    "x2_tiles_workspace_bytes": (_SZ, [_I64]),
-    "x2_tiles_build": (C.c_int, [_P, _I64, _I64, _I32, _P, _I64, _P, _P, _SZ, _P]),
+    "x2_items_bound": (C.c_int64, [_I64, _I64]),
+    "x2_items_workspace_bytes": (_SZ, [_I64]),
+    "x2_items_build": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _SZ, _P]),
     "x2_envelope_fwd": (C.c_int, [_P, _I64, _F, _I32, _F, _F, _F, _P, _P]),
     "x2_radial_fwd": (C.c_int, [_P, _P, _P, _I64, _I32, _F, _P, _P]),
     "x2_radial_bwd_workspace_bytes": (_SZ, [_I64, _I32]),

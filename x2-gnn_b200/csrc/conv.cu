@@ -752,11 +752,12 @@ static int check_desc(const x2_conv_desc* d) {
   return X2_OK;
 }
 
-struct FwdWs { float* xs; void* img; };
+struct FwdWs { float* xs; void* img; float* part; };
 static size_t fwd_layout(const x2_conv_desc* d, void* ws, FwdWs* w) {
   Arena a(ws, (size_t)-1);
   w->xs = a.take<float>((size_t)d->E * d->D + 4);
   w->img = a.take<char>(tc::bimage_bytes(kTcBlock, kTcBlock) + 256);
+  w->part = a.take<float>(d->items ? (size_t)d->items_bound * tc::kTaPart : 4);   // partial states of the fused forward
   return align_up(a.off, 256) + 256;
 }
 
@@ -846,6 +847,7 @@ static int launch_attn_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float*
   return X2_OK;
 }
 
+static unsigned long long* g_tile_trace = nullptr;     // development only (x2_debug_tile_trace)
 static bool tile_fwd_enabled() {
   static const int on = [] { const char* v = getenv("X2GNN_FUSED"); return (v && v[0] == '0') ? 0 : 1; }();
   return on != 0;
@@ -855,7 +857,7 @@ static bool tile_fwd_enabled() {
 static bool tile_fwd_usable(const x2_conv_desc* d, const float* alpha) {
   if (!(d->mode == X2_MODE_TF32X3 || d->mode == X2_MODE_TF32) || !tile_fwd_enabled()) return false;
   if (d->mode == X2_MODE_TF32) return false;                      // the one-pass mode keeps the unfused kernels
-  if (!d->tiles || !d->tile_items || d->n_tiles <= 0 || !d->tgt_sorted || d->T <= 0 || alpha || d->dropout_p > 0.f) return false;
+  if (!d->items || !d->itemptr || d->items_bound <= 0 || !d->tgt_sorted || d->T <= 0 || alpha || d->dropout_p > 0.f) return false;
   if (!tc::tile_fwd_supported(d->D, d->H, d->C, d->A, d->S, d->ea_index != nullptr)) return false;
   if ((reinterpret_cast<uintptr_t>(d->sbf) & 7) != 0) return false;
   if (d->A > 0 && !d->ea_index && (reinterpret_cast<uintptr_t>(d->edge_attr) & 15) != 0) return false;
@@ -875,7 +877,7 @@ static int launch_tile_fwd_lph(const tc::TaParams& p, int ea_mode, int grid, cud
     default: return go(tc::k_tile_fwd<LPH, tc::kTaEaNone>);
   }
 }
-static int launch_tile_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, cudaStream_t st) {
+static int launch_tile_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, float* part, cudaStream_t st) {
   tc::TaParams p{};
   const int ea_mode = d->A == 0 ? tc::kTaEaNone : (d->ea_index ? tc::kTaEaSegment : tc::kTaEaTriplet);
   p.ea = ea_mode == tc::kTaEaSegment ? s->ea : d->edge_attr;
@@ -883,19 +885,30 @@ static int launch_tile_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float*
   p.sbf = d->sbf; p.S = d->S;
   p.w_edge = d->w_edge; p.w_sbf = d->w_sbf; p.b_sbf = d->b_sbf;
   p.qkvs = s->qkvs; p.ldq = 4 * d->D;
-  p.src = d->src; p.tgt = d->tgt; p.rowptr = d->rowptr_tgt;
-  p.tile = d->tiles; p.items = d->tile_items; p.ntiles = (int)d->n_tiles;
-  p.H = d->H; p.C = d->C; p.scale = 1.0f / sqrtf((float)d->C); p.fuse_skip = d->fuse_skip;
-  p.out = out; p.attn = s->attn; p.lse = s->lse;
+  p.src = d->src;
+  p.items = d->items; p.itemptr = d->itemptr;
+  p.E = d->E; p.T = d->T;
+  p.H = d->H; p.C = d->C; p.scale = 1.0f / sqrtf((float)d->C);
+  p.part = part;
   p.ea_out = ea_mode == tc::kTaEaTriplet ? s->ea : nullptr;      // still consumed by the backward kernels
   p.sg_out = s->sg;
-  const int grid = (int)(d->n_tiles < kNumSM ? d->n_tiles : kNumSM);
+  p.trace = g_tile_trace;
+  { static const int dbg = [] { const char* v = getenv("X2GNN_TA_DBG"); return v ? atoi(v) : 0; }(); p.dbg = dbg; }
+  // persistent: one CTA per SM (fewer when the list is short: a unit is ~100 rows)
+  const int64_t units = d->T / (X2_UNIT_ITEMS * X2_ITEM_ROWS) + 1;
+  const int grid = (int)(units < kNumSM ? units : kNumSM);
+  int rc;
   switch (d->C / 4) {
-    case 1: return launch_tile_fwd_lph<1>(p, ea_mode, grid, st);
-    case 2: return launch_tile_fwd_lph<2>(p, ea_mode, grid, st);
-    case 4: return launch_tile_fwd_lph<4>(p, ea_mode, grid, st);
-    default: return launch_tile_fwd_lph<0>(p, ea_mode, grid, st);
+    case 1: rc = launch_tile_fwd_lph<1>(p, ea_mode, grid, st); break;
+    case 2: rc = launch_tile_fwd_lph<2>(p, ea_mode, grid, st); break;
+    case 4: rc = launch_tile_fwd_lph<4>(p, ea_mode, grid, st); break;
+    default: rc = launch_tile_fwd_lph<0>(p, ea_mode, grid, st); break;
   }
+  if (rc != X2_OK) return rc;
+  launch_k(tc::k_item_merge, dim3((unsigned)cdiv(d->E * 32, 128)), dim3(128), 0, st, (const float*)part, d->itemptr,
+           (const float*)s->qkvs, 4 * d->D, d->E, d->H, d->C, d->fuse_skip, out, s->attn, s->lse);
+  X2_LAUNCH_OK();
+  return X2_OK;
 }
 
 template <int VEC, int EA, bool DROP>
@@ -956,6 +969,10 @@ using namespace x2;
   } while (0)
 
 extern "C" {
+
+// development hook (not in x2gnn.h): device buffer of 16 x 256 uint64 that CTA 0 of the fused tile kernel fills
+// with clock64() stamps of its roles (tools/tile_probe.py); NULL turns it off
+void x2_debug_tile_trace(void* dev_buf) { x2::g_tile_trace = static_cast<unsigned long long*>(dev_buf); }
 
 // ---- tensor-core GEMM building blocks (also exercised directly by tests/test_gpu_tc_gemm.py)
 size_t x2_tc_gemm_workspace_bytes(int32_t K, int32_t N) { return tc::bimage_bytes(K, N) + 256; }
@@ -1047,7 +1064,7 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
   if (tile_fwd_usable(d, alpha)) {
     if (d->ea_index) X2_TRY(lin_fwd(L, d->edge_attr, d->A, d->w_edge, d->A, nullptr, s->ea, D, d->ea_rows, D, d->A));
     phase_end(X2_PHASE_TROW_PROJ, st);
-    X2_TRY(launch_tile_fwd(d, s, out, st));
+    X2_TRY(launch_tile_fwd(d, s, out, w.part, st));
     phase_end(X2_PHASE_ATTN_FWD, st);
     return X2_OK;
   }

@@ -306,42 +306,27 @@ __global__ void k_meta_finalize(int32_t* flags_out, const int32_t* flags_in) {
   flags_out[3] = 0;
 }
 
-// Tiles of the fused forward (csrc/tile_attn.cuh): tile k holds the targets whose first triplet lies in the
-// window [k W, (k + 1) W) of the target-sorted list, i.e. whole segments; with W = rows - max_seg + 1 a tile
-// never has more than `rows` triplets.  tile[4k] = first target, [4k+1] = first triplet, [4k+2] = first item;
-// entry ntiles = (E, T, nitems).  One binary search per tile: no scan, no dependence between tiles.
-__global__ void k_tiles_build(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ itemptr, int64_t E,
-                              int64_t T, int window, int64_t ntiles, int32_t* __restrict__ tile) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k > ntiles) return;
-  int64_t lo = k == ntiles ? E : 0;
-  if (k > 0 && k < ntiles) {
-    const int64_t want = k * window;          // first e with rowptr[e] >= want
-    int64_t hi = E;
-    while (lo < hi) {
-      const int64_t mid = (lo + hi) >> 1;
-      if (rowptr[mid] < want) lo = mid + 1; else hi = mid;
-    }
-  }
-  tile[4 * k] = (int32_t)lo;
-  tile[4 * k + 1] = rowptr[lo];
-  tile[4 * k + 2] = itemptr[lo];
-  tile[4 * k + 3] = 0;
-}
-// items of a segment: runs of X2_TILE_ITEM_ROWS rows counted from the segment's own start
+// Work items of the fused tile kernels (csrc/tile_attn.cuh): every target segment cut, from its own start, into
+// runs of X2_ITEM_ROWS rows.  items[i] = (first triplet, (target << 4) | (rows - 1)), in row order; the entry
+// after the last item is the sentinel (T, 0).
 __global__ void k_item_count(const int32_t* __restrict__ rowptr, int64_t E, int32_t* __restrict__ cnt) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < E) cnt[e] = (rowptr[e + 1] - rowptr[e] + X2_TILE_ITEM_ROWS - 1) / X2_TILE_ITEM_ROWS;
+  if (e < E) cnt[e] = (rowptr[e + 1] - rowptr[e] + X2_ITEM_ROWS - 1) / X2_ITEM_ROWS;
 }
 __global__ void k_item_fill(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ itemptr, int64_t E,
                             int32_t* __restrict__ items) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
+  if (e > E) return;
+  if (e == E) {                                   // sentinel after the last item
+    items[2 * itemptr[E]] = rowptr[E];
+    items[2 * itemptr[E] + 1] = 0;
+    return;
+  }
   const int beg = rowptr[e], end = rowptr[e + 1];
   int i = itemptr[e];
-  for (int t = beg; t < end; t += X2_TILE_ITEM_ROWS, ++i) {
+  for (int t = beg; t < end; t += X2_ITEM_ROWS, ++i) {
     items[2 * i] = t;
-    items[2 * i + 1] = (int32_t)((e << 4) | (min(X2_TILE_ITEM_ROWS, end - t) - 1));
+    items[2 * i + 1] = (int32_t)((e << 4) | (min(X2_ITEM_ROWS, end - t) - 1));
   }
 }
 
@@ -518,39 +503,27 @@ int x2_meta_build(const int64_t* edge_index, int64_t T, int64_t E, int32_t* src,
   return X2_OK;
 }
 
-int64_t x2_tiles_count(int64_t T, int32_t max_seg) {
-  const int window = X2_TILE_ROWS - max_seg + 1;
-  if (T <= 0 || max_seg < 0 || window < 16) return 0;
-  return (T + window - 1) / window;
+int64_t x2_items_bound(int64_t T, int64_t E) { return T / X2_ITEM_ROWS + E + 2; }
+
+size_t x2_items_workspace_bytes(int64_t E) {
+  return align_up((size_t)(E + 1) * 4, 256) + scan_workspace_bytes(E) + 512;
 }
 
-int64_t x2_tile_items_bound(int64_t T, int64_t E) { return T / X2_TILE_ITEM_ROWS + E + 1; }
-
-size_t x2_tiles_workspace_bytes(int64_t E) {
-  return 2 * align_up((size_t)(E + 1) * 4, 256) + scan_workspace_bytes(E) + 256;
-}
-
-int x2_tiles_build(const int32_t* rowptr_tgt, int64_t E, int64_t T, int32_t max_seg, int32_t* tile,
-                   int64_t ntiles, int32_t* items, void* ws, size_t ws_bytes, void* stream) {
-  X2_CHECK_ARG(rowptr_tgt && tile && items, "x2_tiles_build: null pointer");
-  X2_CHECK_ARG(E > 0 && E < (1LL << 27), "x2_tiles_build: needs 0 < E < 2^27 (got %lld)", (long long)E);
-  X2_CHECK_ARG(ntiles > 0 && ntiles == x2_tiles_count(T, max_seg), "x2_tiles_build: ntiles does not match x2_tiles_count");
-  if (ws_bytes < x2_tiles_workspace_bytes(E)) { set_error("x2_tiles_build: workspace too small"); return X2_EWORKSPACE; }
+int x2_items_build(const int32_t* rowptr_tgt, int64_t E, int64_t T, int32_t* itemptr, int32_t* items, void* ws,
+                   size_t ws_bytes, void* stream) {
+  X2_CHECK_ARG(rowptr_tgt && itemptr && items, "x2_items_build: null pointer");
+  X2_CHECK_ARG(E > 0 && E < (1LL << 27) && T >= 0, "x2_items_build: needs 0 < E < 2^27 (got %lld)", (long long)E);
+  if (ws_bytes < x2_items_workspace_bytes(E)) { set_error("x2_items_build: workspace too small"); return X2_EWORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   Arena a(ws, ws_bytes);
   int32_t* cnt = a.take<int32_t>(E + 1);
-  int32_t* itemptr = a.take<int32_t>(E + 1);
   const size_t sbytes = scan_workspace_bytes(E);
   void* sws = a.take<char>(sbytes);
-  const unsigned gE = (unsigned)cdiv(E, 256);
-  k_item_count<<<gE, 256, 0, st>>>(rowptr_tgt, E, cnt);
+  k_item_count<<<(unsigned)cdiv(E, 256), 256, 0, st>>>(rowptr_tgt, E, cnt);
   X2_LAUNCH_OK();
   int rc = exclusive_scan_i32(cnt, itemptr, E, sws, sbytes, st);
   if (rc) return rc;
-  k_item_fill<<<gE, 256, 0, st>>>(rowptr_tgt, itemptr, E, items);
-  X2_LAUNCH_OK();
-  const int window = X2_TILE_ROWS - max_seg + 1;
-  k_tiles_build<<<(unsigned)cdiv(ntiles + 1, 256), 256, 0, st>>>(rowptr_tgt, itemptr, E, T, window, ntiles, tile);
+  k_item_fill<<<(unsigned)cdiv(E + 1, 256), 256, 0, st>>>(rowptr_tgt, itemptr, E, items);
   X2_LAUNCH_OK();
   return X2_OK;
 }

@@ -76,6 +76,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
+// Warp-collective wait: every lane polls, the loop branch is taken on a VOTE result.  A vote result is uniform by
+// construction, so the compiler keeps treating the code after the wait as convergent and may use the uniform
+// datapath for it -- with the per-thread branch of mbar_wait() the MMA-issuing warp computed its descriptors in
+// vector registers and paid an R2UR.BROADCAST waterfall (~8 instructions, ~38 cycles) per tcgen05.mma, which
+// made the ISSUE loop, not the tensor core (16 cycles per M128 N32 K8 tf32 MMA, tools/umma_rate.cu), the
+// period of the pipeline.
+__device__ __forceinline__ void mbar_wait_w(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "WAIT_LOOP_W:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "vote.sync.all.pred q, p, 0xffffffff;\n"
+      "@q bra WAIT_DONE_W;\n"
+      "bra WAIT_LOOP_W;\n"
+      "WAIT_DONE_W:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

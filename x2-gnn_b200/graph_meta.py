@@ -26,9 +26,9 @@ class LineGraphMeta:
     order_src: torch.Tensor    # [T] int32
     target_sorted: bool
     max_seg: int = 0           # longest target segment
-    tiles: torch.Tensor = None # [n_tiles + 1, 4] int32 or None: tiling of the target-sorted list for the fused
-    tile_items: torch.Tensor = None   # kernels and its work items [., 2] int32 (x2_tiles_build)
-    n_tiles: int = 0
+    items: torch.Tensor = None     # [items_bound, 2] int32 work items of the fused kernels (x2_items_build), or None
+    itemptr: torch.Tensor = None   # [E+1] int32
+    items_bound: int = 0
 
 
 def build(edge_index: torch.Tensor, num_nodes: int) -> LineGraphMeta:
@@ -56,17 +56,15 @@ def build(edge_index: torch.Tensor, num_nodes: int) -> LineGraphMeta:
     if f[1] != 0:
         raise IndexError(f"edge_index has {f[1]} entries outside [0, {E})")
     meta = LineGraphMeta(T, E, src, tgt, rp_t, od_t, rp_s, od_s, bool(f[0]), int(f[2]))
-    if meta.target_sorted and T > 0:
-        # segment-aligned tiles for the fused tcgen05 kernels; 0 tiles: a segment is too long for the tile
-        n = int(L.x2_tiles_count(T, meta.max_seg))
-        if n > 0 and E < (1 << 27):
-            meta.tiles = torch.empty((n + 1, 4), **i32)
-            meta.tile_items = torch.empty((int(L.x2_tile_items_bound(T, E)), 2), **i32)
-            meta.n_tiles = n
-            ws2 = _lib.workspace(L.x2_tiles_workspace_bytes(E), dev)
-            _lib.check(L.x2_tiles_build(_lib.ptr(rp_t), E, T, meta.max_seg, _lib.ptr(meta.tiles), n,
-                                        _lib.ptr(meta.tile_items), _lib.ptr(ws2), ws2.numel(), _lib.stream()),
-                       "x2_tiles_build")
+    if meta.target_sorted and T > 0 and 0 < E < (1 << 27):
+        # work items (<= 8 rows of one segment each) for the fused tcgen05 kernels
+        nb = int(L.x2_items_bound(T, E))
+        meta.items = torch.empty((nb, 2), **i32)
+        meta.itemptr = torch.empty(E + 1, **i32)
+        meta.items_bound = nb
+        ws2 = _lib.workspace(L.x2_items_workspace_bytes(E), dev)
+        _lib.check(L.x2_items_build(_lib.ptr(rp_t), E, T, _lib.ptr(meta.itemptr), _lib.ptr(meta.items),
+                                    _lib.ptr(ws2), ws2.numel(), _lib.stream()), "x2_items_build")
     return meta
 
 

@@ -115,7 +115,7 @@ class _SBFConvFn(torch.autograd.Function):
         for n in ("src", "tgt", "rowptr_tgt", "order_tgt", "rowptr_src", "order_src"):
             setattr(desc, n, _lib.ptr(getattr(meta, n)))
         _set_groups(desc, groups)
-        desc.tiles, desc.tile_items, desc.n_tiles = _lib.ptr(meta.tiles), _lib.ptr(meta.tile_items), meta.n_tiles
+        desc.items, desc.itemptr, desc.items_bound = _lib.ptr(meta.items), _lib.ptr(meta.itemptr), meta.items_bound
 
         f32 = dict(dtype=torch.float32, device=dev)
         qkvs = torch.empty((E, 4 * D), **f32)
@@ -164,7 +164,7 @@ class _SBFConvFn(torch.autograd.Function):
         for n in ("src", "tgt", "rowptr_tgt", "order_tgt", "rowptr_src", "order_src"):
             setattr(desc, n, _lib.ptr(getattr(meta, n)))
         _set_groups(desc, ctx.groups)
-        desc.tiles, desc.tile_items, desc.n_tiles = _lib.ptr(meta.tiles), _lib.ptr(meta.tile_items), meta.n_tiles
+        desc.items, desc.itemptr, desc.items_bound = _lib.ptr(meta.items), _lib.ptr(meta.itemptr), meta.items_bound
         n_ea = ctx.groups.rows if ctx.groups is not None else T
         saved = _lib.ConvSaved(_lib.ptr(qkvs), _lib.ptr(attn), _lib.ptr(lse), _lib.ptr(ea), _lib.ptr(sg),
                                _lib.ptr(xs))

@@ -212,16 +212,18 @@ typedef struct {
 
 #define X2_MODE_FP32 0    /* fp32 SIMT arithmetic everywhere (1e-5 parity) */
 #define X2_MODE_TF32X3 1  /* Linear layers on tcgen05 tensor cores in 3xTF32 split precision (fp32-accurate,
-                             1e-5 parity); needs D % 128 == 0.  Attention arithmetic stays fp32 SIMT.  When the
-                             caller supplies `tiles` the T-scale forward runs as one fused kernel. */
+                             1e-5 parity); needs D % 128 == 0.  Attention arithmetic stays fp32 SIMT. */
 #define X2_MODE_TF32 3    /* reduced precision: as TF32X3 but ONE tf32 pass per product (operands truncated to
                              10 mantissa bits by the tensor core, fp32 accumulation): ~5e-4 relative error on
                              layer outputs and gradients, inside the 2e-2 tolerance class of the bf16-projection
                              mode; the lo-half passes of the producers and two of three MMAs are skipped */
-#define X2_MODE_TF32X3_UNFUSED 2  /* as TF32X3 but never the fused tile kernels (csrc/tile_attn.cuh): lin_edge /
-                                     lin_sbf as separate tensor-core GEMMs that materialise EA / Sg, then the
-                                     warp-per-target attention kernels (the round-1 decomposition; A/B and
-                                     coverage of the generic kernels) */
+#define X2_MODE_TF32X3_FUSED 2  /* as TF32X3, with lin_edge, lin_sbf and the forward attention as ONE tcgen05 kernel over
+                                   the work items of x2_items_build (csrc/tile_attn.cuh) when the caller supplies them,
+                                   edge_index is target-sorted, D == 128, A in {0, 128}, S even <= 64, no dropout / alpha
+                                   request: edge_attr / sbf are read once and EA / Sg are not re-read by the forward
+                                   (0.83 GB less DRAM traffic per layer step on the bench batch).  Opt-in: parity-green and
+                                   deterministic, but 1 % slower than the unfused kernels on the bench batch today
+                                   (profiles/r2_notes.md); X2GNN_FUSED=1 selects it for X2_MODE_TF32X3 too. */
 
 /* Tensors written by fwd and consumed by bwd (caller-owned, kept alive by autograd). */
 typedef struct {

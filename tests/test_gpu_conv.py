@@ -12,14 +12,13 @@ pytestmark = pytest.mark.gpu
 INPUTS = ("x", "rbf", "sbf", "edge_attr")
 
 
-MODES = {"fp32": 0, "tf32x3": 1, "unfused": 2, "tf32": 3}   # X2_MODE_FP32 / _TF32X3 (fused tile kernels
-# when the tiling exists) / _TF32X3_UNFUSED / _TF32
+MODES = {"fp32": 0, "tf32x3": 1, "fused": 2, "tf32": 3}   # X2_MODE_FP32 / _TF32X3 / _TF32X3_FUSED (tile kernel) / _TF32
 
 
 def _mine(dims, state, mode=None, **kw):
     from x2gnn_b200.sbftransformer_conv import SBFTransformerConv
     D, H, S, R, A = dims
-    if mode in ("tf32x3", "unfused", "tf32") and D % 128:
+    if mode in ("tf32x3", "fused", "tf32") and D % 128:
         pytest.skip("tensor-core mode needs D % 128 == 0")
     c = SBFTransformerConv(D, D // H, heads=H, sbf_dim=S, rbf_dim=R, dropout=kw.pop("dropout", 0),
                            edge_dim=A, **kw)
@@ -58,7 +57,7 @@ def test_reduced_precision_tf32_mode(golden):
     assert max(errs.values()) > FP32_TOL, errs
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32x3", "unfused"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3", "fused"])
 @pytest.mark.parametrize("tag", ["cfg", "small", "c16"])
 def test_golden_fwd_bwd(golden, tag, mode):
     rec = golden("conv")[tag]
@@ -66,7 +65,7 @@ def test_golden_fwd_bwd(golden, tag, mode):
     assert list(conv.state_dict().keys()) == list(rec["state_dict"].keys())
     out, alpha, xs = _run(conv, rec, "cuda", torch.float32, want_alpha=True)
     assert relerr(out, rec["out_f64"]) < FP32_TOL
-    if mode == "tf32x3":      # the alpha request takes the unfused path; run the fused tile kernel as well
+    if mode == "fused":       # the alpha request takes the unfused path; run the fused tile kernel as well
         out2, _, xs2 = _run(conv, rec, "cuda", torch.float32, want_alpha=False)
         assert relerr(out2, rec["out_f64"]) < FP32_TOL
         for k in INPUTS:
@@ -109,7 +108,7 @@ def _graph_inputs(nmol, dims, seed):
 
 def _compare(ref, mine, rec, tol=FP32_TOL, check_alpha=True):
     o_ref, a_ref, x_ref = _run(ref, rec, "cpu", torch.float64, want_alpha=True)
-    if mine.precision == MODES["tf32x3"]:  # forward through the fused tile kernel (no alpha request)
+    if mine.precision == MODES["fused"]:   # forward through the fused tile kernel (no alpha request)
         o_f, _, _ = _run(mine, rec, "cuda", torch.float32, want_alpha=False)
         assert relerr(o_f, o_ref) < tol
     o, a, x = _run(mine, rec, "cuda", torch.float32, want_alpha=True)
@@ -132,7 +131,7 @@ def _compare(ref, mine, rec, tol=FP32_TOL, check_alpha=True):
 
 @pytest.mark.parametrize("dims", [(128, 16, 42, 6, 128), (256, 16, 112, 16, 128), (64, 8, 10, 3, 20),
                                   (32, 1, 5, 2, 7), (128, 4, 42, 6, 128)])
-@pytest.mark.parametrize("mode", ["fp32", "tf32x3", "unfused"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3", "fused"])
 def test_vs_oracle_qm9_batch(dims, mode):
     """config.json dims, class-default dims (xgnn.py:16) and odd shapes on a 6-molecule batch."""
     ref, mine = _oracle_pair(dims, mode=mode)

@@ -19,6 +19,7 @@ def main():
     t = {k: torch.from_numpy(v).cuda() for k, v in ci.items()}
     torch.manual_seed(0)
     conv = SBFTransformerConv(D, D // H, heads=H, sbf_dim=S, rbf_dim=R, edge_dim=A).cuda()
+    conv.precision = 1 if os.environ.get("X2GNN_FUSED") == "0" else 2     # X2_MODE_TF32X3 / X2_MODE_TF32X3_FUSED
     def step():
         with torch.enable_grad():
             x = t["x"].requires_grad_(True)

@@ -669,7 +669,7 @@ k_attn_bwd_src(const float* __restrict__ qkvs, int ldq, const float* __restrict_
 
 // ------------------------------------------------------------------ Linear dispatch (SIMT / tensor core)
 static inline int lin_mode(int mode) {
-  return (mode == X2_MODE_TF32X3_UNFUSED || mode == X2_MODE_TF32) ? X2_MODE_TF32X3 : mode;
+  return (mode == X2_MODE_TF32X3_FUSED || mode == X2_MODE_TF32) ? X2_MODE_TF32X3 : mode;
 }
 
 struct Lin {
@@ -730,7 +730,7 @@ static int lin_wgrad(const Lin& L, const float* dy, int64_t lddy, const float* x
 static int check_desc(const x2_conv_desc* d) {
   X2_CHECK_ARG(d != nullptr, "conv: null descriptor");
   X2_CHECK_ARG(d->E >= 0 && d->T >= 0 && d->E < 2147483647LL && d->T < 2147483647LL, "conv: bad E/T");
-  X2_CHECK_ARG(d->mode == X2_MODE_FP32 || d->mode == X2_MODE_TF32X3 || d->mode == X2_MODE_TF32X3_UNFUSED ||
+  X2_CHECK_ARG(d->mode == X2_MODE_FP32 || d->mode == X2_MODE_TF32X3 || d->mode == X2_MODE_TF32X3_FUSED ||
                    d->mode == X2_MODE_TF32, "conv: unknown mode %d", d->mode);
   X2_CHECK_ARG(d->mode == X2_MODE_FP32 || d->D % 128 == 0,
                "conv: X2_MODE_TF32X3 needs heads*out_channels to be a multiple of 128 (got %d)", d->D);
@@ -848,15 +848,14 @@ static int launch_attn_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float*
 }
 
 static unsigned long long* g_tile_trace = nullptr;     // development only (x2_debug_tile_trace)
-static bool tile_fwd_enabled() {
-  static const int on = [] { const char* v = getenv("X2GNN_FUSED"); return (v && v[0] == '0') ? 0 : 1; }();
+static bool tile_fwd_enabled() {      // X2GNN_FUSED=1: take the fused tile forward in X2_MODE_TF32X3 as well
+  static const int on = [] { const char* v = getenv("X2GNN_FUSED"); return (v && v[0] == '1') ? 1 : 0; }();
   return on != 0;
 }
 // the fused forward needs: tensor-core mode, the tiling of a target-sorted list, D = 128, edge_attr [T,128]
 // (or the table form / no lin_edge), S even <= 64, no dropout, no alpha output, 16-byte aligned rows
 static bool tile_fwd_usable(const x2_conv_desc* d, const float* alpha) {
-  if (!(d->mode == X2_MODE_TF32X3 || d->mode == X2_MODE_TF32) || !tile_fwd_enabled()) return false;
-  if (d->mode == X2_MODE_TF32) return false;                      // the one-pass mode keeps the unfused kernels
+  if (!(d->mode == X2_MODE_TF32X3_FUSED || (d->mode == X2_MODE_TF32X3 && tile_fwd_enabled()))) return false;
   if (!d->items || !d->itemptr || d->items_bound <= 0 || !d->tgt_sorted || d->T <= 0 || alpha || d->dropout_p > 0.f) return false;
   if (!tc::tile_fwd_supported(d->D, d->H, d->C, d->A, d->S, d->ea_index != nullptr)) return false;
   if ((reinterpret_cast<uintptr_t>(d->sbf) & 7) != 0) return false;
@@ -1060,7 +1059,7 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
   phase_end(X2_PHASE_NODE_PROJ, st);
   // (3+4 fused) lin_edge + lin_sbf + segmented attention as ONE tcgen05 kernel over segment-aligned tiles
   // (csrc/tile_attn.cuh): edge_attr / sbf are streamed once, EA / Sg go from tensor memory through a
-  // shared-memory tile straight into the attention warps.  Default whenever the caller supplies the tiling.
+  // shared-memory slot ring straight into the attention warps.  Opt-in (X2_MODE_TF32X3_FUSED / X2GNN_FUSED=1).
   if (tile_fwd_usable(d, alpha)) {
     if (d->ea_index) X2_TRY(lin_fwd(L, d->edge_attr, d->A, d->w_edge, d->A, nullptr, s->ea, D, d->ea_rows, D, d->A));
     phase_end(X2_PHASE_TROW_PROJ, st);

@@ -779,7 +779,8 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base_v = *tmem_slot;
+  const uint32_t tmem_base = tmem_base_v;
   pdl_sync();        // global memory from here on
 
   const int64_t rbeg = cta * p.rows_per_cta;
@@ -791,6 +792,9 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
       const uint32_t idesc = make_idesc(p.N_pad, 0, 1);          // A from TMEM, B MN-major
       const uint32_t s_u = smem_u32(sS);
       const uint32_t leader = elect_one();
+      // tensor-memory addresses derived from the value loaded from shared memory went through an R2UR.BROADCAST per
+      // MMA operand (4 per tcgen05.mma in the SASS); a redux result is uniform for the assembler
+      const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, tmem_base_v);
       uint32_t st = 0, ph = 0;
       for (int64_t c = 0; c < nchunks; ++c) {
         mbar_wait(&full[st], ph);

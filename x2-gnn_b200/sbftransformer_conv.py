@@ -22,13 +22,13 @@ from . import _lib, graph_meta
 
 MODE_FP32 = 0      # X2_MODE_FP32: SIMT fp32 everywhere
 MODE_TF32X3 = 1    # X2_MODE_TF32X3: Linear layers on tcgen05 tensor cores, 3xTF32 (fp32-accurate)
-MODE_TF32X3_UNFUSED = 2   # same numerics, never the fused tile kernels (A/B, coverage of the generic kernels)
+MODE_TF32X3_FUSED = 2   # opt-in: + lin_edge / lin_sbf / forward attention as one tcgen05 tile kernel (csrc/tile_attn.cuh)
 MODE_TF32 = 3      # X2_MODE_TF32: reduced precision, one tf32 pass per product (the 2e-2 tolerance class)
 
 
 def default_mode(hc: int) -> int:
     """Tensor-core Linear layers (fp32-accurate 3xTF32) whenever the shape allows; override with
-    X2GNN_MODE=fp32|tf32x3|tf32x3_unfused|tf32 (tf32 = reduced precision, opt-in only)."""
+    X2GNN_MODE=fp32|tf32x3|tf32x3_fused|tf32 (tf32 = reduced precision, opt-in only)."""
     env = os.environ.get("X2GNN_MODE", "").lower()
     if env == "fp32":
         return MODE_FP32
@@ -36,8 +36,8 @@ def default_mode(hc: int) -> int:
         return MODE_TF32X3
     if env == "tf32":
         return MODE_TF32 if hc % 128 == 0 else MODE_FP32
-    if env == "tf32x3_unfused":
-        return MODE_TF32X3_UNFUSED if hc % 128 == 0 else MODE_FP32
+    if env == "tf32x3_fused":
+        return MODE_TF32X3_FUSED if hc == 128 else (MODE_TF32X3 if hc % 128 == 0 else MODE_FP32)
     return MODE_TF32X3 if hc % 128 == 0 else MODE_FP32
 
 

@@ -47,6 +47,9 @@ def load_edge_graph():
     return mod
 
 
+OUT_DIR = HERE          # `python make_golden.py --out DIR` writes elsewhere (reproducibility test)
+
+
 def main():
     from x2gnn_b200 import synth
     edge_graph = load_edge_graph()
@@ -183,10 +186,13 @@ def main():
     out["model"] = md
 
     for k, v in out.items():
-        path = os.path.join(HERE, f"{k}.pt")
+        path = os.path.join(OUT_DIR, f"{k}.pt")
         torch.save(v, path)
         print(k, os.path.getsize(path) // 1024, "KiB")
 
 
 if __name__ == "__main__":
+    if "--out" in sys.argv:
+        OUT_DIR = sys.argv[sys.argv.index("--out") + 1]
+        os.makedirs(OUT_DIR, exist_ok=True)
     main()

@@ -1,6 +1,7 @@
 """Pin the oracle (CPU restatement) against golden vectors produced by the reference's
 own source (tests/golden/make_golden.py).  CPU only."""
 import math
+import os
 
 import pytest
 import torch
@@ -142,3 +143,36 @@ def test_model_prediction(golden, dtype):
     ref = rec["pred_f64"] if dtype == torch.float64 else rec["pred_f32"]
     tol = 1e-9 if dtype == torch.float64 else 2e-4
     assert torch.allclose(pred, ref, rtol=tol, atol=tol * float(ref.abs().max()))
+
+
+def _same(a, b, path=""):
+    """Structural equality of two fixtures: index tensors bit-equal, floating tensors to 1e-12."""
+    if isinstance(a, dict):
+        assert set(a) == set(b), path
+        for k in a:
+            _same(a[k], b[k], f"{path}/{k}")
+    elif torch.is_tensor(a):
+        assert a.shape == b.shape and a.dtype == b.dtype, path
+        if a.dtype.is_floating_point:
+            assert float((a.double() - b.double()).abs().max()) <= 1e-12 if a.numel() else True, path
+        else:
+            assert torch.equal(a, b), path
+    elif isinstance(a, (list, tuple)):
+        assert len(a) == len(b), path
+        for i, (u, v) in enumerate(zip(a, b)):
+            _same(u, v, f"{path}[{i}]")
+    else:
+        assert a == b, path
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference mount exists only in the build container")
+def test_committed_fixtures_reproduce_from_the_reference(tmp_path):
+    """tests/golden/*.pt are what tests/golden/make_golden.py produces TODAY from the unmodified reference
+    source (a stale fixture is still a valid reference output, but nobody could regenerate it)."""
+    import subprocess
+    import sys
+    gen = os.path.join(os.path.dirname(__file__), "golden", "make_golden.py")
+    subprocess.run([sys.executable, gen, "--out", str(tmp_path)], check=True, capture_output=True, timeout=900)
+    for name in ("graph", "bases", "conv", "model"):
+        _same(torch.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}.pt")),
+              torch.load(tmp_path / f"{name}.pt"), name)

@@ -44,8 +44,9 @@ def algorithmic_bytes(E, T, D, S, R, A):
 
 
 def host_workload(rank: int = 0, world: int = 1, nmol: int = NMOL):
-    """The rank's graphs of a global batch of nmol * world molecules (seed 0), whole molecules dealt to
-    ranks balanced by triplet count (x2gnn_b200.ddp.shard_graphs); world == 1 is the seed-0 batch."""
+    """The rank's batch of nmol molecules: rank 0 (and world == 1) is the seed-0 batch, every other rank draws its
+    own molecules with the same triplet count to within 0.5 % (x2gnn_b200.synth.qm9_shard): weak scaling with
+    identical per-rank work at every N."""
     from x2gnn_b200 import synth
     b, mine = synth.qm9_shard(nmol, world, rank, seed=0)
     tri = synth.triplets_host(b["edge_index"], len(b["x"]))[0]
@@ -243,7 +244,9 @@ def train_step_bench(dev, world, rank, steps, warmup, with_cpu):
            "ms_each_step": in_order,
            "molecules_per_gpu": NMOL, "molecules_this_rank": nmine, "loss": float(loss.detach()), "N": len(b["x"]),
            "E": int(b["edge_index"].shape[1]),
-           "sharding": "global batch of 128 x N molecules (seed 0), whole molecules dealt to ranks balanced by triplet count"}
+           "triplets_this_rank": int(synth.triplets_host(b["edge_index"], len(b["x"]))[0].shape[1]),
+           "sharding": "128 molecules per rank; every rank's batch has the N = 1 batch's triplet count to within 0.5 % "
+                       "(synth.qm9_shard), so molecules/s and triplets/s scale alike"}
     # ---- the same step with its dense part replayed as ONE CUDA graph (the eager step above is bound by the
     # host: ~800 launches from Python).  Every replayed step still runs the whole path: `prepare` (the integer
     # kernels building triplets + CSR metadata, eager, with their size read-backs) is inside the timed region,
@@ -366,6 +369,245 @@ def _train_step_graph(dev, world, rank, steps, data, y, nmine):
     return out
 
 
+# ---------------------------------------------------------------------------------- secondary legs (rank 0, N = 1)
+def _timed(fn, iters, warmup=3):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def reference_on_gpu_leg(dev, w, iters=5):
+    """SURVEY.md 8(d) last row: the reference's composite PyTorch path (the oracle port: gathers, scatter
+    softmax, elementwise passes, index_add -- ~35 launches forward, ~70 backward) on the SAME B200 and the same
+    tensors as the headline step.  A baseline leg: the checker runs beside the product, never inside it."""
+    import torch
+    from oracle import conv as oconv
+    D, H, S, R, A = (DIMS[k] for k in "DHSRA")
+    torch.manual_seed(0)
+    ref = oconv.OracleSBFTransformerConv(D, D // H, heads=H, sbf_dim=S, rbf_dim=R, edge_dim=A).to(dev)
+    t = {k: torch.from_numpy(w[k]).to(dev) for k in ("x", "rbf", "edge_attr", "sbf", "edge_index")}
+    for k in ("x", "rbf", "edge_attr"):
+        t[k].requires_grad_(True)
+    gout = torch.randn(w["E"], D, device=dev, generator=torch.Generator(dev).manual_seed(1))
+    params = list(ref.parameters())
+
+    def step():
+        out = ref(t["sbf"], t["rbf"], x=t["x"], edge_index=t["edge_index"], edge_attr=t["edge_attr"])
+        torch.autograd.grad(out, [t["x"], t["rbf"], t["edge_attr"]] + params, gout)
+    ms = _timed(step, iters, warmup=2)
+    return {"ms_per_step": ms, "value": w["T"] / (ms * 1e-3), "unit": UNIT,
+            "what": "composite PyTorch path of the reference (oracle port) on this GPU, same tensors, fp32"}
+
+
+def ocelot_inference_leg(dev, iters=5):
+    """BASELINE.json configs[2]: inference throughput on OCELOT-sized molecules -- here the real 60-146-atom
+    geometries the reference ships (raw/AID_kcal.xyz, numeric fixture tests/golden/aid_geometries.npz), batches
+    of 12, full harness model forward (radius graph is part of the dataset in the reference; triplets, bases
+    and the 4 conv layers run per batch)."""
+    import torch
+    from x2gnn_b200 import edge_graph, synth
+    from x2gnn_b200.xgnn_model import XGNNPoly
+    torch.manual_seed(0)
+    net = XGNNPoly(**HPARAMS).to(dev).eval()
+    out = []
+    for seg, name in ((False, "edge_attr [T,A] as in the reference"), (True, "segment-constant edge_attr table (opt-in)")):
+        net.segment_edge_attr = seg
+        mols = tot_ms = tot_T = 0
+        for b0 in (0, 12, 24):
+            ob = synth.aid_batch(range(b0, b0 + 12), seed=b0)
+            data = {k: (torch.from_numpy(v).to(dev) if hasattr(v, "shape") else v) for k, v in ob.items()}
+            with torch.no_grad():
+                tri = edge_graph.vertex_to_edge_2(data["edge_index"], data["x"].size(0))[0]
+                ms = _timed(lambda: net(data), iters, warmup=2)
+            mols += 12
+            tot_ms += ms
+            tot_T += int(tri.size(1))
+        out.append({"edge_attr": name, "molecules_per_sec": mols / (tot_ms * 1e-3),
+                    "edge_messages_per_sec_4_layers": 4 * tot_T / (tot_ms * 1e-3), "ms_per_batch_of_12": tot_ms / 3,
+                    "triplets_per_batch": tot_T // 3})
+    return {"geometries": "raw/AID_kcal.xyz molecules 0..35 (60-146 atoms), 3 batches of 12", "runs": out}
+
+
+def ball500_sweep_leg(dev, peak, iters=8):
+    """BASELINE.json configs[3]: conv-layer fwd+bwd on ball-packed 500-atom graphs (radius-cutoff edges, segments of
+    13-62 triplets), two sizes; HBM fraction in algorithmic bytes against the measured peak."""
+    import torch
+    from x2gnn_b200 import edge_graph, synth
+    from x2gnn_b200.sbftransformer_conv import SBFTransformerConv
+    D, H, S, R, A = (DIMS[k] for k in "DHSRA")
+    torch.manual_seed(0)
+    layer = SBFTransformerConv(D, D // H, heads=H, sbf_dim=S, rbf_dim=R, edge_dim=A).to(dev)
+    params = list(layer.parameters())
+    rows = []
+    for natoms, ngraphs in ((500, 1), (500, 4)):
+        b = synth.ball_batch(ngraphs, n_atoms=natoms, seed=0)
+        ei = torch.from_numpy(b["edge_index"]).to(dev)
+        tri = edge_graph.vertex_to_edge_2(ei, len(b["x"]))[0]
+        E, T = ei.size(1), tri.size(1)
+        g = torch.Generator(dev).manual_seed(1)
+        x = torch.randn(E, D, device=dev, generator=g).requires_grad_(True)
+        rbf = (torch.rand(E, R, device=dev, generator=g) * 2 - 1).requires_grad_(True)
+        sbf = torch.randn(T, S, device=dev, generator=g)
+        ea = torch.randn(T, A, device=dev, generator=g).requires_grad_(True)
+        gout = torch.randn(E, D, device=dev, generator=g)
+
+        def step():
+            out = layer(sbf, rbf, x=x, edge_index=tri, edge_attr=ea)
+            torch.autograd.grad(out, [x, rbf, ea] + params, gout)
+        ms = _timed(step, iters)
+        fb, bb = algorithmic_bytes(E, T, D, S, R, A)
+        rows.append({"atoms": natoms, "graphs": ngraphs, "E": int(E), "T": int(T), "ms_per_step": ms,
+                     "edge_messages_per_sec": T / (ms * 1e-3), "hbm_frac": (fb + bb) / (ms * 1e-3) / 1e9 / peak})
+        del x, rbf, sbf, ea, gout
+    return rows
+
+
+def e2e_from_atoms_leg(dev, world, rank, steps):
+    """The path the north star names, end to end from host memory: pinned host atoms (positions, atomic numbers,
+    molecule ids) and pair features edge_attr[E, 338] -> device -> radius graph -> triplets -> bases -> embeddings
+    -> 4 SBFTransformerConv layers (+ the model's LayerNorm / residual / readout blocks) forward, loss, backward
+    -> loss and predictions back on the host.  One training-style step of the harness model per batch of 128
+    molecules per GPU; ~60 MB cross PCIe per step instead of the 588 MB of the conv-boundary `e2e` (sbf[T,42]
+    and edge_attr[T,128] are produced on the device here, as in the real model).  Copies of step i+1 overlap
+    step i on a copy stream (two buffer sets)."""
+    import torch
+    import torch.distributed as dist
+    from x2gnn_b200 import atom_graph, synth
+    from x2gnn_b200.xgnn_model import XGNNPoly
+    b, _ = synth.qm9_shard(NMOL, world, rank, seed=0)
+    pin = {k: torch.from_numpy(b[k]).pin_memory() for k in ("atom_pos", "x", "batch", "edge_attr", "edge_num", "y")}
+    B = int(b["num_graphs"])
+    res = {}
+    for seg in (False, True):
+        torch.manual_seed(0)
+        net = XGNNPoly(**HPARAMS).to(dev)
+        net.segment_edge_attr = seg
+        bufs = [{k: torch.empty_like(v, device=dev) for k, v in pin.items()} for _ in range(2)]
+        h_pred, h_loss = torch.empty(B).pin_memory(), torch.empty(()).pin_memory()
+        copy_stream = torch.cuda.Stream(device=dev)
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        cnt = [0]
+        stat = {}
+
+        def stage(slot):
+            with torch.cuda.stream(copy_stream), torch.no_grad():
+                copy_stream.wait_event(consumed[slot])
+                for k in pin:
+                    bufs[slot][k].copy_(pin[k], non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        def step():
+            i = cnt[0]
+            cnt[0] += 1
+            slot = i & 1
+            stage(slot ^ 1)
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ready[slot])
+            t = bufs[slot]
+            ei, _ = atom_graph.radius_graph(t["atom_pos"], t["batch"], 5.0)        # atom_graph.py:32-45 on the device
+            data = {"x": t["x"], "atom_pos": t["atom_pos"], "edge_index": ei, "edge_attr": t["edge_attr"],
+                    "edge_num": t["edge_num"], "batch": t["batch"], "num_graphs": B}
+            net.zero_grad(set_to_none=True)
+            pred = net(data)
+            loss = torch.nn.functional.smooth_l1_loss(pred, t["y"])
+            loss.backward()
+            consumed[slot].record(cur)
+            h_pred.copy_(pred.detach(), non_blocking=True)
+            h_loss.copy_(loss.detach(), non_blocking=True)
+            cur.synchronize()
+            stat["E"] = int(ei.size(1))
+
+        for ev in consumed:
+            ev.record()
+        stage(0)
+        for _ in range(3):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        T = int(synth.triplets_host(b["edge_index"], len(b["x"]))[0].shape[1])
+        tt = torch.tensor([ms, float(T)], device=dev, dtype=torch.float64)
+        if world > 1:
+            mx = tt.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            ms, T_all = float(mx[0]), float(tt[1])
+        else:
+            T_all = float(T)
+        key = "segment_constant_edge_attr_table" if seg else "edge_attr_TA_as_in_the_reference"
+        res[key] = {"ms_per_step": ms, "molecules_per_sec": world * NMOL / (ms * 1e-3),
+                    "edge_messages_per_sec_4_layers": HPARAMS["conv_layers"] * T_all / (ms * 1e-3),
+                    "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in pin.values()),
+                    "d2h_bytes_per_step": h_pred.numel() * 4 + 4}
+        del net, bufs
+    res["what"] = ("pinned host atoms + pair features -> device -> radius graph -> triplets -> bases -> 4 conv layers "
+                   "(full harness model) forward + loss + backward -> predictions and loss on the host, per step")
+    res["value"] = res["edge_attr_TA_as_in_the_reference"]["edge_messages_per_sec_4_layers"]
+    res["unit"] = UNIT
+    return res
+
+
+def dp_gradient_check(dev, world, rank, layer, params):
+    """SURVEY.md 4 item 5 on the hardware: every rank's shard gradients, all-reduced (sum), against the SAME global
+    batch run unsharded on rank 0 (every rank can regenerate every shard: the shards are seeded).  Returns the
+    largest relative error over the parameter tensors (max |a - b| / max |b|)."""
+    import torch
+    import torch.distributed as dist
+    D = DIMS["D"]
+
+    def grads_of(w, seed):
+        t = {k: torch.from_numpy(w[k]).to(dev) for k in ("x", "rbf", "edge_attr", "sbf", "edge_index")}
+        gout = torch.randn(w["E"], D, device=dev, generator=torch.Generator(dev).manual_seed(100 + seed))
+        out = layer(t["sbf"], t["rbf"], x=t["x"], edge_index=t["edge_index"], edge_attr=t["edge_attr"])
+        return torch.autograd.grad(out, params, gout), t, gout
+
+    g_mine, _, _ = grads_of(host_workload(rank, world), rank)
+    flat = torch.cat([g.reshape(-1) for g in g_mine])
+    dist.all_reduce(flat)
+    err = None
+    if rank == 0:
+        ws = [host_workload(r, world) for r in range(world)]
+        import numpy as np
+        eoff = np.cumsum([0] + [w["E"] for w in ws])
+        cat = {k: np.concatenate([w[k] for w in ws], axis=0) for k in ("x", "rbf", "edge_attr", "sbf")}
+        cat["edge_index"] = np.concatenate([w["edge_index"] + eoff[r] for r, w in enumerate(ws)], axis=1)
+        t = {k: torch.from_numpy(v).to(dev) for k, v in cat.items()}
+        gout = torch.cat([torch.randn(w["E"], D, device=dev, generator=torch.Generator(dev).manual_seed(100 + r))
+                          for r, w in enumerate(ws)])
+        out = layer(t["sbf"], t["rbf"], x=t["x"], edge_index=t["edge_index"], edge_attr=t["edge_attr"])
+        g_all = torch.autograd.grad(out, params, gout)
+        err, off = 0.0, 0
+        for g in g_all:
+            n = g.numel()
+            a, bref = flat[off:off + n].double(), g.reshape(-1).double()
+            off += n
+            scale = float(bref.abs().max())
+            if scale > 1e-12:
+                err = max(err, float((a - bref).abs().max()) / scale)
+        del t, gout, out, g_all
+    dist.barrier()
+    torch.cuda.empty_cache()
+    return err
+
+
 # ---------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -413,6 +655,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ------------------------------------------------ N > 1: sharded gradient == unsharded gradient, on the hardware
+    dp_err = None
+    if world > 1 and not args.layer_only:
+        dp_err = dp_gradient_check(dev, world, rank, layer, params)
+        if rank == 0 and not (dp_err <= 1e-5):
+            raise SystemExit(f"bench.py: all-reduced shard gradients differ from the unsharded global batch: {dp_err}")
+
     # ------------------------------------------------ resident-input throughput (`value`)
     for _ in range(warmup):
         step()
@@ -454,7 +703,7 @@ def run_ours(args):
     # (SURVEY.md §8f row 1).  Same layer, same graph; edge_attr is a per-atom table [N, A] indexed by the
     # central atom of the target bond instead of a [T, A] stream.  Reported beside the headline, never as it.
     seg = None
-    if world == 1:
+    if world == 1 and not args.layer_only:
         N = w["N"]
         tab = torch.randn(N, A, device=dev, generator=torch.Generator(dev).manual_seed(2)).requires_grad_(True)
         idx = torch.from_numpy(w["center"]).to(dev)
@@ -485,6 +734,15 @@ def run_ours(args):
         seg = {"value": T / (seg_ms * 1e-3), "unit": UNIT, "ms_per_step": seg_ms,
                "edge_attr": f"table [{N}, {A}] + edge_attr_index [{E}] (central atom of the target bond)",
                "algorithmic_bytes_per_step": seg_bytes, "phase_ms_per_step": seg_phases}
+
+    if args.layer_only:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+                              "ms_per_step": ms_per_step, "mode": args.mode, "layer_only": True,
+                              "gpu_launches_per_step": int(launches), "config": {"E": E, "T": T}}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ------------------------------------------------ end to end through the module call (`e2e`)
     # Every step copies ITS inputs host -> device and its results device -> host.  Like a training
@@ -554,6 +812,12 @@ def run_ours(args):
         e_ms = float(t[0])
     e2e_value = total_T / (e_ms / e2e_steps * 1e-3)
 
+    # ------------------------------------------------ end to end from atoms (the path the north star names), all ranks
+    try:
+        from_atoms = e2e_from_atoms_leg(dev, world, rank, max(3, min(steps, 10)))
+    except Exception as exc:
+        from_atoms = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+
     # ------------------------------------------------ full training step (molecules/s), all ranks
     train = None
     if not args.no_train_step:
@@ -580,14 +844,23 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = (fwd_b + bwd_b) / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
-    # DRAM traffic of the same step from the committed ncu capture (only valid for the same workload / mode)
+    # DRAM traffic of the same step: ncu launch list of THIS library build (tools/step_traffic.py writes the file
+    # with the digest of the sources the .so was built from; a file of another build is refused, not reused)
     traffic, traffic_src, phase_rates = None, None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_step_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_step_traffic.json")
+    dpath = os.path.join(ROOT, "x2-gnn_b200", "lib", "libx2gnn.sha256")
+    lib_digest = open(dpath).read().strip() if os.path.exists(dpath) else None
     if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        if tj.get("E") == E and tj.get("T") == T and tj.get("mode") == args.mode:
+        tj = json.load(open(tpath)).get(args.mode)
+        if not tj:
+            traffic_src = f"no ncu capture for mode {args.mode} in profiles/r2_step_traffic.json"
+        elif tj.get("lib_sha256") != lib_digest:
+            traffic_src = ("stale: profiles/r2_step_traffic.json was captured with another build of libx2gnn.so "
+                           "(re-run tools/step_traffic.py)")
+        elif tj.get("E") != E or tj.get("T") != T:
+            traffic_src = "profiles/r2_step_traffic.json is for another workload"
+        else:
             traffic, traffic_src = tj["dram_bytes_per_step"], tj["source"]
-            # per phase: DRAM bytes of the committed ncu launch list / event time measured in THIS run
             if "phase_dram_MB" in tj:
                 phase_rates = {k: {"dram_MB": round(mb, 1), "ms": phase_ms[k],
                                    "dram_GBs": round(mb / phase_ms[k], 1) if phase_ms.get(k) else None,
@@ -612,6 +885,20 @@ def run_ours(args):
                "sample": f"full seed-0 batch (E={E}, T={T}), 1 warm-up + 3 timed fwd+bwd steps, "
                          f"oracle port of the reference's composite PyTorch path, fp32"}
 
+    extra = {}
+    if world == 1:
+        for key, fn in (("reference_on_gpu", lambda: reference_on_gpu_leg(dev, w)),
+                        ("ocelot_inference", lambda: ocelot_inference_leg(dev)),
+                        ("ball500_sweep", lambda: ball500_sweep_leg(dev, peak))):
+            try:
+                torch.cuda.empty_cache()
+                extra[key] = fn()
+            except Exception as exc:
+                extra[key] = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+        if isinstance(extra.get("reference_on_gpu"), dict) and "ms_per_step" in extra["reference_on_gpu"]:
+            extra["reference_on_gpu"]["x2gnn_b200_ms_per_step"] = ms_per_step
+            extra["reference_on_gpu"]["speedup"] = extra["reference_on_gpu"]["ms_per_step"] / ms_per_step
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -620,8 +907,8 @@ def run_ours(args):
                    "molecules_per_gpu": NMOL, "E": E, "T": T, "precision_mode": ("fp32 SIMT (1e-5 parity)" if args.mode == "fp32" else
                                       "REDUCED PRECISION: one tf32 pass in the Linear layers (2e-2 class)" if args.mode == "tf32" else
                                       "fp32 I/O, Linear layers on tcgen05 in 3xTF32 split precision (1e-5 parity)"),
-                   "parallelism": f"dp{world} (global batch of {NMOL} x {world} molecules, whole molecules dealt to ranks "
-                                  f"balanced by triplet count; NCCL all-reduce of the flat parameter gradient)",
+                   "parallelism": f"dp{world} ({NMOL} whole molecules per rank, every rank's batch within 0.5 % of the "
+                                  f"N = 1 batch's triplet count; NCCL all-reduce of the flat parameter gradient)",
                    "l2": f"no flush: per-step T-row inputs {680 * T / 1e6:.0f} MB > 126 MB L2"},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -630,6 +917,10 @@ def run_ours(args):
         "clocks": clocks.summary(),
         "train_step": train,
         "segment_constant_edge_attr": seg,
+        "e2e_from_atoms": from_atoms,
+        "dp_grad_max_rel_err": dp_err,
+        "triplets_per_sec": value,
+        **extra,
     }
     if seg is not None:
         seg["roofline_frac"] = seg["algorithmic_bytes_per_step"] / (seg["ms_per_step"] * 1e-3) / 1e9 / peak
@@ -646,6 +937,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-step", action="store_true", help="skip the secondary molecules/s measurement")
+    ap.add_argument("--layer-only", action="store_true",
+                    help="only the headline layer step (for ncu launch lists: tools/step_traffic.py)")
     ap.add_argument("--mode", default="tf32x3", choices=["fp32", "tf32x3", "tf32x3_fused", "tf32"],
                     help="fp32: SIMT GEMMs; tf32x3: tcgen05 3xTF32 GEMMs (both meet the 1e-5 parity bar); "
                          "tf32: one tf32 pass (reduced precision, 2e-2 class -- never the headline)")

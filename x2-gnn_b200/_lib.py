@@ -107,8 +107,36 @@ class X2Error(RuntimeError):
     pass
 
 
+_tls = threading.local()      # .dev: index of the device of the tensors of the call in progress (require_cuda)
+
+
+class _DeviceBound:
+    """The library launches on the calling thread's CURRENT device and the stream it is handed.  Every
+    entry point that takes a stream is wrapped so that it runs with the device of the call's tensors
+    current (`require_cuda` records it; `stream()` returns that device's current stream): a model on cuda:1
+    works while cuda:0 is the process's current device.  Entering the guard is a no-op when the device is
+    already current (the one-process-per-GPU case)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def __getattr__(self, name):
+        fn = getattr(self._h, name)
+        if SIGNATURES.get(name, (None, []))[1][-1:] != [_P] or name in ("x2_timing_read",):
+            wrapped = fn                                    # no stream argument: nothing is launched
+        else:
+            def wrapped(*args, _fn=fn):
+                dev = getattr(_tls, "dev", None)
+                if dev is None or dev == torch.cuda.current_device():
+                    return _fn(*args)
+                with torch.cuda.device(dev):
+                    return _fn(*args)
+        setattr(self, name, wrapped)
+        return wrapped
+
+
 def lib():
-    """Load (once) and return the ctypes handle.  Raises if the library is absent."""
+    """Load (once) and return the library handle.  Raises if the library is absent."""
     global _lib
     if _lib is not None:
         return _lib
@@ -123,7 +151,7 @@ def lib():
                 fn = getattr(h, name)      # AttributeError => header/library mismatch
                 fn.restype = res
                 fn.argtypes = args
-            _lib = h
+            _lib = _DeviceBound(h)
     return _lib
 
 
@@ -149,6 +177,7 @@ def require_cuda(*tensors, what: str):
     if dev is None:
         raise X2Error(f"{what}: no tensors given")
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    _tls.dev = idx
     if idx not in _checked_devices:
         check(lib().x2_device_check(idx), "x2_device_check")
         _checked_devices.add(idx)
@@ -168,7 +197,9 @@ def ptr(t):
 
 
 def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """Current stream of the device of the call in progress (see _DeviceBound)."""
+    dev = getattr(_tls, "dev", None)
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
 NUM_PHASES = 8

@@ -29,6 +29,15 @@ def shard_graphs(costs: Sequence[int], world: int) -> List[List[int]]:
     return [sorted(p) for p in parts]
 
 
+def global_mean_scale(n_local: int, n_global: int, world: int) -> float:
+    """Factor for a rank's MEAN loss so that `FlatGradBucket.allreduce(average=True)` yields the gradient of
+    the mean over the GLOBAL batch: ranks hold different numbers of molecules when shards are balanced by
+    triplets, and a mean of per-rank means is not the global mean.  (1/W) sum_r s_r grad(mean_r) with
+    s_r = n_r W / N equals grad of (1/N) sum over all molecules -- the single-GPU step of trainer.py:41-42 on
+    the same global batch."""
+    return float(n_local) * float(world) / float(n_global)
+
+
 class FlatGradBucket:
     """All parameter gradients packed into one contiguous fp32 buffer, so that a training step
     issues a single all-reduce (4.64 MB at config.json dims)."""

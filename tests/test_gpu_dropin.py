@@ -67,10 +67,10 @@ def test_unmodified_reference_callers_forward_backward_checkpoint(reference_xgnn
     hp = dict(conv_layers=4, sbf_dim=7, rbf_dim=6, in_channels=128, heads=16, embedding_size=128)   # config.json
     torch.manual_seed(0)
     oracle = omodel.XGNNPoly(**hp)
-    net = xgnn.xgnn_poly(**hp)               # the reference's own class, unchanged
+    net = xgnn.xgnn_poly(**hp, device="cuda")    # the reference's own class, built as train_ema.py:42 builds it
     assert list(net.state_dict().keys()) == list(oracle.state_dict().keys())
     net.load_state_dict(oracle.state_dict())
-    net = net.cuda()
+    net = net.to("cuda")
     # every conv layer is the drop-in, and it took the tensor-core path
     from x2gnn_b200.sbftransformer_conv import SBFTransformerConv
     assert all(isinstance(c, SBFTransformerConv) for c in net.fin_model.convs)
@@ -108,7 +108,9 @@ def test_unmodified_reference_callers_forward_backward_checkpoint(reference_xgnn
     torch.save({"model": net.state_dict(), "optimizer": opt.state_dict(), "epoch": 101}, buf)
     buf.seek(0)
     ckpt = torch.load(buf, map_location="cuda")
-    fresh = xgnn.xgnn_poly(**hp).cuda()
+    fresh = xgnn.xgnn_poly(**hp, device="cuda").to("cuda")
     fresh.load_state_dict(ckpt["model"])
     with torch.no_grad():
-        assert torch.equal(fresh(data), net(data))
+        # (not bitwise: the callers' own scatter_add -- torch index_add_ in compat/, atomics in torch_scatter -- sums
+        # in a run-dependent order; the drop-in modules themselves are deterministic, tests/test_gpu_conv.py)
+        assert torch.allclose(fresh(data), net(data), rtol=1e-6, atol=0)

@@ -595,12 +595,13 @@ def dp_gradient_check(dev, world, rank, layer, params):
         out = layer(t["sbf"], t["rbf"], x=t["x"], edge_index=t["edge_index"], edge_attr=t["edge_attr"])
         g_all = torch.autograd.grad(out, params, gout)
         err, off = 0.0, 0
+        top = max(float(g.abs().max()) for g in g_all)
         for g in g_all:
             n = g.numel()
             a, bref = flat[off:off + n].double(), g.reshape(-1).double()
             off += n
             scale = float(bref.abs().max())
-            if scale > 1e-12:
+            if scale > 1e-6 * top:        # lin_key.bias: its gradient is identically zero (App. A), only rounding noise
                 err = max(err, float((a - bref).abs().max()) / scale)
         del t, gout, out, g_all
     dist.barrier()

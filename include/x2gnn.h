@@ -127,6 +127,21 @@ size_t x2_items_workspace_bytes(int64_t E);
 int x2_items_build(const int32_t* rowptr_tgt, int64_t E, int64_t T, int32_t* itemptr, int32_t* items, void* ws,
                    size_t ws_bytes, void* stream);
 
+/* Closed blocks of a target-sorted line graph (csrc/blk_attn.cuh; SURVEY.md section 7 "structural facts": for
+ * the line graph built by edge_graph.py:12-30 a block is "the bonds leaving atom j" with the bonds entering j
+ * as its targets).  A block is a contiguous range of line-nodes [blk_sptr[b], blk_sptr[b+1]) such that every
+ * target segment draws all of its sources from one block; blk_tptr[b] .. blk_tptr[b+1] indexes blk_tord, the
+ * target ids of block b in ascending order.  Every line-node is the source side of exactly one block and the
+ * target side of exactly one block.  Nothing is assumed about edge_index beyond target-sortedness: the
+ * closure is VERIFIED, flags[0] = 1 iff it holds (otherwise the block kernels must not be used).
+ * flags int32 [6]: ok, number of blocks, most triplets in a block, most sources in a block, most targets in a
+ * block, 0.  blk_sptr / blk_tptr: int32 [E + 1]; blk_tord: int32 [E]; blk_tpos: int32 [E], position of a target
+ * inside its block (blk_tord[blk_tptr[b] + blk_tpos[e]] == e).  ws >= x2_blocks_workspace_bytes(T, E). */
+size_t x2_blocks_workspace_bytes(int64_t T, int64_t E);
+int x2_blocks_build(const int32_t* src, const int32_t* tgt, const int32_t* rowptr_tgt, int64_t T, int64_t E,
+                    int32_t* blk_sptr, int32_t* blk_tptr, int32_t* blk_tord, int32_t* blk_tpos, int32_t* flags,
+                    void* ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------- basis expansions
  * envelop.py:16-21: out = 1/x + a x^(p-1) + b x^p + c x^(p+1), x = d * inv_cutoff. */
 int x2_envelope_fwd(const float* d, int64_t n, float inv_cutoff, int32_t p, float a, float b,
@@ -208,6 +223,23 @@ typedef struct {
   const int32_t* items;
   const int32_t* itemptr;
   int64_t items_bound;   /* capacity of `items` in entries (>= number of items + 1): sizes the partial-state scratch */
+  /* Optional closed blocks of the line graph (x2_blocks_build with flags[0] == 1); nblk == 0 => generic kernels.
+   * With them (tgt_sorted, D == 128, no dropout) the backward runs its by-target and by-source passes in ONE
+   * kernel, one CTA per block (csrc/blk_attn.cuh). */
+  int64_t nblk;
+  int32_t blk_max_src;   /* most sources in a block (flags[3]) */
+  int32_t sbf_L, sbf_R;  /* factorised sbf: num_spherical, num_radial (S == sbf_L * sbf_R) */
+  int32_t blk_max_trip;  /* most triplets in a block (flags[2]) */
+  int32_t blk_max_tgt;   /* most targets in a block (flags[4]) */
+  int32_t pad0_;
+  const int32_t *blk_sptr, *blk_tptr, *blk_tord, *blk_tpos;
+  /* Optional factorised form of sbf (angular_basis_layer.py:80-93):
+   * sbf[t, l R + n] == sbf_tab[src(t), l R + n] * Y_l0(angles[t]) with sbf_tab [E, S] the per-bond radial
+   * table (x2_sbf_table) and angles [T] -- what x2_sbf_fwd multiplies out.  When both are given together
+   * with the blocks (and sbf_L <= 8, sbf_R <= 8, grads.dsbf == NULL), lin_sbf is evaluated inside the
+   * attention kernels from a per-source table built in shared memory: `sbf` is not read, saved.sg is not
+   * written (both may be NULL) and d(lin_sbf out) never exists. */
+  const float *sbf_tab, *angles;
 } x2_conv_desc;
 
 #define X2_MODE_FP32 0    /* fp32 SIMT arithmetic everywhere (1e-5 parity) */
@@ -231,7 +263,7 @@ typedef struct {
   float* attn;   /* [E, D]   attention output before the skip add */
   float* lse;    /* [E, H]   log-sum-exp of the logits per (target, head) */
   float* ea;     /* [T, D]   lin_edge(edge_attr)  (NULL if A == 0) */
-  float* sg;     /* [T, D]   lin_sbf(sbf) */
+  float* sg;     /* [T, D]   lin_sbf(sbf)  (NULL allowed with the factorised sbf of x2_conv_desc) */
   float* xs;     /* [E, D]   x * lin_rbf(rbf), the filtered source features (sbftransformer_conv.py:100); optional:
                     NULL => fwd keeps it in its workspace and bwd recomputes it (one more E-scale kernel) */
 } x2_conv_saved;
@@ -244,6 +276,12 @@ typedef struct {
   float *dw_skip, *db_skip;    /* used iff fuse_skip (db_skip may be NULL) */
 } x2_conv_grads;
 
+/* Which optional paths a descriptor selects (bit set): X2_PLAN_BLOCKS = the backward runs the block-centric
+ * kernel; X2_PLAN_FACTORISED_SBF = lin_sbf is evaluated from sbf_tab / angles inside the attention kernels
+ * (forward without alpha output and backward), so saved.sg is not needed.  The caller sizes its buffers by it. */
+#define X2_PLAN_BLOCKS 1
+#define X2_PLAN_FACTORISED_SBF 2
+int x2_sbfconv_plan(const x2_conv_desc* d);
 size_t x2_sbfconv_fwd_workspace_bytes(const x2_conv_desc* d);
 size_t x2_sbfconv_bwd_workspace_bytes(const x2_conv_desc* d);
 /* out[E,D]; alpha[T,H] optional (return_attention_weights), NULL otherwise. */

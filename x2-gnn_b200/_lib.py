@@ -41,6 +41,10 @@ class ConvDesc(C.Structure):
         ("w_skip", c_f32p), ("b_skip", c_f32p),
         ("ea_rows", C.c_int64), ("ea_index", c_i32p), ("ea_rowptr", c_i32p), ("ea_order", c_i32p),
         ("items", c_i32p), ("itemptr", c_i32p), ("items_bound", C.c_int64),
+        ("nblk", C.c_int64), ("blk_max_src", C.c_int32), ("sbf_L", C.c_int32), ("sbf_R", C.c_int32),
+        ("blk_max_trip", C.c_int32), ("blk_max_tgt", C.c_int32), ("pad0_", C.c_int32),
+        ("blk_sptr", c_i32p), ("blk_tptr", c_i32p), ("blk_tord", c_i32p), ("blk_tpos", c_i32p),
+        ("sbf_tab", c_f32p), ("angles", c_f32p),
     ]
 
 
@@ -79,6 +83,8 @@ SIGNATURES = {
     "x2_items_bound": (C.c_int64, [_I64, _I64]),
     "x2_items_workspace_bytes": (_SZ, [_I64]),
     "x2_items_build": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _SZ, _P]),
+    "x2_blocks_workspace_bytes": (_SZ, [_I64, _I64]),
+    "x2_blocks_build": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "x2_envelope_fwd": (C.c_int, [_P, _I64, _F, _I32, _F, _F, _F, _P, _P]),
     "x2_radial_fwd": (C.c_int, [_P, _P, _P, _I64, _I32, _F, _P, _P]),
     "x2_radial_bwd_workspace_bytes": (_SZ, [_I64, _I32]),
@@ -90,6 +96,7 @@ SIGNATURES = {
     "x2_tc_gemm": (C.c_int, [_P, _I64, _I64, _I32, _P, _I64, _I64, _I32, _P, _P, _I64, _I32, _P, _SZ, _P]),
     "x2_tc_wgrad_workspace_bytes": (_SZ, [_I64, _I32]),
     "x2_tc_wgrad": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _P, _I64, _P, _P, _SZ, _P]),
+    "x2_sbfconv_plan": (C.c_int, [C.POINTER(ConvDesc)]),
     "x2_sbfconv_fwd_workspace_bytes": (_SZ, [C.POINTER(ConvDesc)]),
     "x2_sbfconv_bwd_workspace_bytes": (_SZ, [C.POINTER(ConvDesc)]),
     "x2_sbfconv_fwd": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(ConvSaved), _P, _P, _P, _SZ, _P]),

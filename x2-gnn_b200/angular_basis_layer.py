@@ -57,6 +57,33 @@ def _device_tables(L, R, device):
     return _table_cache[key]
 
 
+class SbfFactors:
+    """What F_B_2D.forward multiplied out: sbf[t, l R + n] = table[idx[t], l R + n] * Y_l0(angles[t]).
+    Attached to the returned tensor as `_x2_factors`; SBFTransformerConv uses it to evaluate lin_sbf(sbf)
+    inside its attention kernels instead of streaming the [T, L R] tensor (the tensor itself is still a
+    plain, fully materialised torch.Tensor for every other consumer).  X2GNN_SGF=0 disables the shortcut."""
+    __slots__ = ("table", "angles", "idx", "L", "R", "version", "_checked")
+
+    def __init__(self, table, angles, idx, L, R, version):
+        self.table, self.angles, self.idx, self.L, self.R, self.version = table, angles, idx, L, R, version
+        self._checked = {}
+
+    def describes(self, sbf: torch.Tensor, edge_index: torch.Tensor) -> bool:
+        """True iff `sbf` is unmodified since F_B_2D produced it and idx == edge_index[0] (the source
+        line-node of every triplet, xgnn.py:66)."""
+        if sbf._version != self.version or edge_index.dim() != 2 or edge_index.size(1) != self.idx.numel():
+            return False
+        if edge_index.device != self.idx.device:
+            return False
+        if (self.idx.data_ptr() == edge_index.data_ptr() and edge_index.stride(1) == 1 and self.idx.stride(0) == 1
+                and self.idx.dtype == edge_index.dtype):
+            return True                       # idx IS row 0 of edge_index (a view): xgnn.py:66
+        key = (id(edge_index), edge_index._version)
+        if key not in self._checked:          # one comparison (and host sync) per (sbf, edge_index) pair
+            self._checked = {key: bool(torch.equal(self.idx.long(), edge_index[0].long()))}
+        return self._checked[key]
+
+
 class F_B_2D(nn.Module):
     def __init__(self, num_spherical, num_radial, cutoff, envelope_exponent=5):
         super().__init__()
@@ -97,4 +124,5 @@ class F_B_2D(nn.Module):
         out = torch.empty((T, L * R), dtype=torch.float32, device=dev)
         _lib.check(_lib.lib().x2_sbf_fwd(_lib.ptr(table), _lib.ptr(ang), _lib.ptr(idx), T, E, L, R,
                                          _lib.ptr(out), _lib.stream()), "x2_sbf_fwd")
+        out._x2_factors = SbfFactors(table, ang, edge_index_1, L, R, out._version)
         return out

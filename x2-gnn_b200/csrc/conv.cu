@@ -667,6 +667,10 @@ k_attn_bwd_src(const float* __restrict__ qkvs, int ldq, const float* __restrict_
   stv<VEC>(dqkv + f * ldg + 2 * D + ch, dv);
 }
 
+}  // namespace x2
+#include "blk_attn.cuh"      // block-centric kernels (one CTA per closed block of the line graph)
+namespace x2 {
+
 // ------------------------------------------------------------------ Linear dispatch (SIMT / tensor core)
 static inline int lin_mode(int mode) {
   return (mode == X2_MODE_TF32X3_FUSED || mode == X2_MODE_TF32) ? X2_MODE_TF32X3 : mode;
@@ -752,17 +756,47 @@ static int check_desc(const x2_conv_desc* d) {
   return X2_OK;
 }
 
-struct FwdWs { float* xs; void* img; float* part; };
+struct FwdWs { float* xs; void* img; float* part; float* wsT; };
 static size_t fwd_layout(const x2_conv_desc* d, void* ws, FwdWs* w) {
   Arena a(ws, (size_t)-1);
   w->xs = a.take<float>((size_t)d->E * d->D + 4);
   w->img = a.take<char>(tc::bimage_bytes(kTcBlock, kTcBlock) + 256);
   w->part = a.take<float>(d->items ? (size_t)d->items_bound * tc::kTaPart : 4);   // partial states of the fused forward
+  w->wsT = a.take<float>((size_t)d->S * d->D + 4);                                 // lin_sbf.weight^T (factorised sbf)
   return align_up(a.off, 256) + 256;
 }
 
+// ---- block-centric kernels (csrc/blk_attn.cuh): when they apply
+static bool env_on(const char* name) {       // default on; NAME=0 turns the path off (A/B runs)
+  const char* v = getenv(name);
+  return !(v && v[0] == '0');
+}
+static bool blk_usable(const x2_conv_desc* d) {
+  static const bool on = env_on("X2GNN_BLOCK");
+  return on && d->nblk > 0 && d->blk_sptr && d->blk_tptr && d->blk_tord && d->tgt_sorted && d->T > 0 && d->D == 128 &&
+         d->dropout_p == 0.f && (d->A == 0 || d->A > 0);
+}
+// With a DENSE Sg tensor the one-kernel backward is slower than the two generic kernels (0.58 vs 0.47 ms on the
+// bench batch: profiles/r2_notes.md), so it is opt-in there (X2GNN_BLOCK_DENSE=1); the factorised path always uses it.
+static bool blk_dense_enabled() {
+  static const bool on = [] { const char* v = getenv("X2GNN_BLOCK_DENSE"); return v && v[0] == '1'; }();
+  return on;
+}
+constexpr int kDwsParts = 2 * kNumSM;
+constexpr size_t kBlkSmemMax = 220 * 1024;    // per-source basis tables of a block (factorised sbf)
+// rows per source of the staged table: the config's 7 orders exactly, anything else padded to 8 with zero rows
+static int blk_lt(const x2_conv_desc* d) { return d->sbf_L == 7 ? 7 : kBlkLMax; }
+static size_t blk_smem_bytes(const x2_conv_desc* d) { return (size_t)d->blk_max_src * blk_lt(d) * 128 * sizeof(float); }
+// factorised lin_sbf: blocks + the factors of sbf, L <= 8 orders of <= 8 radial functions, the block's table fits smem
+static bool sgf_usable(const x2_conv_desc* d) {
+  static const bool on = env_on("X2GNN_SGF");
+  return on && blk_usable(d) && d->sbf_tab && d->angles && d->sbf_L >= 1 && d->sbf_L <= kBlkLMax && d->sbf_R >= 1 &&
+         d->sbf_R <= kBlkRMax && d->sbf_L * d->sbf_R == d->S && d->blk_max_src > 0 && blk_smem_bytes(d) <= kBlkSmemMax &&
+         (reinterpret_cast<uintptr_t>(d->b_sbf) & 15) == 0;
+}
+
 struct BwdWs {
-  float *dea, *dea_tab, *dsg, *al, *da, *dqkv, *xs, *F, *dxs, *dxs2, *dx2, *wg;
+  float *dea, *dea_tab, *dsg, *al, *da, *dqkv, *xs, *F, *dxs, *dxs2, *dx2, *wg, *wsT, *dP;
   void* img;
   size_t wg_floats;
 };
@@ -772,7 +806,10 @@ static size_t bwd_layout(const x2_conv_desc* d, void* ws, BwdWs* w) {
   // segment-constant edge_attr: one d(lin_edge out) row per target + one per table row
   w->dea = d->A > 0 ? a.take<float>((d->ea_index ? ED : TD) + 4) : nullptr;
   w->dea_tab = d->ea_index ? a.take<float>((size_t)d->ea_rows * d->D + 4) : nullptr;
-  w->dsg = a.take<float>(TD + 4);
+  const bool sgf = sgf_usable(d);
+  w->dsg = a.take<float>(sgf ? 4 : TD + 4);
+  w->wsT = a.take<float>((size_t)d->S * d->D + 4);
+  w->dP = a.take<float>(sgf ? (size_t)d->E * d->sbf_L * d->D + 4 : 4);      // d(per-source basis table)
   w->al = a.take<float>(TH + 4);
   w->da = a.take<float>(TH + 4);
   w->dqkv = a.take<float>(3 * ED + 4);
@@ -789,6 +826,8 @@ static size_t bwd_layout(const x2_conv_desc* d, void* ws, BwdWs* w) {
   t2 = wgrad_workspace_floats(d->E, d->D, d->R);
   if (t2 > wg) wg = t2;
   t2 = tc::tc_wgrad_workspace_floats(d->T > d->E ? d->T : d->E, kTcBlock);
+  if (t2 > wg) wg = t2;
+  t2 = (size_t)kDwsParts * ((size_t)d->D * d->S + d->D) + 64;
   if (t2 > wg) wg = t2;
   w->wg_floats = wg;
   w->wg = a.take<float>(wg);
@@ -957,6 +996,62 @@ static int launch_attn_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const 
   return X2_OK;
 }
 
+// ---- block-centric launches
+static void blk_fill(const x2_conv_desc* d, const x2_conv_saved* s, BlkParams& p, const float* wsT) {
+  p.qkvs = s->qkvs; p.ldq = 4 * d->D;
+  p.ea = s->ea; p.ea_index = d->ea_index;
+  p.sg = s->sg;
+  p.stab = d->sbf_tab; p.angles = d->angles; p.wsT = wsT; p.b_sbf = d->b_sbf;
+  p.L = d->sbf_L; p.Rr = d->sbf_R; p.S = d->S;
+  p.src = d->src; p.tgt = d->tgt; p.rowptr_tgt = d->rowptr_tgt; p.rowptr_src = d->rowptr_src; p.order_src = d->order_src;
+  p.blk_sptr = d->blk_sptr; p.blk_tptr = d->blk_tptr; p.blk_tord = d->blk_tord;
+  p.E = d->E; p.H = d->H; p.C = d->C; p.scale = 1.0f / sqrtf((float)d->C);
+  p.fuse_skip = d->fuse_skip;
+}
+template <bool SGF, int LPH, int LT>
+static int launch_blk_fwd_t(const x2_conv_desc* d, const BlkParams& p, cudaStream_t st) {
+  const int ea = d->A == 0 ? kEaNone : (d->ea_index ? kEaSegment : kEaTriplet);
+  const size_t smem = SGF ? blk_smem_bytes(d) : 0;
+  auto go = [&](auto kern) -> int {
+    if (SGF) X2_DYN_SMEM(kern, kBlkSmemMax);      // once per (kernel, device): the largest table the path takes
+    launch_k(kern, dim3((unsigned)d->nblk), dim3(kBlkThreads), smem, st, p);
+    X2_LAUNCH_OK();
+    return X2_OK;
+  };
+  switch (ea) {
+    case kEaNone: return go(k_blk_fwd<kEaNone, SGF, LPH, LT>);
+    case kEaTriplet: return go(k_blk_fwd<kEaTriplet, SGF, LPH, LT>);
+    default: return go(k_blk_fwd<kEaSegment, SGF, LPH, LT>);
+  }
+}
+template <bool SGF, int LPH, int LT>
+static int launch_blk_bwd_t(const x2_conv_desc* d, const BlkParams& p, cudaStream_t st) {
+  const int ea = d->A == 0 ? kEaNone : (d->ea_index ? kEaSegment : kEaTriplet);
+  const size_t smem = SGF ? blk_smem_bytes(d) : 0;
+  auto go = [&](auto kern) -> int {
+    if (SGF) X2_DYN_SMEM(kern, kBlkSmemMax);
+    launch_k(kern, dim3((unsigned)d->nblk), dim3(kBlkThreads), smem, st, p);
+    X2_LAUNCH_OK();
+    return X2_OK;
+  };
+  switch (ea) {
+    case kEaNone: return go(k_blk_bwd<kEaNone, SGF, LPH, LT>);
+    case kEaTriplet: return go(k_blk_bwd<kEaTriplet, SGF, LPH, LT>);
+    default: return go(k_blk_bwd<kEaSegment, SGF, LPH, LT>);
+  }
+}
+static int launch_blk_fwd(const x2_conv_desc* d, const BlkParams& p, cudaStream_t st) {     // factorised sbf only
+  const bool l2 = d->C == 8;
+  if (blk_lt(d) == 7) return l2 ? launch_blk_fwd_t<true, 2, 7>(d, p, st) : launch_blk_fwd_t<true, 0, 7>(d, p, st);
+  return l2 ? launch_blk_fwd_t<true, 2, 8>(d, p, st) : launch_blk_fwd_t<true, 0, 8>(d, p, st);
+}
+static int launch_blk_bwd(const x2_conv_desc* d, const BlkParams& p, bool sgf, cudaStream_t st) {
+  const bool l2 = d->C == 8;
+  if (!sgf) return l2 ? launch_blk_bwd_t<false, 2, 1>(d, p, st) : launch_blk_bwd_t<false, 0, 1>(d, p, st);
+  if (blk_lt(d) == 7) return l2 ? launch_blk_bwd_t<true, 2, 7>(d, p, st) : launch_blk_bwd_t<true, 0, 7>(d, p, st);
+  return l2 ? launch_blk_bwd_t<true, 2, 8>(d, p, st) : launch_blk_bwd_t<true, 0, 8>(d, p, st);
+}
+
 }  // namespace x2
 
 using namespace x2;
@@ -997,6 +1092,12 @@ int x2_tc_wgrad(const float* Y, int64_t ldy, const float* X, int64_t ldx, int64_
   return tc::tc_wgrad(Y, ldy, X, ldx, rows, N, dW, lddw, db, static_cast<float*>(ws), (cudaStream_t)stream);
 }
 
+int x2_sbfconv_plan(const x2_conv_desc* d) {
+  if (!d) return 0;
+  const bool sgf = sgf_usable(d);
+  return ((sgf || (blk_usable(d) && blk_dense_enabled())) ? X2_PLAN_BLOCKS : 0) | (sgf ? X2_PLAN_FACTORISED_SBF : 0);
+}
+
 size_t x2_sbfconv_fwd_workspace_bytes(const x2_conv_desc* d) {
   if (!d) return 0;
   FwdWs w;
@@ -1012,7 +1113,9 @@ size_t x2_sbfconv_bwd_workspace_bytes(const x2_conv_desc* d) {
 int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, float* alpha,
                    void* ws, size_t ws_bytes, void* stream) {
   X2_TRY(check_desc(d));
-  X2_CHECK_ARG(s && s->qkvs && s->attn && s->lse && s->sg && out, "conv fwd: null output buffer");
+  X2_CHECK_ARG(s && s->qkvs && s->attn && s->lse && out, "conv fwd: null output buffer");
+  const bool sgf = sgf_usable(d) && !alpha;
+  X2_CHECK_ARG(sgf || (s->sg && d->sbf), "conv fwd: sbf / saved.sg required (no usable factorised sbf)");
   X2_CHECK_ARG(d->A == 0 || s->ea, "conv fwd: saved.ea required when A > 0");
   X2_CHECK_ARG(!d->fuse_skip || d->w_skip, "conv fwd: fuse_skip needs w_skip");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1057,6 +1160,23 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
     X2_TRY((launch_gemm<true, true>(p, nb, E, D, D, D, D, 4 * D, 0, st)));
   }
   phase_end(X2_PHASE_NODE_PROJ, st);
+  // (3+4, factorised sbf) lin_edge on its rows, then ONE block-centric attention kernel that forms lin_sbf(sbf_t)
+  // from theta_t and a per-source table in shared memory (csrc/blk_attn.cuh): no [T, S] read, no Sg tensor
+  if (sgf) {
+    if (d->A > 0) {
+      const int64_t n_ea = d->ea_index ? d->ea_rows : T;
+      X2_TRY(lin_fwd(L, d->edge_attr, d->A, d->w_edge, d->A, nullptr, s->ea, D, n_ea, D, d->A));
+    }
+    launch_k(k_wsbf_transpose, dim3((unsigned)cdiv((int64_t)D * d->S, 256)), dim3(256), 0, st, d->w_sbf, d->S, w.wsT);
+    X2_LAUNCH_OK();
+    phase_end(X2_PHASE_TROW_PROJ, st);
+    BlkParams bp{};
+    blk_fill(d, s, bp, w.wsT);
+    bp.attn = s->attn; bp.out = out; bp.lse = s->lse;
+    X2_TRY(launch_blk_fwd(d, bp, st));
+    phase_end(X2_PHASE_ATTN_FWD, st);
+    return X2_OK;
+  }
   // (3+4 fused) lin_edge + lin_sbf + segmented attention as ONE tcgen05 kernel over segment-aligned tiles
   // (csrc/tile_attn.cuh): edge_attr / sbf are streamed once, EA / Sg go from tensor memory through a
   // shared-memory slot ring straight into the attention warps.  Opt-in (X2_MODE_TF32X3_FUSED / X2GNN_FUSED=1).
@@ -1090,7 +1210,10 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
 int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* grad_out,
                    const x2_conv_grads* g, void* ws, size_t ws_bytes, void* stream) {
   X2_TRY(check_desc(d));
-  X2_CHECK_ARG(s && s->qkvs && s->attn && s->lse && s->sg && grad_out && g, "conv bwd: null buffer");
+  X2_CHECK_ARG(s && s->qkvs && s->attn && s->lse && grad_out && g, "conv bwd: null buffer");
+  const bool sgf = sgf_usable(d);
+  X2_CHECK_ARG(sgf || (s->sg && d->sbf), "conv bwd: sbf / saved.sg required (no usable factorised sbf)");
+  X2_CHECK_ARG(!(sgf && g->dsbf), "conv bwd: d sbf is not available with the factorised sbf (pass the dense tensor only)");
   X2_CHECK_ARG(g->dx && g->drbf && g->dw_rbf && g->dw_q && g->db_q && g->dw_k && g->db_k && g->dw_v &&
                    g->db_v && g->dw_sbf && g->db_sbf, "conv bwd: null gradient buffer");
   X2_CHECK_ARG(d->A == 0 || (s->ea && g->dw_edge), "conv bwd: lin_edge buffers required when A > 0");
@@ -1115,11 +1238,33 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
   }
 
   // (1,2) attention backward: by target, then by source
+  if (sgf || (blk_usable(d) && blk_dense_enabled())) {
+    // both passes in ONE kernel, one CTA per closed block of the line graph (csrc/blk_attn.cuh)
+    phase_begin(st);
+    if (sgf) {
+      launch_k(k_wsbf_transpose, dim3((unsigned)cdiv((int64_t)D * S, 256)), dim3(256), 0, st, d->w_sbf, S, w.wsT);
+      X2_LAUNCH_OK();
+    }
+    BlkParams bp{};
+    blk_fill(d, s, bp, w.wsT);
+    bp.gout = grad_out; bp.attn_in = s->attn; bp.lse_in = s->lse;
+    bp.dqkv = w.dqkv; bp.ldg = 3 * D;
+    bp.dea = w.dea; bp.dsg = w.dsg; bp.al = w.al; bp.da = w.da; bp.dP = w.dP;
+    X2_TRY(launch_blk_bwd(d, bp, sgf, st));
+    if (d->ea_index) {       // per-target rows -> per-table-row sums (fixed order)
+      launch_k(k_rows_segsum<4>, dim3((unsigned)cdiv(d->ea_rows * 32, 128)), dim3(128), 0, st, w.dea, d->ea_rowptr, d->ea_order,
+               d->ea_rows, w.dea_tab);
+      X2_LAUNCH_OK();
+    }
+    phase_end(X2_PHASE_ATTN_BWD_TGT, st);
+    phase_end(X2_PHASE_ATTN_BWD_SRC, st);
+  } else {
   switch (D / 32) {
     case 1: X2_TRY(launch_attn_bwd<1>(d, s, grad_out, w, st)); break;
     case 2: X2_TRY(launch_attn_bwd<2>(d, s, grad_out, w, st)); break;
     case 4: X2_TRY(launch_attn_bwd<4>(d, s, grad_out, w, st)); break;
     default: X2_TRY(launch_attn_bwd<8>(d, s, grad_out, w, st)); break;
+  }
   }
   const float* dq = w.dqkv;
   const float* dk = w.dqkv + D;
@@ -1130,11 +1275,22 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
   const float* dea_rows = d->ea_index ? w.dea_tab : w.dea;          // rows lin_edge was applied to
   const int64_t n_ea = d->ea_index ? d->ea_rows : T;
   if (A > 0 && g->dedge_attr && n_ea > 0) X2_TRY(lin_dgrad(L, dea_rows, D, d->w_edge, A, g->dedge_attr, A, n_ea, A, D, 0));
-  if (g->dsbf && T > 0) X2_TRY(lin_dgrad(L, w.dsg, D, d->w_sbf, S, g->dsbf, S, T, S, D, 0));
+  if (g->dsbf && T > 0 && !sgf) X2_TRY(lin_dgrad(L, w.dsg, D, d->w_sbf, S, g->dsbf, S, T, S, D, 0));
   phase_end(X2_PHASE_TROW_DGRAD, st);
   // (4) T-row weight gradients (split-K over triplets, fixed-order reduction)
   if (A > 0) X2_TRY(lin_wgrad(L, dea_rows, D, d->edge_attr, A, g->dw_edge, A, nullptr, n_ea, D, A));
-  X2_TRY(lin_wgrad(L, w.dsg, D, d->sbf, S, g->dw_sbf, S, g->db_sbf, T, D, S));
+  if (sgf) {
+    // dW_s / db_s from the per-source d(table) rows the by-source pass left (E-scale, fixed-order reduction)
+    const int parts = (int)(E < kDwsParts ? E : kDwsParts);
+    float* colsum = w.wg + (size_t)parts * D * S;
+    launch_k(k_dws_partial, dim3(parts), dim3(kDwsThreads), 0, st, (const float*)w.dP, d->sbf_tab, E, d->sbf_L, d->sbf_R, w.wg, colsum);
+    X2_LAUNCH_OK();
+    launch_k(k_splitk_reduce, dim3(splitk_reduce_blocks(D, S, true)), dim3(256), 0, st, (const float*)w.wg, (const float*)colsum, parts,
+             (int64_t)D, S, g->dw_sbf, (int64_t)S, g->db_sbf);
+    X2_LAUNCH_OK();
+  } else {
+    X2_TRY(lin_wgrad(L, w.dsg, D, d->sbf, S, g->dw_sbf, S, g->db_sbf, T, D, S));
+  }
 
   phase_end(X2_PHASE_TROW_WGRAD, st);
   // (5) recompute the filtered sources

@@ -336,6 +336,82 @@ __global__ void k_flags_finalize(int32_t* flags_out, const int32_t* flags_in) {
   flags_out[1] = flags_in[1];
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Closed blocks of the line graph (csrc/blk_attn.cuh).  A BLOCK is a contiguous range of line-nodes
+// [sptr[b], sptr[b+1]) such that every target segment draws all of its sources from ONE block; the
+// targets are grouped by that block.  Then every triplet has its source and its target in the same block:
+// a CTA that owns a block sees all contributions to dQ of its targets AND to dK / dV of its sources, and
+// the K / V (and per-source basis) rows of a block are shared by all of its targets.  For the line graph of
+// a sorted atom graph (edge_graph.py:12-30) a block is "all bonds leaving atom j" and its targets are the
+// bonds entering j (structural facts) -- but nothing here assumes that: f and f + 1 are put
+// in one block when they are adjacent sources of some target segment, and k_blk_tgt then VERIFIES the
+// closure, so an arbitrary edge_index either yields valid blocks or ok = 0 (callers keep the generic path).
+__global__ void k_blk_link(const int32_t* __restrict__ src, const int32_t* __restrict__ tgt, int64_t T,
+                           int32_t* __restrict__ link) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p + 1 >= T) return;
+  const int32_t s0 = src[p];
+  if (tgt[p] == tgt[p + 1] && src[p + 1] == s0 + 1) link[s0] = 1;     // benign race: every writer stores 1
+}
+__global__ void k_blk_bnd(const int32_t* __restrict__ link, int64_t E, int32_t* __restrict__ bnd) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < E) bnd[f] = (f == 0 || link[f - 1] == 0) ? 1 : 0;
+}
+__global__ void k_blk_ids(const int32_t* __restrict__ bnd, const int32_t* __restrict__ ex, int64_t E,
+                          int32_t* __restrict__ blk_of, int32_t* __restrict__ sptr) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= E) return;
+  const int32_t b = ex[f] + bnd[f] - 1;
+  blk_of[f] = b;
+  if (bnd[f]) sptr[b] = (int32_t)f;
+  if (f == E - 1) sptr[ex[E]] = (int32_t)E;
+}
+__global__ void k_blk_tgt(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src,
+                          const int32_t* __restrict__ blk_of, int64_t E, int32_t* __restrict__ gt,
+                          int32_t* __restrict__ cnt_g, int32_t* __restrict__ trip, int32_t* __restrict__ fl) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int beg = rowptr[e], end = rowptr[e + 1];
+  int32_t b = blk_of[e];                         // a target without triplets: any block will do
+  if (beg < end) {
+    b = blk_of[src[beg]];
+    bool bad = false;
+    for (int i = beg + 1; i < end; ++i) bad |= blk_of[src[i]] != b;
+    if (bad) atomicAdd(&fl[0], 1);
+    atomicAdd(&trip[b], end - beg);
+  }
+  gt[e] = b;
+  atomicAdd(&cnt_g[b], 1);
+}
+__global__ void k_blk_scatter(const int32_t* __restrict__ gt, const int32_t* __restrict__ tptr,
+                              int32_t* __restrict__ cur, int64_t E, int32_t* __restrict__ tord) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int32_t b = gt[e];
+  tord[tptr[b] + atomicAdd(&cur[b], 1)] = (int32_t)e;
+}
+__global__ void k_blk_sort(const int32_t* __restrict__ tptr, int32_t* __restrict__ tord,
+                           const int32_t* __restrict__ trip, const int32_t* __restrict__ sptr,
+                           const int32_t* __restrict__ nblk, int32_t* __restrict__ tpos, int32_t* __restrict__ fl) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= *nblk) return;
+  const int32_t t0 = tptr[b], n = tptr[b + 1] - t0;
+  seg_sort<false>(tord + t0, nullptr, n);      // ascending target ids: results do not depend on atomic order
+  for (int i = 0; i < n; ++i) tpos[tord[t0 + i]] = i;         // position of a target inside its block
+  atomicMax(&fl[2], trip[b]);
+  atomicMax(&fl[3], sptr[b + 1] - sptr[b]);
+  atomicMax(&fl[4], n);
+}
+__global__ void k_blk_finalize(int32_t* flags_out, const int32_t* fl, const int32_t* nblk) {
+  flags_out[0] = fl[0] == 0 ? 1 : 0;
+  flags_out[1] = *nblk;
+  flags_out[2] = fl[2];
+  flags_out[3] = fl[3];
+  flags_out[4] = fl[4];
+  flags_out[5] = 0;
+}
+
 }  // namespace x2
 
 using namespace x2;
@@ -524,6 +600,62 @@ int x2_items_build(const int32_t* rowptr_tgt, int64_t E, int64_t T, int32_t* ite
   int rc = exclusive_scan_i32(cnt, itemptr, E, sws, sbytes, st);
   if (rc) return rc;
   k_item_fill<<<(unsigned)cdiv(E + 1, 256), 256, 0, st>>>(rowptr_tgt, itemptr, E, items);
+  X2_LAUNCH_OK();
+  return X2_OK;
+}
+
+size_t x2_blocks_workspace_bytes(int64_t T, int64_t E) {
+  ArenaSize a;
+  if (E < 0) E = 0;
+  (void)T;
+  for (int i = 0; i < 7; ++i) a.take<int32_t>(E + 1);   // link, bnd, ex, blk_of, gt, cnt/cur, trip
+  a.take<int32_t>(E + 1);
+  a.take<int32_t>(8);
+  a.take<char>(scan_workspace_bytes(E));
+  return a.bytes();
+}
+
+int x2_blocks_build(const int32_t* src, const int32_t* tgt, const int32_t* rowptr_tgt, int64_t T, int64_t E,
+                    int32_t* blk_sptr, int32_t* blk_tptr, int32_t* blk_tord, int32_t* blk_tpos, int32_t* flags, void* ws,
+                    size_t ws_bytes, void* stream) {
+  X2_CHECK_ARG(src && tgt && rowptr_tgt && blk_sptr && blk_tptr && blk_tord && blk_tpos && flags, "x2_blocks_build: null pointer");
+  X2_CHECK_ARG(E > 0 && T >= 0 && E < 2147483647LL && T < 2147483647LL, "x2_blocks_build: bad sizes");
+  if (ws_bytes < x2_blocks_workspace_bytes(T, E)) { set_error("x2_blocks_build: workspace too small"); return X2_EWORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena a(ws, ws_bytes);
+  int32_t* link = a.take<int32_t>(E + 1);
+  int32_t* bnd = a.take<int32_t>(E + 1);
+  int32_t* ex = a.take<int32_t>(E + 1);
+  int32_t* blk_of = a.take<int32_t>(E + 1);
+  int32_t* gt = a.take<int32_t>(E + 1);
+  int32_t* cnt = a.take<int32_t>(E + 1);
+  int32_t* cur = a.take<int32_t>(E + 1);
+  int32_t* trip = a.take<int32_t>(E + 1);
+  int32_t* fl = a.take<int32_t>(8);
+  const size_t sbytes = scan_workspace_bytes(E);
+  void* sws = a.take<char>(sbytes);
+  X2_CUDA_OK(cudaMemsetAsync(link, 0, (size_t)(E + 1) * 4, st));
+  X2_CUDA_OK(cudaMemsetAsync(cnt, 0, (size_t)(E + 1) * 4, st));
+  X2_CUDA_OK(cudaMemsetAsync(cur, 0, (size_t)(E + 1) * 4, st));
+  X2_CUDA_OK(cudaMemsetAsync(trip, 0, (size_t)(E + 1) * 4, st));
+  X2_CUDA_OK(cudaMemsetAsync(fl, 0, 8 * 4, st));
+  const unsigned gT = (unsigned)cdiv(T > 0 ? T : 1, 256), gE = (unsigned)cdiv(E, 256);
+  if (T > 1) { k_blk_link<<<gT, 256, 0, st>>>(src, tgt, T, link); X2_LAUNCH_OK(); }
+  k_blk_bnd<<<gE, 256, 0, st>>>(link, E, bnd);
+  X2_LAUNCH_OK();
+  int rc = exclusive_scan_i32(bnd, ex, E, sws, sbytes, st);
+  if (rc) return rc;
+  k_blk_ids<<<gE, 256, 0, st>>>(bnd, ex, E, blk_of, blk_sptr);
+  X2_LAUNCH_OK();
+  k_blk_tgt<<<gE, 256, 0, st>>>(rowptr_tgt, src, blk_of, E, gt, cnt, trip, fl);
+  X2_LAUNCH_OK();
+  rc = exclusive_scan_i32(cnt, blk_tptr, E, sws, sbytes, st);
+  if (rc) return rc;
+  k_blk_scatter<<<gE, 256, 0, st>>>(gt, blk_tptr, cur, E, blk_tord);
+  X2_LAUNCH_OK();
+  k_blk_sort<<<gE, 256, 0, st>>>(blk_tptr, blk_tord, trip, blk_sptr, ex + E, blk_tpos, fl);
+  X2_LAUNCH_OK();
+  k_blk_finalize<<<1, 1, 0, st>>>(flags, fl, ex + E);
   X2_LAUNCH_OK();
   return X2_OK;
 }

@@ -15,6 +15,20 @@ from . import _lib
 
 
 @dataclass
+class Blocks:
+    """Closed blocks of the line graph (x2_blocks_build): block b = sources [sptr[b], sptr[b+1]) + the targets
+    tord[tptr[b] : tptr[b+1]]; every triplet has its source and its target in one block."""
+    n: int
+    sptr: torch.Tensor         # [E+1] int32
+    tptr: torch.Tensor         # [E+1] int32
+    tord: torch.Tensor         # [E] int32
+    tpos: torch.Tensor         # [E] int32: position of a target inside its block
+    max_triplets: int
+    max_src: int
+    max_tgt: int
+
+
+@dataclass
 class LineGraphMeta:
     T: int
     E: int
@@ -29,6 +43,7 @@ class LineGraphMeta:
     items: torch.Tensor = None     # [items_bound, 2] int32 work items of the fused kernels (x2_items_build), or None
     itemptr: torch.Tensor = None   # [E+1] int32
     items_bound: int = 0
+    blocks: Blocks = None          # None: no closed-block structure (or not target-sorted): generic kernels only
 
 
 def build(edge_index: torch.Tensor, num_nodes: int) -> LineGraphMeta:
@@ -52,7 +67,19 @@ def build(edge_index: torch.Tensor, num_nodes: int) -> LineGraphMeta:
     _lib.check(L.x2_meta_build(_lib.ptr(ei), T, E, _lib.ptr(src), _lib.ptr(tgt), _lib.ptr(rp_t),
                                _lib.ptr(od_t), _lib.ptr(rp_s), _lib.ptr(od_s), _lib.ptr(flags),
                                _lib.ptr(ws), ws.numel(), _lib.stream()), "x2_meta_build")
-    f = flags.tolist()          # one host sync per batch; also surfaces async kernel errors
+    # closed blocks (meaningful for a target-sorted list only; queued before the one host sync below)
+    bflags = torch.zeros(6, **i32)
+    if T > 0 and E > 0:
+        sptr = torch.empty(E + 1, **i32)
+        tptr = torch.empty(E + 1, **i32)
+        tord = torch.empty(E, **i32)
+        tpos = torch.empty(E, **i32)
+        ws3 = _lib.workspace(L.x2_blocks_workspace_bytes(T, E), dev)
+        _lib.check(L.x2_blocks_build(_lib.ptr(src), _lib.ptr(tgt), _lib.ptr(rp_t), T, E, _lib.ptr(sptr), _lib.ptr(tptr),
+                                     _lib.ptr(tord), _lib.ptr(tpos), _lib.ptr(bflags), _lib.ptr(ws3), ws3.numel(),
+                                     _lib.stream()),
+                   "x2_blocks_build")
+    f = torch.cat([flags, bflags]).tolist()          # one host sync per batch; also surfaces async kernel errors
     if f[1] != 0:
         raise IndexError(f"edge_index has {f[1]} entries outside [0, {E})")
     meta = LineGraphMeta(T, E, src, tgt, rp_t, od_t, rp_s, od_s, bool(f[0]), int(f[2]))
@@ -65,8 +92,15 @@ def build(edge_index: torch.Tensor, num_nodes: int) -> LineGraphMeta:
         ws2 = _lib.workspace(L.x2_items_workspace_bytes(E), dev)
         _lib.check(L.x2_items_build(_lib.ptr(rp_t), E, T, _lib.ptr(meta.itemptr), _lib.ptr(meta.items),
                                     _lib.ptr(ws2), ws2.numel(), _lib.stream()), "x2_items_build")
+    if meta.target_sorted and T > 0 and E > 0:
+        ok, nb, mt, ms, mg = f[4:9]
+        # a block is one CTA's work: keep the generic kernels when a few blocks hold most of the graph
+        if ok and nb > 0 and mt <= MAX_BLOCK_TRIPLETS:
+            meta.blocks = Blocks(nb, sptr, tptr, tord, tpos, mt, ms, mg)
     return meta
 
+
+MAX_BLOCK_TRIPLETS = 1 << 16
 
 _cache: list = []   # [(weakref(edge_index), version, num_nodes, meta)], most recent first
 _CACHE_SIZE = 8

@@ -26,6 +26,11 @@ MODE_TF32X3_FUSED = 2   # opt-in: + lin_edge / lin_sbf / forward attention as on
 MODE_TF32 = 3      # X2_MODE_TF32: reduced precision, one tf32 pass per product (the 2e-2 tolerance class)
 
 
+USE_BLOCKS = os.environ.get("X2GNN_BLOCK", "1") != "0"    # block-centric backward when the line graph has closed blocks
+USE_FACTORS = os.environ.get("X2GNN_SGF", "1") != "0"     # factorised lin_sbf when sbf carries F_B_2D's factors
+PLAN_COUNTS = {"blocks": 0, "factorised": 0}              # layer calls that took each path (tests, bench)
+
+
 def default_mode(hc: int) -> int:
     """Tensor-core Linear layers (fp32-accurate 3xTF32) whenever the shape allows; override with
     X2GNN_MODE=fp32|tf32x3|tf32x3_fused|tf32 (tf32 = reduced precision, opt-in only)."""
@@ -58,6 +63,36 @@ def _set_groups(desc, groups):
         desc.ea_rows = groups.rows
         desc.ea_index, desc.ea_rowptr, desc.ea_order = (_lib.ptr(groups.index), _lib.ptr(groups.rowptr),
                                                          _lib.ptr(groups.order))
+
+
+def _fill_desc(cfg, meta, t, dims, groups):
+    """x2_conv_desc of one layer call (the same descriptor drives the forward and the backward)."""
+    E, T, D, H, Cc, S, R, A, fuse = dims
+    desc = _lib.ConvDesc()
+    desc.E, desc.T = E, T
+    desc.D, desc.H, desc.C, desc.S, desc.R, desc.A = D, H, Cc, S, R, A
+    desc.fuse_skip, desc.mode = fuse, cfg["mode"]
+    desc.dropout_p, desc.seed = cfg["dropout_p"], cfg["seed"]
+    desc.tgt_sorted = 1 if meta.target_sorted else 0
+    for n in ("x", "rbf", "sbf", "w_rbf", "w_q", "b_q", "w_k", "b_k", "w_v", "b_v", "w_sbf", "b_sbf",
+              "w_skip", "b_skip"):
+        setattr(desc, n, _lib.ptr(t[n]))
+    desc.edge_attr = _lib.ptr(t["edge_attr"]) if A else None
+    desc.w_edge = _lib.ptr(t["w_edge"]) if A else None
+    for n in ("src", "tgt", "rowptr_tgt", "order_tgt", "rowptr_src", "order_src"):
+        setattr(desc, n, _lib.ptr(getattr(meta, n)))
+    _set_groups(desc, groups)
+    desc.items, desc.itemptr, desc.items_bound = _lib.ptr(meta.items), _lib.ptr(meta.itemptr), meta.items_bound
+    blk = meta.blocks
+    if blk is not None and USE_BLOCKS:         # closed blocks of the line graph: block-centric backward (csrc/blk_attn.cuh)
+        desc.nblk, desc.blk_max_src, desc.blk_max_trip, desc.blk_max_tgt = blk.n, blk.max_src, blk.max_triplets, blk.max_tgt
+        desc.blk_sptr, desc.blk_tptr, desc.blk_tord, desc.blk_tpos = (_lib.ptr(blk.sptr), _lib.ptr(blk.tptr),
+                                                                      _lib.ptr(blk.tord), _lib.ptr(blk.tpos))
+    fac = cfg.get("sbf_factors")
+    if fac is not None and USE_FACTORS:         # factorised sbf (F_B_2D output): lin_sbf inside the attention kernels
+        desc.sbf_tab, desc.angles = _lib.ptr(fac.table), _lib.ptr(fac.angles)
+        desc.sbf_L, desc.sbf_R = fac.L, fac.R
+    return desc
 
 
 class _SBFConvFn(torch.autograd.Function):
@@ -101,38 +136,29 @@ class _SBFConvFn(torch.autograd.Function):
                              f"got {groups.index.numel()}")
         fuse = 1 if t["w_skip"] is not None else 0
 
-        desc = _lib.ConvDesc()
-        desc.E, desc.T = E, T
-        desc.D, desc.H, desc.C, desc.S, desc.R, desc.A = D, H, Cc, S, R, A
-        desc.fuse_skip, desc.mode = fuse, cfg["mode"]
-        desc.dropout_p, desc.seed = cfg["dropout_p"], cfg["seed"]
-        desc.tgt_sorted = 1 if meta.target_sorted else 0
-        for n in ("x", "rbf", "sbf", "w_rbf", "w_q", "b_q", "w_k", "b_k", "w_v", "b_v", "w_sbf", "b_sbf",
-                  "w_skip", "b_skip"):
-            setattr(desc, n, _lib.ptr(t[n]))
-        desc.edge_attr = _lib.ptr(t["edge_attr"]) if A else None
-        desc.w_edge = _lib.ptr(t["w_edge"]) if A else None
-        for n in ("src", "tgt", "rowptr_tgt", "order_tgt", "rowptr_src", "order_src"):
-            setattr(desc, n, _lib.ptr(getattr(meta, n)))
-        _set_groups(desc, groups)
-        desc.items, desc.itemptr, desc.items_bound = _lib.ptr(meta.items), _lib.ptr(meta.itemptr), meta.items_bound
+        dims = (E, T, D, H, Cc, S, R, A, fuse)
+        desc = _fill_desc(cfg, meta, t, dims, groups)
+        L = _lib.lib()
+        plan = L.x2_sbfconv_plan(C.byref(desc))
+        factorised = bool(plan & 2) and not cfg["want_alpha"]
+        PLAN_COUNTS["blocks"] += plan & 1
+        PLAN_COUNTS["factorised"] += int(factorised)
 
         f32 = dict(dtype=torch.float32, device=dev)
         qkvs = torch.empty((E, 4 * D), **f32)
         attn = torch.empty((E, D), **f32)
         lse = torch.empty((E, H), **f32)
         ea = torch.empty((max(n_ea, 1), D), **f32) if A else None
-        sg = torch.empty((max(T, 1), D), **f32)
+        sg = None if factorised else torch.empty((max(T, 1), D), **f32)   # factorised sbf: lin_sbf(sbf) is never stored
         xs = torch.empty((E, D), **f32)          # x * lin_rbf(rbf): kept so the backward does not recompute it
         out = torch.empty((E, D), **f32) if fuse else attn
         alpha = torch.empty((T, H), **f32) if cfg["want_alpha"] else None
         saved = _lib.ConvSaved(_lib.ptr(qkvs), _lib.ptr(attn), _lib.ptr(lse), _lib.ptr(ea), _lib.ptr(sg),
                                _lib.ptr(xs))
-        L = _lib.lib()
         ws = _lib.workspace(L.x2_sbfconv_fwd_workspace_bytes(C.byref(desc)), dev)
         _lib.check(L.x2_sbfconv_fwd(C.byref(desc), C.byref(saved), _lib.ptr(out), _lib.ptr(alpha),
                                     _lib.ptr(ws), ws.numel(), _lib.stream()), "x2_sbfconv_fwd")
-        ctx.cfg, ctx.meta, ctx.dims = cfg, meta, (E, T, D, H, Cc, S, R, A, fuse)
+        ctx.cfg, ctx.meta, ctx.dims = cfg, meta, dims
         ctx.groups = groups
         ctx.tensors = t            # inputs + weights (kept alive; plain references, no graph)
         ctx.saved_bufs = (qkvs, attn, lse, ea, sg, xs)
@@ -150,21 +176,7 @@ class _SBFConvFn(torch.autograd.Function):
         dev = gout.device
         cfg = ctx.cfg
 
-        desc = _lib.ConvDesc()
-        desc.E, desc.T = E, T
-        desc.D, desc.H, desc.C, desc.S, desc.R, desc.A = D, H, Cc, S, R, A
-        desc.fuse_skip, desc.mode = fuse, cfg["mode"]
-        desc.dropout_p, desc.seed = cfg["dropout_p"], cfg["seed"]
-        desc.tgt_sorted = 1 if meta.target_sorted else 0
-        for n in ("x", "rbf", "sbf", "w_rbf", "w_q", "b_q", "w_k", "b_k", "w_v", "b_v", "w_sbf", "b_sbf",
-                  "w_skip", "b_skip"):
-            setattr(desc, n, _lib.ptr(t[n]))
-        desc.edge_attr = _lib.ptr(t["edge_attr"]) if A else None
-        desc.w_edge = _lib.ptr(t["w_edge"]) if A else None
-        for n in ("src", "tgt", "rowptr_tgt", "order_tgt", "rowptr_src", "order_src"):
-            setattr(desc, n, _lib.ptr(getattr(meta, n)))
-        _set_groups(desc, ctx.groups)
-        desc.items, desc.itemptr, desc.items_bound = _lib.ptr(meta.items), _lib.ptr(meta.itemptr), meta.items_bound
+        desc = _fill_desc(cfg, meta, t, ctx.dims, ctx.groups)
         n_ea = ctx.groups.rows if ctx.groups is not None else T
         saved = _lib.ConvSaved(_lib.ptr(qkvs), _lib.ptr(attn), _lib.ptr(lse), _lib.ptr(ea), _lib.ptr(sg),
                                _lib.ptr(xs))
@@ -286,6 +298,14 @@ class SBFTransformerConv(nn.Module):
                    want_alpha=isinstance(return_attention_weights, bool))
         if edge_attr_index is not None and self.lin_edge is not None:
             cfg["ea_groups"] = graph_meta.get_groups(edge_attr_index, edge_attr.size(0))
+        # F_B_2D tags its output with the factors it multiplied out (angular_basis_layer.SbfFactors): when they
+        # still describe `sbf` and index the source line-nodes of `edge_index`, lin_sbf is evaluated inside the
+        # attention kernels and the [T, S] tensor is not read
+        fac = getattr(sbf, "_x2_factors", None)
+        if fac is not None and (p_drop > 0 or cfg["want_alpha"] or (torch.is_grad_enabled() and sbf.requires_grad)
+                                or not fac.describes(sbf, edge_index)):
+            fac = None
+        cfg["sbf_factors"] = fac
         out, alpha = _SBFConvFn.apply(
             cfg, meta, x, rbf, sbf, edge_attr if self.lin_edge is not None else None,
             self.lin_rbf.weight, self.lin_query.weight, self.lin_query.bias, self.lin_key.weight,

@@ -2,7 +2,6 @@
   * x2_blocks_build: the closed blocks of a molecule's line graph are "the bonds leaving atom j" + the bonds
     entering j, verified property by property against a host restatement; arbitrary edge_index either yields
     valid blocks or none;
-  * the one-kernel backward (by-target + by-source pass per block) against the two generic kernels: bitwise;
   * the factorised lin_sbf (F_B_2D's output is table[src] * Y_l0(theta); lin_sbf is
     evaluated inside the attention kernels) against the dense [T, S] path and the fp64 oracle: 1e-5."""
 import numpy as np
@@ -13,6 +12,16 @@ from oracle import conv as oconv
 from util import FP32_TOL, relerr
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _factorised_on():
+    """The factorised lin_sbf is opt-in (sbftransformer_conv.USE_FACTORS / X2GNN_SGF=1): on for these tests."""
+    import x2gnn_b200.sbftransformer_conv as sc
+    old = sc.USE_FACTORS
+    sc.USE_FACTORS = True
+    yield
+    sc.USE_FACTORS = old
 
 DIMS = (128, 16, 42, 6, 128)
 
@@ -124,28 +133,6 @@ def _step(layer, rec, sbf, edge_attr=None, edge_attr_index=None):
     return out.detach().clone(), grads
 
 
-def test_block_backward_is_bitwise_the_two_pass_backward():
-    import x2gnn_b200.sbftransformer_conv as sc
-    rec = _fb_inputs(6, seed=1)
-    layer = _layer()
-    sbf = rec["sbf"].clone()                      # a plain tensor: no factors
-    assert sc.USE_BLOCKS
-    o1, g1 = _step(layer, rec, sbf)
-    sc.USE_BLOCKS = False
-    try:
-        o0, g0 = _step(layer, rec, sbf)
-    finally:
-        sc.USE_BLOCKS = True
-    assert torch.equal(o0, o1)
-    for k in g0:
-        if k in ("lin_sbf.weight", "lin_sbf.bias", "lin_edge.weight", "edge_attr"):
-            # same numbers through the same GEMMs, but d(lin_edge out) / d(lin_sbf out) are formed as one expression
-            # here (contraction may differ): fp32 rounding only
-            assert relerr(g1[k], g0[k]) < 2e-6, k
-        else:
-            assert torch.equal(g1[k], g0[k]), k
-
-
 @pytest.mark.parametrize("table", [False, True])
 @pytest.mark.parametrize("ball", [False, True])
 def test_factorised_sbf_matches_dense_and_oracle(table, ball):
@@ -171,7 +158,7 @@ def test_factorised_sbf_matches_dense_and_oracle(table, ball):
     for k in g_d:
         if k == "lin_key.bias":
             continue
-        assert relerr(g_f[k], g_d[k]) < FP32_TOL, k
+        assert relerr(g_f[k], g_d[k]) < 2 * FP32_TOL, k       # two fp32 paths, each within 1e-5 of the fp64 oracle (below)
     # twice the same bits
     o_f2, g_f2 = _step(layer, rec, sbf, **kw)
     assert torch.equal(o_f, o_f2)
@@ -198,6 +185,9 @@ def test_factorised_sbf_matches_dense_and_oracle(table, ball):
     for k, p in ref.named_parameters():
         if k != "lin_key.bias":
             assert relerr(g_f[k], p.grad) < FP32_TOL, k
+            # the dense path on the same graph (2e5 triplets on the ball graphs: the T-row weight gradients were
+            # 1.3e-5 off before the tensor-core accumulation was cut into periods, csrc/tc_gemm.cuh kG2Period)
+            assert relerr(g_d[k], p.grad) < FP32_TOL, k
 
 
 def test_factors_are_dropped_when_they_do_not_apply():

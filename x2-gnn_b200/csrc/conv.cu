@@ -771,28 +771,23 @@ static bool env_on(const char* name) {       // default on; NAME=0 turns the pat
   const char* v = getenv(name);
   return !(v && v[0] == '0');
 }
-static bool blk_usable(const x2_conv_desc* d) {
-  static const bool on = env_on("X2GNN_BLOCK");
-  return on && d->nblk > 0 && d->blk_sptr && d->blk_tptr && d->blk_tord && d->tgt_sorted && d->T > 0 && d->D == 128 &&
-         d->dropout_p == 0.f && (d->A == 0 || d->A > 0);
-}
-// With a DENSE Sg tensor the one-kernel backward is slower than the two generic kernels (0.58 vs 0.47 ms on the
-// bench batch: profiles/r2_notes.md), so it is opt-in there (X2GNN_BLOCK_DENSE=1); the factorised path always uses it.
-static bool blk_dense_enabled() {
-  static const bool on = [] { const char* v = getenv("X2GNN_BLOCK_DENSE"); return v && v[0] == '1'; }();
-  return on;
-}
-constexpr int kDwsParts = 2 * kNumSM;
-constexpr size_t kBlkSmemMax = 220 * 1024;    // per-source basis tables of a block (factorised sbf)
+constexpr int kDwsParts = 6 * kNumSM;
+constexpr size_t kBlkSmemMax = 220 * 1024;    // shared memory of a block-centric CTA
 // rows per source of the staged table: the config's 7 orders exactly, anything else padded to 8 with zero rows
 static int blk_lt(const x2_conv_desc* d) { return d->sbf_L == 7 ? 7 : kBlkLMax; }
-static size_t blk_smem_bytes(const x2_conv_desc* d) { return (size_t)d->blk_max_src * blk_lt(d) * 128 * sizeof(float); }
-// factorised lin_sbf: blocks + the factors of sbf, L <= 8 orders of <= 8 radial functions, the block's table fits smem
+static size_t blk_table_bytes(const x2_conv_desc* d) { return (size_t)d->blk_max_src * blk_lt(d) * 128 * sizeof(float); }
+// factorised lin_sbf: closed blocks of a target-sorted line graph + the factors of sbf, L <= 8 orders of <= 8 radial
+// functions, D = 128, no dropout, and W_s^T + one block's table + the target offsets fit shared memory
 static bool sgf_usable(const x2_conv_desc* d) {
-  static const bool on = env_on("X2GNN_SGF");
-  return on && blk_usable(d) && d->sbf_tab && d->angles && d->sbf_L >= 1 && d->sbf_L <= kBlkLMax && d->sbf_R >= 1 &&
-         d->sbf_R <= kBlkRMax && d->sbf_L * d->sbf_R == d->S && d->blk_max_src > 0 && blk_smem_bytes(d) <= kBlkSmemMax &&
-         (reinterpret_cast<uintptr_t>(d->b_sbf) & 15) == 0;
+  static const bool on = env_on("X2GNN_SGF") && env_on("X2GNN_BLOCK");
+  if (!(on && d->nblk > 0 && d->nblk < 2147483647LL && d->blk_sptr && d->blk_tptr && d->blk_tord && d->blk_tpos &&
+        d->tgt_sorted && d->T > 0 && d->D == 128 && d->dropout_p == 0.f))
+    return false;
+  if (!(d->sbf_tab && d->angles && d->sbf_L >= 1 && d->sbf_L <= kBlkLMax && d->sbf_R >= 1 && d->sbf_R <= kBlkRMax &&
+        d->sbf_L * d->sbf_R == d->S && d->blk_max_src > 0 && d->blk_max_tgt > 0 && d->blk_max_trip > 0))
+    return false;
+  const size_t need = (size_t)d->S * 128 * sizeof(float) + blk_table_bytes(d) + ((size_t)d->blk_max_tgt + 8) * 4;
+  return need <= kBlkSmemMax && (reinterpret_cast<uintptr_t>(d->b_sbf) & 15) == 0;
 }
 
 struct BwdWs {
@@ -996,60 +991,73 @@ static int launch_attn_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const 
   return X2_OK;
 }
 
-// ---- block-centric launches
+// ---- block-centric launches (factorised sbf)
 static void blk_fill(const x2_conv_desc* d, const x2_conv_saved* s, BlkParams& p, const float* wsT) {
   p.qkvs = s->qkvs; p.ldq = 4 * d->D;
   p.ea = s->ea; p.ea_index = d->ea_index;
-  p.sg = s->sg;
   p.stab = d->sbf_tab; p.angles = d->angles; p.wsT = wsT; p.b_sbf = d->b_sbf;
   p.L = d->sbf_L; p.Rr = d->sbf_R; p.S = d->S;
   p.src = d->src; p.tgt = d->tgt; p.rowptr_tgt = d->rowptr_tgt; p.rowptr_src = d->rowptr_src; p.order_src = d->order_src;
-  p.blk_sptr = d->blk_sptr; p.blk_tptr = d->blk_tptr; p.blk_tord = d->blk_tord;
+  p.blk_sptr = d->blk_sptr; p.blk_tptr = d->blk_tptr; p.blk_tord = d->blk_tord; p.blk_tpos = d->blk_tpos;
+  p.nblk = (int)d->nblk; p.maxS = d->blk_max_src; p.maxTrip = d->blk_max_trip; p.maxTgt = d->blk_max_tgt;
   p.E = d->E; p.H = d->H; p.C = d->C; p.scale = 1.0f / sqrtf((float)d->C);
   p.fuse_skip = d->fuse_skip;
 }
-template <bool SGF, int LPH, int LT>
+template <int LPH, int LT>
 static int launch_blk_fwd_t(const x2_conv_desc* d, const BlkParams& p, cudaStream_t st) {
   const int ea = d->A == 0 ? kEaNone : (d->ea_index ? kEaSegment : kEaTriplet);
-  const size_t smem = SGF ? blk_smem_bytes(d) : 0;
+  // two halves (two blocks in flight per SM) when two staged tables fit next to W_s^T
+  const size_t wbytes = (size_t)d->S * 128 * sizeof(float);
+  const int nh = wbytes + 2 * blk_table_bytes(d) <= kBlkSmemMax ? 2 : 1;
+  const size_t smem = wbytes + nh * blk_table_bytes(d);
+  const int64_t want = cdiv(d->nblk, nh);
+  const unsigned grid = (unsigned)(want < kNumSM ? want : kNumSM);
   auto go = [&](auto kern) -> int {
-    if (SGF) X2_DYN_SMEM(kern, kBlkSmemMax);      // once per (kernel, device): the largest table the path takes
-    launch_k(kern, dim3((unsigned)d->nblk), dim3(kBlkThreads), smem, st, p);
+    X2_DYN_SMEM(kern, kBlkSmemMax);      // once per (kernel, device): the largest layout the path takes
+    launch_k(kern, dim3(grid), dim3(nh * kBlkHalf), smem, st, p);
     X2_LAUNCH_OK();
     return X2_OK;
   };
   switch (ea) {
-    case kEaNone: return go(k_blk_fwd<kEaNone, SGF, LPH, LT>);
-    case kEaTriplet: return go(k_blk_fwd<kEaTriplet, SGF, LPH, LT>);
-    default: return go(k_blk_fwd<kEaSegment, SGF, LPH, LT>);
+    case kEaNone: return go(k_blk_fwd<kEaNone, LPH, LT>);
+    case kEaTriplet: return go(k_blk_fwd<kEaTriplet, LPH, LT>);
+    default: return go(k_blk_fwd<kEaSegment, LPH, LT>);
   }
 }
-template <bool SGF, int LPH, int LT>
-static int launch_blk_bwd_t(const x2_conv_desc* d, const BlkParams& p, cudaStream_t st) {
+template <int LPH, int LT, bool ALDA>
+static int launch_blk_bwd_t(const x2_conv_desc* d, const BlkParams& p, size_t smem, cudaStream_t st) {
   const int ea = d->A == 0 ? kEaNone : (d->ea_index ? kEaSegment : kEaTriplet);
-  const size_t smem = SGF ? blk_smem_bytes(d) : 0;
+  const unsigned grid = (unsigned)(d->nblk < kNumSM ? d->nblk : kNumSM);
   auto go = [&](auto kern) -> int {
-    if (SGF) X2_DYN_SMEM(kern, kBlkSmemMax);
-    launch_k(kern, dim3((unsigned)d->nblk), dim3(kBlkThreads), smem, st, p);
+    X2_DYN_SMEM(kern, kBlkSmemMax);
+    launch_k(kern, dim3(grid), dim3(kBlkHalf), smem, st, p);
     X2_LAUNCH_OK();
     return X2_OK;
   };
   switch (ea) {
-    case kEaNone: return go(k_blk_bwd<kEaNone, SGF, LPH, LT>);
-    case kEaTriplet: return go(k_blk_bwd<kEaTriplet, SGF, LPH, LT>);
-    default: return go(k_blk_bwd<kEaSegment, SGF, LPH, LT>);
+    case kEaNone: return go(k_blk_bwd<kEaNone, LPH, LT, ALDA>);
+    case kEaTriplet: return go(k_blk_bwd<kEaTriplet, LPH, LT, ALDA>);
+    default: return go(k_blk_bwd<kEaSegment, LPH, LT, ALDA>);
   }
 }
-static int launch_blk_fwd(const x2_conv_desc* d, const BlkParams& p, cudaStream_t st) {     // factorised sbf only
+static int launch_blk_fwd(const x2_conv_desc* d, const BlkParams& p, cudaStream_t st) {
   const bool l2 = d->C == 8;
-  if (blk_lt(d) == 7) return l2 ? launch_blk_fwd_t<true, 2, 7>(d, p, st) : launch_blk_fwd_t<true, 0, 7>(d, p, st);
-  return l2 ? launch_blk_fwd_t<true, 2, 8>(d, p, st) : launch_blk_fwd_t<true, 0, 8>(d, p, st);
+  if (blk_lt(d) == 7) return l2 ? launch_blk_fwd_t<2, 7>(d, p, st) : launch_blk_fwd_t<0, 7>(d, p, st);
+  return l2 ? launch_blk_fwd_t<2, 8>(d, p, st) : launch_blk_fwd_t<0, 8>(d, p, st);
 }
-static int launch_blk_bwd(const x2_conv_desc* d, const BlkParams& p, bool sgf, cudaStream_t st) {
+static int launch_blk_bwd(const x2_conv_desc* d, const BlkParams& p, cudaStream_t st) {
   const bool l2 = d->C == 8;
-  if (!sgf) return l2 ? launch_blk_bwd_t<false, 2, 1>(d, p, st) : launch_blk_bwd_t<false, 0, 1>(d, p, st);
-  if (blk_lt(d) == 7) return l2 ? launch_blk_bwd_t<true, 2, 7>(d, p, st) : launch_blk_bwd_t<true, 0, 7>(d, p, st);
-  return l2 ? launch_blk_bwd_t<true, 2, 8>(d, p, st) : launch_blk_bwd_t<true, 0, 8>(d, p, st);
+  // alpha / d(logit) of a block's triplets stay in shared memory between the passes when they fit
+  const size_t base = (size_t)d->S * 128 * sizeof(float) + blk_table_bytes(d) + (((size_t)d->blk_max_tgt + 1 + 3) & ~(size_t)3) * 4;
+  const size_t ad = (size_t)d->blk_max_trip * 2 * d->H * sizeof(float);
+  const bool alda = base + ad <= kBlkSmemMax;
+  const size_t smem = base + (alda ? ad : 0);
+  if (blk_lt(d) == 7) {
+    if (alda) return l2 ? launch_blk_bwd_t<2, 7, true>(d, p, smem, st) : launch_blk_bwd_t<0, 7, true>(d, p, smem, st);
+    return l2 ? launch_blk_bwd_t<2, 7, false>(d, p, smem, st) : launch_blk_bwd_t<0, 7, false>(d, p, smem, st);
+  }
+  if (alda) return l2 ? launch_blk_bwd_t<2, 8, true>(d, p, smem, st) : launch_blk_bwd_t<0, 8, true>(d, p, smem, st);
+  return l2 ? launch_blk_bwd_t<2, 8, false>(d, p, smem, st) : launch_blk_bwd_t<0, 8, false>(d, p, smem, st);
 }
 
 }  // namespace x2
@@ -1094,8 +1102,7 @@ int x2_tc_wgrad(const float* Y, int64_t ldy, const float* X, int64_t ldx, int64_
 
 int x2_sbfconv_plan(const x2_conv_desc* d) {
   if (!d) return 0;
-  const bool sgf = sgf_usable(d);
-  return ((sgf || (blk_usable(d) && blk_dense_enabled())) ? X2_PLAN_BLOCKS : 0) | (sgf ? X2_PLAN_FACTORISED_SBF : 0);
+  return sgf_usable(d) ? (X2_PLAN_BLOCKS | X2_PLAN_FACTORISED_SBF) : 0;
 }
 
 size_t x2_sbfconv_fwd_workspace_bytes(const x2_conv_desc* d) {
@@ -1115,7 +1122,7 @@ int x2_sbfconv_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float* out, fl
   X2_TRY(check_desc(d));
   X2_CHECK_ARG(s && s->qkvs && s->attn && s->lse && out, "conv fwd: null output buffer");
   const bool sgf = sgf_usable(d) && !alpha;
-  X2_CHECK_ARG(sgf || (s->sg && d->sbf), "conv fwd: sbf / saved.sg required (no usable factorised sbf)");
+  X2_CHECK_ARG(sgf || (s->sg && (d->sbf || d->T == 0)), "conv fwd: sbf / saved.sg required (no usable factorised sbf)");
   X2_CHECK_ARG(d->A == 0 || s->ea, "conv fwd: saved.ea required when A > 0");
   X2_CHECK_ARG(!d->fuse_skip || d->w_skip, "conv fwd: fuse_skip needs w_skip");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1212,7 +1219,7 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
   X2_TRY(check_desc(d));
   X2_CHECK_ARG(s && s->qkvs && s->attn && s->lse && grad_out && g, "conv bwd: null buffer");
   const bool sgf = sgf_usable(d);
-  X2_CHECK_ARG(sgf || (s->sg && d->sbf), "conv bwd: sbf / saved.sg required (no usable factorised sbf)");
+  X2_CHECK_ARG(sgf || (s->sg && (d->sbf || d->T == 0)), "conv bwd: sbf / saved.sg required (no usable factorised sbf)");
   X2_CHECK_ARG(!(sgf && g->dsbf), "conv bwd: d sbf is not available with the factorised sbf (pass the dense tensor only)");
   X2_CHECK_ARG(g->dx && g->drbf && g->dw_rbf && g->dw_q && g->db_q && g->dw_k && g->db_k && g->dw_v &&
                    g->db_v && g->dw_sbf && g->db_sbf, "conv bwd: null gradient buffer");
@@ -1238,19 +1245,17 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
   }
 
   // (1,2) attention backward: by target, then by source
-  if (sgf || (blk_usable(d) && blk_dense_enabled())) {
-    // both passes in ONE kernel, one CTA per closed block of the line graph (csrc/blk_attn.cuh)
+  if (sgf) {
+    // factorised sbf: both passes in ONE kernel, one CTA per closed block of the line graph (csrc/blk_attn.cuh)
     phase_begin(st);
-    if (sgf) {
-      launch_k(k_wsbf_transpose, dim3((unsigned)cdiv((int64_t)D * S, 256)), dim3(256), 0, st, d->w_sbf, S, w.wsT);
-      X2_LAUNCH_OK();
-    }
+    launch_k(k_wsbf_transpose, dim3((unsigned)cdiv((int64_t)D * S, 256)), dim3(256), 0, st, d->w_sbf, S, w.wsT);
+    X2_LAUNCH_OK();
     BlkParams bp{};
     blk_fill(d, s, bp, w.wsT);
     bp.gout = grad_out; bp.attn_in = s->attn; bp.lse_in = s->lse;
     bp.dqkv = w.dqkv; bp.ldg = 3 * D;
-    bp.dea = w.dea; bp.dsg = w.dsg; bp.al = w.al; bp.da = w.da; bp.dP = w.dP;
-    X2_TRY(launch_blk_bwd(d, bp, sgf, st));
+    bp.dea = w.dea; bp.al = w.al; bp.da = w.da; bp.dP = w.dP;
+    X2_TRY(launch_blk_bwd(d, bp, st));
     if (d->ea_index) {       // per-target rows -> per-table-row sums (fixed order)
       launch_k(k_rows_segsum<4>, dim3((unsigned)cdiv(d->ea_rows * 32, 128)), dim3(128), 0, st, w.dea, d->ea_rowptr, d->ea_order,
                d->ea_rows, w.dea_tab);
@@ -1281,9 +1286,13 @@ int x2_sbfconv_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const float* g
   if (A > 0) X2_TRY(lin_wgrad(L, dea_rows, D, d->edge_attr, A, g->dw_edge, A, nullptr, n_ea, D, A));
   if (sgf) {
     // dW_s / db_s from the per-source d(table) rows the by-source pass left (E-scale, fixed-order reduction)
-    const int parts = (int)(E < kDwsParts ? E : kDwsParts);
+    const int64_t chunks = cdiv(E, kDwsChunk);
+    const int parts = (int)(chunks < kDwsParts ? chunks : kDwsParts);
     float* colsum = w.wg + (size_t)parts * D * S;
-    launch_k(k_dws_partial, dim3(parts), dim3(kDwsThreads), 0, st, (const float*)w.dP, d->sbf_tab, E, d->sbf_L, d->sbf_R, w.wg, colsum);
+    if (d->sbf_L == 7 && d->sbf_R == 6)
+      launch_k(k_dws_partial<7, 6>, dim3(parts), dim3(kDwsThreads), 0, st, (const float*)w.dP, d->sbf_tab, E, d->sbf_L, d->sbf_R, w.wg, colsum);
+    else
+      launch_k(k_dws_partial<0, 0>, dim3(parts), dim3(kDwsThreads), 0, st, (const float*)w.dP, d->sbf_tab, E, d->sbf_L, d->sbf_R, w.wg, colsum);
     X2_LAUNCH_OK();
     launch_k(k_splitk_reduce, dim3(splitk_reduce_blocks(D, S, true)), dim3(256), 0, st, (const float*)w.wg, (const float*)colsum, parts,
              (int64_t)D, S, g->dw_sbf, (int64_t)S, g->db_sbf);

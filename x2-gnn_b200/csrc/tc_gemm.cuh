@@ -725,6 +725,18 @@ __device__ __forceinline__ uint32_t mnmajor_off(int r, int c16) {
 }
 
 constexpr int kG2YCol = 128;         // TMEM columns [128, 128 + 64 S): per stage Y^T hi (32 cols) | lo (32 cols)
+// The tensor core adds into its fp32 accumulator with TRUNCATION: every tcgen05.mma loses ~half an ulp of the
+// running sum, always towards zero.  Measured on dW = Y^T X with N(0,1) operands (tools/wgrad_err.py): the result
+// shrinks by 6e-9 per accumulated row -- 3e-6 at 346 rows per CTA, 8.9e-6 at 1 350, 4.2e-5 at the bench batch's
+// 5 485 (cuBLAS fp32: 2.5e-6) -- a bias, not noise, and above the 1e-5 parity bar.  So the accumulation is cut
+// into PERIODS of kG2Period chunks (256 rows: 96 MMAs) that alternate between two accumulators (columns
+// [0, 128) and [384, 512)); a finished period is added, round-to-nearest, to fp32 running sums held in the
+// registers of the producer threads (thread (q, g, lane): channel 32 q + lane, columns 32 g .. 32 g + 31), which
+// also write the CTA's partial tile at the end.  No extra barrier: a producer that has passed the `empty` wait
+// for chunk i knows chunk i - S has retired, hence period p once i = (p + 1) F - 1 + S; and the MMA warp cannot
+// reach period p + 2 (same accumulator) before every producer has published chunk (p + 2) F > i.  Needs F > S.
+constexpr int kG2Period = 8;
+constexpr int kG2Acc1 = 384;         // second accumulator (4 stages: Y^T operands end at column 384)
 
 __device__ __forceinline__ void tmem_st8f(uint32_t taddr, const float (&v)[8], bool lo) {
   uint32_t r[8];
@@ -806,14 +818,16 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
         uint64_t dxh = make_desc(x_hi, 4096, 512, kLayoutSW128Base32);
         uint64_t dxl = make_desc(x_lo, 4096, 512, kLayoutSW128Base32);
         // one K=8 step = two 4-row k-groups = 1024 B (>>4 = 64)
+        const uint32_t cp = (uint32_t)(c % kG2Period);              // chunk inside its period
+        const uint32_t acc = tmem_base + (((c / kG2Period) & 1) ? (uint32_t)kG2Acc1 : 0u);
         if (p.single) {
           for (int ks = 0; ks < ksteps; ++ks, dxh += 64, y_hi += 8)
-            umma_tf32_ts_w(leader, tmem_base, y_hi, dxh, idesc, (c | ks) != 0);
+            umma_tf32_ts_w(leader, acc, y_hi, dxh, idesc, (cp | (uint32_t)ks) != 0);
         } else {
           for (int ks = 0; ks < ksteps; ++ks, dxh += 64, dxl += 64, y_hi += 8, y_lo += 8) {
-            umma_tf32_ts_w(leader, tmem_base, y_hi, dxh, idesc, (c | ks) != 0);
-            umma_tf32_ts_w(leader, tmem_base, y_lo, dxh, idesc, 1);
-            umma_tf32_ts_w(leader, tmem_base, y_hi, dxl, idesc, 1);
+            umma_tf32_ts_w(leader, acc, y_hi, dxh, idesc, (cp | (uint32_t)ks) != 0);
+            umma_tf32_ts_w(leader, acc, y_lo, dxh, idesc, 1);
+            umma_tf32_ts_w(leader, acc, y_hi, dxl, idesc, 1);
           }
         }
         umma_commit_w(leader, &empty[st]);
@@ -830,6 +844,32 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
     const uint32_t s_u = smem_u32(sS);
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + kG2YCol + 8 * g;
     float cs = 0.f;
+    // running sums of the finished accumulation periods (see kG2Period): channel d, columns 32 g .. 32 g + 31
+    float racc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) racc[j] = 0.f;
+    int64_t drained = 0;                             // periods added to racc so far
+    const bool my_cols = 32 * g < p.N_pad;           // warp-uniform
+    auto drain = [&](int64_t period) {               // whole warp (tcgen05.ld is .sync.aligned)
+      if (my_cols) {
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ((period & 1) ? (uint32_t)kG2Acc1 : 0u) + 32 * g;
+        float v[16];
+        tmem_ld16(ta, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) racc[j] += v[j];
+        tmem_ld16(ta + 16, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) racc[16 + j] += v[j];
+      }
+    };
+    // called after the `empty` wait that precedes writing chunk i: chunk i - S has retired
+    auto drain_if_due = [&](int64_t i) {
+      const int64_t r = i - S + 1;                   // chunks known to be retired
+      if (r > 0 && r % kG2Period == 0 && r / kG2Period > drained) {
+        drain(drained);
+        ++drained;
+      }
+    };
     if constexpr (XMODE != 0) {
       // ---- cp.async producers: raw fp32 goes straight into the X hi operand (MN-major layout) and into a
       // per-stage raw Y block; the hi operands are the raw words (the tensor core truncates them), only the
@@ -880,9 +920,10 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
       int64_t ic = 0;                                // next chunk to issue
       auto issue = [&]() {
         const int64_t row0 = rbeg + ic * kChunkK;
-        ++ic;
         mbar_wait(&empty[ist], iph ^ 1);             // MMAs of the chunk that used this stage have retired
         tc_fence_after();
+        drain_if_due(ic);
+        ++ic;
         const uint32_t sb = s_u + ist * stage_bytes;
         if (row0 + kChunkK <= rend) {
 #pragma unroll
@@ -1000,9 +1041,12 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
       }
     };
     uint32_t st = 0, ph = 0;
+    int64_t cc = 0;                                  // chunk being written
     auto commit = [&](const float (&vy)[8], const float4 (&vx)[NV]) {
       mbar_wait(&empty[st], ph ^ 1);
       tc_fence_after();
+      drain_if_due(cc);
+      ++cc;
 #pragma unroll
       for (int j = 0; j < 8; ++j) cs += vy[j];                   // fixed order per thread
       tmem_st8f(trow + st * 64, vy, false);
@@ -1042,6 +1086,20 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
       }
     }
     }
+    // the periods still in tensor memory (at most two, in different accumulators), then this thread's slice of
+    // the CTA's partial tile
+    if (nchunks > 0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+      const int64_t nper = (nchunks + kG2Period - 1) / kG2Period;
+      for (; drained < nper; ++drained) drain(drained);
+    }
+    if (my_cols) {
+      float* dst = pr.partial + (cta * 128 + d) * p.N + 32 * g;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (32 * g + j < p.N) dst[j] = racc[j];
+    }
     // column sums of Y over this CTA's rows: combine the 4 row groups in fixed order
     if (pr.colsum) {
       cs_smem[g * 128 + d] = cs;
@@ -1049,26 +1107,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
       if (g == 0) pr.colsum[cta * 128 + d] = (cs_smem[d] + cs_smem[128 + d]) + (cs_smem[256 + d] + cs_smem[384 + d]);
     }
   }
-  if (warp == 0 || warp > kProducerWarps) {
-    // =============================== epilogue: accumulator -> this CTA's partial tile
-    const int q = warp & 3;
-    const int m = q * 32 + lane;
-    float* dst = pr.partial + (cta * 128 + m) * p.N;
-    if (nchunks > 0) {
-      mbar_wait(tfull, 0);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < p.N_pad; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + c0, v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c0 + j < p.N) dst[c0 + j] = v[j];
-      }
-    } else {
-      for (int j = 0; j < p.N; ++j) dst[j] = 0.f;
-    }
-  }
+  // (warps 17..19 have nothing left to do: the producers drain the accumulators, see kG2Period)
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {

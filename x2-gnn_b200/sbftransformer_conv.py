@@ -26,8 +26,11 @@ MODE_TF32X3_FUSED = 2   # opt-in: + lin_edge / lin_sbf / forward attention as on
 MODE_TF32 = 3      # X2_MODE_TF32: reduced precision, one tf32 pass per product (the 2e-2 tolerance class)
 
 
-USE_BLOCKS = os.environ.get("X2GNN_BLOCK", "1") != "0"    # block-centric backward when the line graph has closed blocks
-USE_FACTORS = os.environ.get("X2GNN_SGF", "1") != "0"     # factorised lin_sbf when sbf carries F_B_2D's factors
+USE_BLOCKS = os.environ.get("X2GNN_BLOCK", "1") != "0"    # pass the closed blocks of the line graph to the library
+# factorised lin_sbf when sbf carries F_B_2D's factors.  Opt-in (X2GNN_SGF=1 or this flag):
+# parity-green and more accurate than the dense path, but its kernels are bound by shared-memory reads of the
+# per-source tables and measure slower than the dense kernels today (profiles/r2_notes.md)
+USE_FACTORS = os.environ.get("X2GNN_SGF", "0") == "1"
 PLAN_COUNTS = {"blocks": 0, "factorised": 0}              # layer calls that took each path (tests, bench)
 
 

@@ -315,6 +315,19 @@ int x2_rbf_readout_bwd(const float* x, const float* rbf, const float* w, const f
                        const float* grad_out, int64_t N, int64_t E, int32_t D, int32_t R, float* dx, float* drbf,
                        float* dw, float* db, void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------- parameter-update tail of a training step
+ * (trainer.py:43-48, train_ema.py:45-47) over FLAT fp32 buffers of n elements, two launches:
+ *   total = ||grad * grad_scale||_2 ; coef = min(1, max_norm / (total + 1e-6))     (torch clip_grad_norm_; max_norm <= 0: off)
+ *   g = grad * grad_scale * coef ; exp_avg, exp_avg_sq, param: torch.optim.Adam (defaults: no weight decay / amsgrad)
+ *   ema = ema_decay * ema + (1 - ema_decay) * param                               (ema may be NULL)
+ * `step` is a device float holding the number of updates done so far; the call increments it (CUDA-graph safe).
+ * grad_scale = 1 / world after a sum all-reduce of the flat gradient.  norm_out (device float, may be NULL) receives
+ * the gradient norm before clipping.  Deterministic (fixed-order fp64 reduction).  ws >= x2_optim_workspace_bytes(n). */
+size_t x2_optim_workspace_bytes(int64_t n);
+int x2_optim_tail(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, int64_t n,
+                  float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, float ema_decay,
+                  float* step, float* norm_out, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

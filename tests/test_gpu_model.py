@@ -174,3 +174,54 @@ def test_rbf_readout_kernel_matches_composite(D, R, bias, deg):
     out2 = rbf_readout(dev["x"].detach(), dev["rbf"].detach(), dev["w"].detach(),
                        dev["b"].detach() if bias else None, rowptr_from_counts(cnt.cuda()))
     assert torch.equal(out2, out.detach())                      # deterministic
+
+
+def test_fused_optimizer_tail_matches_torch():
+    """x2_optim_tail (clip_grad_norm_ + Adam + EMA over flat buffers, two launches) against torch's own
+    clip_grad_norm_ / Adam / lerp on the same tensors, 6 updates, with and without clipping active."""
+    from x2gnn_b200.optim_tail import FusedTail
+    for max_norm in (100.0, 0.05):
+        torch.manual_seed(3)
+        shapes = [(128, 128), (128,), (42, 7), (1,), (338, 256)]
+        pa = [torch.nn.Parameter(torch.randn(*s, device="cuda") * 0.1) for s in shapes]
+        pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+        tail = FusedTail(pa, lr=1e-3, max_norm=max_norm, ema_decay=0.95)
+        opt = torch.optim.Adam(pb, lr=1e-3)
+        ema = [p.detach().clone() for p in pb]
+        g = torch.Generator(device="cuda").manual_seed(1)
+        for it in range(6):
+            grads = [torch.randn(*s, device="cuda", generator=g) * (1.0 + it) for s in shapes]
+            tail.zero_grad()
+            for p, gr in zip(pa, grads):
+                p.grad.add_(gr)                       # what autograd's in-place accumulation does
+            tail.step()
+            opt.zero_grad(set_to_none=True)
+            for p, gr in zip(pb, grads):
+                p.grad = gr.clone()
+            norm = torch.nn.utils.clip_grad_norm_(pb, max_norm=max_norm)
+            opt.step()
+            torch._foreach_lerp_(ema, [p.detach() for p in pb], 1.0 - 0.95)
+            assert float(tail.grad_norm) == pytest.approx(float(norm), rel=1e-6)
+        assert float(tail.step_count) == 6.0
+        for a, b in zip(pa, pb):
+            assert relerr(a, b) < 1e-6
+        for a, b in zip(tail.ema_views, ema):
+            assert relerr(a, b) < 1e-6
+        # the module's tensors are views of the flat buffers
+        assert pa[0].data_ptr() == tail.flat_p.data_ptr() and pa[0].grad.data_ptr() == tail.flat_g.data_ptr()
+
+
+def test_graphed_train_step_torch_tail_still_available():
+    from x2gnn_b200 import synth
+    from x2gnn_b200.train_graph import GraphedTrainStep
+    from x2gnn_b200.xgnn_model import XGNNPoly
+    hp = dict(conv_layers=1, sbf_dim=7, rbf_dim=6, in_channels=128, heads=16, embedding_size=128)
+    data = to_t(synth.qm9_batch(3, seed=2), device="cuda")
+    y = torch.linspace(-1, 1, 3, device="cuda")
+    losses = {}
+    for fused in (True, False):
+        torch.manual_seed(0)
+        net = XGNNPoly(**hp).cuda()
+        gs = GraphedTrainStep(net, data, y, lr=1e-3, warmup=2, fused_tail=fused)
+        losses[fused] = [float(gs.replay()) for _ in range(3)]
+    assert losses[True] == pytest.approx(losses[False], rel=2e-4)

@@ -21,6 +21,17 @@ import torch
 from . import ddp
 
 
+def fused_dense_step(model, tail, data, prep, y):
+    """The same update with the tail (all-reduce buffer, clip, Adam, EMA) in flat buffers and two launches
+    (optim_tail.FusedTail / x2_optim_tail) instead of ~300."""
+    tail.zero_grad()
+    loss = torch.nn.functional.smooth_l1_loss(model(data, prep), y)
+    loss.backward()
+    tail.allreduce()
+    tail.step()
+    return loss
+
+
 def dense_step(model, opt, params, data, prep, y, ema_params=None, ema_decay=0.95, bucket=None,
                max_norm=100.0):
     """The parameter-dependent part of one update, written with sync-free ops only (eager or under capture)."""
@@ -40,29 +51,43 @@ def dense_step(model, opt, params, data, prep, y, ema_params=None, ema_decay=0.9
 
 class GraphedTrainStep:
     def __init__(self, model, data: dict, y: torch.Tensor, lr: float = 1e-3, ema_decay: float = 0.95,
-                 bucket: "ddp.FlatGradBucket | None" = None, max_norm: float = 100.0, warmup: int = 3):
+                 bucket: "ddp.FlatGradBucket | None" = None, max_norm: float = 100.0, warmup: int = 3,
+                 fused_tail: bool = True):
+        """fused_tail: parameters / gradients / Adam moments / EMA in flat buffers, updated by x2_optim_tail (two
+        launches; the flat gradient is also the all-reduce buffer, `bucket` is then only a flag that the step is
+        data-parallel).  False: torch's capturable fused Adam + foreach clip / lerp, as in round 1."""
         dev = y.device
         if dev.type != "cuda":
             raise RuntimeError("GraphedTrainStep needs CUDA tensors (x2gnn_b200 has no CPU path)")
         self.model, self.data, self.y = model, data, y
         self.params = [p for p in model.parameters() if p.requires_grad]
-        # capturable: the step counters live on the device, so Adam's bias correction replays correctly
-        self.opt = torch.optim.Adam(self.params, lr=lr, fused=True, capturable=True)
-        self.ema_params = [p.detach().clone() for p in self.params]
         self.prep = model.prepare(data)          # index tensors + CSR metadata the graph will point at
         self.stream = torch.cuda.Stream(device=dev)
-        args = (model, self.opt, self.params, data, self.prep, y, self.ema_params, ema_decay, bucket, max_norm)
+        if fused_tail:
+            from .optim_tail import FusedTail
+            self.tail = FusedTail(self.params, lr=lr, max_norm=max_norm, ema_decay=ema_decay)
+            self.opt = None
+            self.ema_params = self.tail.ema_views
+            run = lambda: fused_dense_step(model, self.tail, data, self.prep, y)
+        else:
+            self.tail = None
+            # capturable: the step counters live on the device, so Adam's bias correction replays correctly
+            self.opt = torch.optim.Adam(self.params, lr=lr, fused=True, capturable=True)
+            self.ema_params = [p.detach().clone() for p in self.params]
+            args = (model, self.opt, self.params, data, self.prep, y, self.ema_params, ema_decay, bucket, max_norm)
+            run = lambda: dense_step(*args)
         self.stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(self.stream):     # scratch buffers and lazy tables are created per stream
             for _ in range(warmup):
-                dense_step(*args)
+                run()
         torch.cuda.current_stream(dev).wait_stream(self.stream)
         torch.cuda.synchronize(dev)
         self.warmup_updates = warmup
         self.graph = torch.cuda.CUDAGraph()
-        self.opt.zero_grad(set_to_none=True)
+        if self.opt is not None:
+            self.opt.zero_grad(set_to_none=True)
         with torch.cuda.graph(self.graph, stream=self.stream):
-            self.loss = dense_step(*args)
+            self.loss = run()
 
     def replay(self):
         self.graph.replay()

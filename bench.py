@@ -448,6 +448,61 @@ def parity_full_size_leg(dev, w, layer):
             "what": "layer fwd+bwd on the bench batch vs the fp64 oracle on this GPU, same weights"}
 
 
+def factorised_sbf_leg(dev, iters=20):
+    """SURVEY.md 8f row 2 (opt-in, sbftransformer_conv.USE_FACTORS / X2GNN_SGF=1): sbf produced by F_B_2D from the
+    bench batch's geometry carries its factors (per-bond radial table x Y_l0(angle)); the conv layer then evaluates
+    lin_sbf inside its block-centric attention kernels (csrc/blk_attn.cuh) and neither reads the [T, S] tensor nor
+    writes lin_sbf(sbf) / its gradient.  Layer forward + backward, CUDA events, same seed-0 batch; with edge_attr
+    [T, A] as in the reference and with the segment-constant table.  The dense path on the same F_B_2D tensor is
+    timed beside it (the factors are dropped by cloning the tensor)."""
+    import torch
+    import x2gnn_b200.sbftransformer_conv as sc
+    from x2gnn_b200 import synth
+    from x2gnn_b200.angular_basis_layer import F_B_2D
+    from x2gnn_b200.edge_graph import vertex_to_edge_2
+    D, H, S, R, A = (DIMS[k] for k in "DHSRA")
+    b = synth.qm9_batch(NMOL, seed=0)
+    ei = torch.from_numpy(b["edge_index"]).to(dev)
+    N = len(b["x"])
+    tri, aj, ai, ak = vertex_to_edge_2(ei, N)
+    pos = torch.from_numpy(b["atom_pos"]).to(dev)
+    d = (pos[ei[0]] - pos[ei[1]]).norm(dim=1)
+    ji, jk = pos[ai] - pos[aj], pos[ak] - pos[aj]
+    ang = torch.atan2(torch.linalg.cross(ji, jk).norm(dim=1), (ji * jk).sum(1))
+    sbf = F_B_2D(7, R, 5.0)(d, ang, tri[0])
+    E, T = int(ei.size(1)), int(tri.size(1))
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(E, D, device=dev, generator=g).requires_grad_(True)
+    rbf = (torch.rand(E, R, device=dev, generator=g) * 2 - 1).requires_grad_(True)
+    ea = torch.randn(T, A, device=dev, generator=g).requires_grad_(True)
+    tab = torch.randn(N, A, device=dev, generator=g).requires_grad_(True)
+    gout = torch.randn(E, D, device=dev, generator=g)
+    torch.manual_seed(0)
+    layer = sc.SBFTransformerConv(D, D // H, heads=H, sbf_dim=S, rbf_dim=R, edge_dim=A).to(dev)
+    params = list(layer.parameters())
+    res = {"E": E, "T": T, "what": "layer fwd+bwd ms per step on the seed-0 batch with sbf = F_B_2D(geometry)"}
+    old = sc.USE_FACTORS
+    try:
+        for name, kw, inp in (("edge_attr_TA", dict(edge_attr=ea), ea),
+                              ("edge_attr_table", dict(edge_attr=tab, edge_attr_index=ei[1].contiguous()), tab)):
+            for fact in (True, False):
+                sc.USE_FACTORS = fact
+                s_in = sbf if fact else sbf.clone()
+                before = sc.PLAN_COUNTS["factorised"]
+
+                def step():
+                    out = layer(s_in, rbf, x=x, edge_index=tri, **kw)
+                    torch.autograd.grad(out, [x, rbf, inp] + params, gout)
+                ms = _timed(step, iters, warmup=3)
+                took = sc.PLAN_COUNTS["factorised"] > before
+                res[f"{name}_{'factorised' if fact else 'dense'}_ms"] = round(ms, 4)
+                if fact and not took:
+                    res[f"{name}_factorised_ms"] = None
+    finally:
+        sc.USE_FACTORS = old
+    return res
+
+
 def ocelot_inference_leg(dev, iters=5):
     """BASELINE.json configs[2]: inference throughput on OCELOT-sized molecules -- here the real 60-146-atom
     geometries the reference ships (raw/AID_kcal.xyz, numeric fixture tests/golden/aid_geometries.npz), batches
@@ -931,6 +986,7 @@ def run_ours(args):
     if world == 1:
         for key, fn in (("parity_full_size", lambda: parity_full_size_leg(dev, w, layer)),
                         ("reference_on_gpu", lambda: reference_on_gpu_leg(dev, w)),
+                        ("factorised_sbf", lambda: factorised_sbf_leg(dev)),
                         ("ocelot_inference", lambda: ocelot_inference_leg(dev)),
                         ("ball500_sweep", lambda: ball500_sweep_leg(dev, peak))):
             try:

@@ -90,6 +90,20 @@ def test_f_b_2d_small_distances_and_sizes():
     assert empty.shape == (0, 42)
 
 
+def test_dimenet_radialbasis_twin():
+    """radial_basis_layer.py:6-17 `radialbasis` (unused by the model, kept importable): sqrt(2/c) sin(n pi r / c) / r
+    for one distance and for a column of distances, against the formula in fp64."""
+    import numpy as np
+    from x2gnn_b200 import radial_basis_layer as rbl
+    for r in (torch.tensor([1.3]), torch.linspace(0.8, 4.9, 37).unsqueeze(1)):
+        got = rbl.radialbasis(r.cuda(), 5.0, 6)
+        n = torch.arange(1, 7, dtype=torch.float64).unsqueeze(0)
+        rr = r.double().reshape(-1, 1)
+        want = (2 / 5.0) ** 0.5 * torch.sin(rr * n * np.pi / 5.0) / rr
+        assert got.shape == want.shape
+        assert float((got.cpu().double() - want).abs().max()) < 2e-6
+
+
 def test_angular_basis(golden):
     from x2gnn_b200 import angular_basis_layer as abl
     b = golden("bases")

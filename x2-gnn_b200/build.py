@@ -72,5 +72,36 @@ def build(force: bool = False, verbose: bool = True) -> str:
     return LIB
 
 
+def sass_summary(path: str = None) -> str:
+    """Counts of the Blackwell-specific SASS mnemonics per object (cuobjdump -sass): tcgen05 MMA (UTC*MMA), tensor
+    memory loads / stores (LDTM / STTM), tcgen05 commit barriers (UTCBAR), bulk copies (UBLKCP), cp.async (LDGSTS),
+    legacy tensor path (HMMA: must be 0).  Written to profiles/sass_summary.txt by `python build.py --sass`."""
+    import re
+    cuobjdump = os.path.join(os.path.dirname(_nvcc()), "cuobjdump")
+    pats = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "LDGSTS", "HMMA", "MUFU.EX2", "REDUX"]
+    lines = [f"# SASS mnemonic counts per object of libx2gnn.so (cuobjdump -sass, sm_100a; digest {_digest()[:16]})",
+             "# object      " + "  ".join(f"{p:>8s}" for p in pats)]
+    for src in SOURCES:
+        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        if not os.path.exists(obj):
+            continue
+        out = subprocess.run([cuobjdump, "-sass", obj], capture_output=True, text=True).stdout
+        cnt = []
+        for pat in pats:
+            if pat == "HMMA":       # the legacy mma.sync path, not the UTCHMMA substring
+                cnt.append(len(re.findall(r"(?<!UTC)HMMA", out)))
+            else:
+                cnt.append(out.count(pat))
+        lines.append(f"{os.path.basename(obj):13s} " + "  ".join(f"{c:8d}" for c in cnt))
+    text = "\n".join(lines) + "\n"
+    if path:
+        with open(path, "w") as f:
+            f.write(text)
+    return text
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    if "--sass" in sys.argv:
+        root = os.path.dirname(HERE) if "HERE" in globals() else os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        print(sass_summary(os.path.join(root, "profiles", "sass_summary.txt")))

@@ -47,8 +47,10 @@ def RadialBasis_func(bond_distances, cutoff=5.0, embedding_size=16):
 
 def radialbasis(r, cutoff, embedding_size):
     """DimeNet-style sqrt(2/c) sin(n pi r / c) / r (unused by the model; reference :6-17)."""
-    out = RadialBasis_func(r, cutoff, embedding_size)
-    return (2 / cutoff) ** 0.5 * out / r.unsqueeze(-1)
+    # the reference broadcasts r * n with n [1, embedding_size]: r is one distance ([1]) or a column ([num, 1])
+    rr = r.reshape(-1)
+    out = RadialBasis_func(rr, cutoff, embedding_size)
+    return (2 / cutoff) ** 0.5 * out / rr.unsqueeze(-1)
 
 
 class RadialBasis(nn.Module):

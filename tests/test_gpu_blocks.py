@@ -40,7 +40,7 @@ def test_blocks_of_a_molecule_batch_are_the_atoms():
     from x2gnn_b200 import graph_meta
     b, ei, N, tri, aj, ai, ak = _graph(5, seed=3)
     E = ei.size(1)
-    meta = graph_meta.build(tri, E)
+    meta = graph_meta.build(tri, E, want_blocks=True)
     blk = meta.blocks
     assert blk is not None and meta.target_sorted
     sptr, tptr, tord = blk.sptr.cpu().numpy(), blk.tptr.cpu().numpy(), blk.tord.cpu().numpy()
@@ -73,7 +73,7 @@ def test_blocks_rejected_or_valid_for_arbitrary_graphs():
     E, T = 300, 4000
     tgt = torch.sort(torch.randint(0, E, (T,), generator=g)).values
     src = torch.randint(0, E, (T,), generator=g)
-    meta = graph_meta.build(torch.stack([src, tgt]).cuda(), E)
+    meta = graph_meta.build(torch.stack([src, tgt]).cuda(), E, want_blocks=True)
     if meta.blocks is not None:        # random sources: essentially never closed, but if so it must be valid
         blk = meta.blocks
         sp = blk.sptr.cpu().numpy()
@@ -84,7 +84,7 @@ def test_blocks_rejected_or_valid_for_arbitrary_graphs():
             bt[to[tp[k]:tp[k + 1]]] = k
         assert np.array_equal(bs[src.numpy()], bt[tgt.numpy()])
     # unsorted targets: no blocks
-    meta2 = graph_meta.build(torch.stack([src, tgt.flip(0)]).cuda(), E)
+    meta2 = graph_meta.build(torch.stack([src, tgt.flip(0)]).cuda(), E, want_blocks=True)
     assert meta2.blocks is None
 
 

@@ -44,9 +44,17 @@ class LineGraphMeta:
     itemptr: torch.Tensor = None   # [E+1] int32
     items_bound: int = 0
     blocks: Blocks = None          # None: no closed-block structure (or not target-sorted): generic kernels only
+    blocks_tried: bool = False     # False: the blocks were not asked for when this record was built
 
 
-def build(edge_index: torch.Tensor, num_nodes: int) -> LineGraphMeta:
+import os
+
+# The closed blocks (x2_blocks_build) only serve the factorised lin_sbf kernels, which are opt-in (X2GNN_SGF=1 /
+# sbftransformer_conv.USE_FACTORS): they are built -- eight small launches -- only when asked for.
+WANT_BLOCKS = os.environ.get("X2GNN_SGF", "0") == "1"
+
+
+def build(edge_index: torch.Tensor, num_nodes: int, want_blocks: bool = None) -> LineGraphMeta:
     if edge_index.dim() != 2 or edge_index.size(0) != 2:
         raise ValueError(f"edge_index must be [2, T], got {tuple(edge_index.shape)}")
     if edge_index.dtype != torch.int64:
@@ -69,7 +77,9 @@ def build(edge_index: torch.Tensor, num_nodes: int) -> LineGraphMeta:
                                _lib.ptr(ws), ws.numel(), _lib.stream()), "x2_meta_build")
     # closed blocks (meaningful for a target-sorted list only; queued before the one host sync below)
     bflags = torch.zeros(6, **i32)
-    if T > 0 and E > 0:
+    if want_blocks is None:
+        want_blocks = WANT_BLOCKS
+    if want_blocks and T > 0 and E > 0:
         sptr = torch.empty(E + 1, **i32)
         tptr = torch.empty(E + 1, **i32)
         tord = torch.empty(E, **i32)
@@ -92,7 +102,8 @@ def build(edge_index: torch.Tensor, num_nodes: int) -> LineGraphMeta:
         ws2 = _lib.workspace(L.x2_items_workspace_bytes(E), dev)
         _lib.check(L.x2_items_build(_lib.ptr(rp_t), E, T, _lib.ptr(meta.itemptr), _lib.ptr(meta.items),
                                     _lib.ptr(ws2), ws2.numel(), _lib.stream()), "x2_items_build")
-    if meta.target_sorted and T > 0 and E > 0:
+    meta.blocks_tried = bool(want_blocks)
+    if want_blocks and meta.target_sorted and T > 0 and E > 0:
         ok, nb, mt, ms, mg = f[4:9]
         # a block is one CTA's work: keep the generic kernels when a few blocks hold most of the graph
         if ok and nb > 0 and mt <= MAX_BLOCK_TRIPLETS:
@@ -106,16 +117,16 @@ _cache: list = []   # [(weakref(edge_index), version, num_nodes, meta)], most re
 _CACHE_SIZE = 8
 
 
-def get(edge_index: torch.Tensor, num_nodes: int) -> LineGraphMeta:
+def get(edge_index: torch.Tensor, num_nodes: int, want_blocks: bool = False) -> LineGraphMeta:
     """Cached `build`: the same tensor object (unchanged `_version`) is passed to every conv
     layer of a forward pass (model.py:45), so the metadata is built once per batch."""
     ver = edge_index._version
     for i, (ref, v, n, meta) in enumerate(_cache):
-        if ref() is edge_index and v == ver and n == num_nodes:
+        if ref() is edge_index and v == ver and n == num_nodes and (meta.blocks_tried or not want_blocks):
             if i:
                 _cache.insert(0, _cache.pop(i))
             return meta
-    meta = build(edge_index, num_nodes)
+    meta = build(edge_index, num_nodes, want_blocks=want_blocks or WANT_BLOCKS)
     _cache.insert(0, (weakref.ref(edge_index), ver, num_nodes, meta))
     del _cache[_CACHE_SIZE:]
     return meta

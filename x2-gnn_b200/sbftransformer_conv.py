@@ -292,7 +292,9 @@ class SBFTransformerConv(nn.Module):
         if self.in_channels != self.heads * self.out_channels and isinstance(self.in_channels, int):
             raise NotImplementedError("SBFTransformerConv: in_channels must equal heads*out_channels")
         H, Cc = self.heads, self.out_channels
-        meta = graph_meta.get(edge_index, x.size(0))
+        # (the closed blocks of the line graph are only built when the factorised lin_sbf can use them)
+        meta = graph_meta.get(edge_index, x.size(0),
+                              want_blocks=USE_FACTORS and USE_BLOCKS and getattr(sbf, "_x2_factors", None) is not None)
         fuse = self.concat and self.root_weight and self.lin_beta is None
         p_drop = float(self.dropout) if self.training else 0.0
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0 else 0

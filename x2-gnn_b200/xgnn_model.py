@@ -213,7 +213,8 @@ class XGNNPoly(nn.Module):
                                if E == 0 or bool((ei0[1:] >= ei0[:-1]).all()) else None)
         # built here, found in the cache by the 4 layers (same tensor objects); referenced from `prep` so the
         # device buffers outlive the cache's eviction for as long as a captured graph points at them
-        prep["line_graph_meta"] = graph_meta.get(tri, E)
+        from . import sbftransformer_conv as _sc
+        prep["line_graph_meta"] = graph_meta.get(tri, E, want_blocks=_sc.USE_FACTORS and _sc.USE_BLOCKS)
         if self.segment_edge_attr:
             prep["edge_attr_groups"] = graph_meta.get_groups(prep["ei1"], N)
         return prep

@@ -926,7 +926,6 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
         const int64_t row0 = rbeg + ic * kChunkK;
         mbar_wait(&empty[ist], iph ^ 1);             // MMAs of the chunk that used this stage have retired
         tc_fence_after();
-        drain_if_due(ic);
         ++ic;
         const uint32_t sb = s_u + ist * stage_bytes;
         if (row0 + kChunkK <= rend) {
@@ -993,8 +992,13 @@ __global__ void __launch_bounds__(kG2Threads, 1) k_tc_wgrad(const G2Params p) {
         cp_async_commit();
       }
       for (int64_t c = 0; c < nchunks; ++c) {
-        if (c + AHEAD < nchunks) issue();
-        cp_async_commit();
+        if (c + AHEAD < nchunks) {
+          issue();
+          cp_async_commit();
+          drain_if_due(ic - 1);                      // after the copies are in flight: the drain overlaps them
+        } else {
+          cp_async_commit();
+        }
         cp_async_wait<AHEAD>();                      // this thread's copies of chunk c are complete
         consume();
       }

@@ -654,6 +654,64 @@ def e2e_from_atoms_leg(dev, world, rank, steps):
                     "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in pin.values()),
                     "d2h_bytes_per_step": h_pred.numel() * 4 + 4}
         del net, bufs
+    # ---- the same path through the repo's graphed training step (train_graph.GraphedTrainStep: forward, loss,
+    # backward, all-reduce, clip, Adam, EMA replayed as one CUDA graph).  Per step: pinned host -> the graph's
+    # static device buffers, radius graph + triplets + CSR metadata rebuilt eagerly from the copied atoms, one
+    # replay, predictions-free loss back to the host.  One buffer set: copy and compute do not overlap here.
+    try:
+        from x2gnn_b200.train_graph import GraphedTrainStep
+        from x2gnn_b200 import ddp
+        torch.manual_seed(0)
+        net = XGNNPoly(**HPARAMS).to(dev)
+        sbuf = {k: v.to(dev) for k, v in pin.items()}
+        ei0, _ = atom_graph.radius_graph(sbuf["atom_pos"], sbuf["batch"], 5.0)
+        data = {"x": sbuf["x"], "atom_pos": sbuf["atom_pos"], "edge_index": ei0, "edge_attr": sbuf["edge_attr"],
+                "edge_num": sbuf["edge_num"], "batch": sbuf["batch"], "num_graphs": B}
+        bucket = ddp.FlatGradBucket(net.parameters()) if world > 1 else None
+        gs = GraphedTrainStep(net, data, sbuf["y"], lr=1e-3, bucket=bucket)
+        h_loss = torch.empty(()).pin_memory()
+        same = [True]
+
+        def gstep():
+            with torch.no_grad():
+                for k in pin:
+                    sbuf[k].copy_(pin[k], non_blocking=True)
+                ei, _ = atom_graph.radius_graph(sbuf["atom_pos"], sbuf["batch"], 5.0)
+                p2 = net.prepare(dict(data, edge_index=ei))          # the integer work of this batch, every step
+                same[0] = same[0] and ei.shape == ei0.shape and p2["tri"].shape == gs.prep["tri"].shape
+                ei0.copy_(ei)
+            gs.replay()
+            h_loss.copy_(gs.loss.detach(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(3):
+            gstep()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            gstep()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            mx = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            ms = float(mx[0])
+        res["graphed_training_step"] = {
+            "ms_per_step": ms, "molecules_per_sec": world * NMOL / (ms * 1e-3), "loss": float(h_loss),
+            "same_layout_every_step": same[0],
+            "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in pin.values()), "d2h_bytes_per_step": 4,
+            "what": "full training step (segment-constant edge_attr table, the harness model's default): H2D into the "
+                    "graph's static buffers, radius graph + triplets + metadata eager, one CUDA-graph replay incl. "
+                    "optimizer, loss to the host"}
+        del net, gs
+    except Exception as exc:
+        res["graphed_training_step"] = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
     res["what"] = ("pinned host atoms + pair features -> device -> radius graph -> triplets -> bases -> 4 conv layers "
                    "(full harness model) forward + loss + backward -> predictions and loss on the host, per step")
     res["value"] = res["edge_attr_TA_as_in_the_reference"]["edge_messages_per_sec_4_layers"]

@@ -154,7 +154,9 @@ class _SBFConvFn(torch.autograd.Function):
         ea = torch.empty((max(n_ea, 1), D), **f32) if A else None
         sg = None if factorised else torch.empty((max(T, 1), D), **f32)   # factorised sbf: lin_sbf(sbf) is never stored
         xs = torch.empty((E, D), **f32)          # x * lin_rbf(rbf): kept so the backward does not recompute it
-        out = torch.empty((E, D), **f32) if fuse else attn
+        # (not the saved `attn` buffer itself when there is no fused skip add: a caller's in-place op on the layer
+        # output would silently corrupt the backward, which reads attn to form r = <G, O>)
+        out = torch.empty((E, D), **f32)
         alpha = torch.empty((T, H), **f32) if cfg["want_alpha"] else None
         saved = _lib.ConvSaved(_lib.ptr(qkvs), _lib.ptr(attn), _lib.ptr(lse), _lib.ptr(ea), _lib.ptr(sg),
                                _lib.ptr(xs))
@@ -297,6 +299,9 @@ class SBFTransformerConv(nn.Module):
                               want_blocks=USE_FACTORS and USE_BLOCKS and getattr(sbf, "_x2_factors", None) is not None)
         fuse = self.concat and self.root_weight and self.lin_beta is None
         p_drop = float(self.dropout) if self.training else 0.0
+        if p_drop > 0 and x.is_cuda and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("SBFTransformerConv: attention dropout inside a CUDA graph capture would replay one "
+                               "frozen mask (the seed is drawn on the host); capture with dropout = 0")
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0 else 0
         mode = default_mode(H * Cc) if self.precision is None else self.precision
         cfg = dict(heads=H, out_channels=Cc, mode=mode, dropout_p=p_drop, seed=seed,

@@ -503,6 +503,54 @@ def factorised_sbf_leg(dev, iters=20):
     return res
 
 
+def unchanged_reference_callers_leg(dev, iters=5):
+    """SURVEY.md 8(d) metric (ii) on the reference's OWN model code: the unmodified xgnn.py / model.py / readout.py /
+    residual_layer.py / atom_embedding.py (staged under baseline/_ref by __graft_entry__.build()) imported after
+    `x2gnn_b200.install()`, so that only their hot-path imports (SBFTransformerConv, F_B_2D, RadialBasis, poly_envelop,
+    vertex_to_edge_2) resolve to the sm_100a drop-in modules and their torch_geometric / torch_scatter imports to
+    compat/ (plain PyTorch on the GPU).  One training step as trainer.py:37-48 runs it (forward, SmoothL1, backward,
+    clip, Adam), batch 128, eager: edge_attr is the [T, A] gather of xgnn.py:57-58 and edgenn runs on T rows, as in
+    the reference."""
+    import importlib
+    import torch
+    import x2gnn_b200
+    from x2gnn_b200 import synth
+    root = os.path.dirname(os.path.abspath(__file__))
+    d = os.path.join(root, "baseline", "_ref")
+    if not os.path.exists(os.path.join(d, "xgnn.py")):
+        return {"unavailable": "baseline/_ref/xgnn.py not staged"}
+    callers = ("xgnn", "model", "readout", "residual_layer", "atom_embedding", "initializer")
+    x2gnn_b200.install()
+    sys.path.append(d)
+    for m in callers:
+        sys.modules.pop(m, None)
+    try:
+        xgnn = importlib.import_module("xgnn")
+        from torch_geometric.data import Data
+        torch.manual_seed(0)
+        net = xgnn.xgnn_poly(**HPARAMS, device=str(dev)).to(dev)
+        b = synth.qm9_batch(NMOL, seed=0)
+        data = Data(**{k: (torch.from_numpy(v).to(dev) if hasattr(v, "shape") else v) for k, v in b.items()})
+        y = torch.zeros(NMOL, device=dev)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.smooth_l1_loss(net(data), y)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=100.0)
+            opt.step()
+        ms = _timed(step, iters, warmup=3)
+        return {"ms_per_step": ms, "molecules_per_sec": NMOL / (ms * 1e-3),
+                "what": "unmodified reference xgnn_poly (baseline/_ref) over the drop-in modules + compat/, eager "
+                        "training step (forward, loss, backward, clip, Adam), batch 128, edge_attr [T, A] as in xgnn.py:57-58"}
+    finally:
+        sys.path.remove(d)
+        for m in callers:
+            sys.modules.pop(m, None)
+        x2gnn_b200.uninstall()
+
+
 def ocelot_inference_leg(dev, iters=5):
     """BASELINE.json configs[2]: inference throughput on OCELOT-sized molecules -- here the real 60-146-atom
     geometries the reference ships (raw/AID_kcal.xyz, numeric fixture tests/golden/aid_geometries.npz), batches
@@ -1045,6 +1093,7 @@ def run_ours(args):
         for key, fn in (("parity_full_size", lambda: parity_full_size_leg(dev, w, layer)),
                         ("reference_on_gpu", lambda: reference_on_gpu_leg(dev, w)),
                         ("factorised_sbf", lambda: factorised_sbf_leg(dev)),
+                        ("unchanged_reference_callers", lambda: unchanged_reference_callers_leg(dev)),
                         ("ocelot_inference", lambda: ocelot_inference_leg(dev)),
                         ("ball500_sweep", lambda: ball500_sweep_leg(dev, peak))):
             try:

@@ -757,6 +757,55 @@ def e2e_from_atoms_leg(dev, world, rank, steps):
             "what": "full training step (segment-constant edge_attr table, the harness model's default): H2D into the "
                     "graph's static buffers, radius graph + triplets + metadata eager, one CUDA-graph replay incl. "
                     "optimizer, loss to the host"}
+        # ---- the same step fed by the device-resident dataset (collate.DeviceDataset: the whole dataset uploaded
+        # once, a batch is a gather on the device -- x2_collate_sizes / x2_collate_fill -- instead of a host
+        # collation + a 58 MB copy); the batch is the same 128 molecules, so the captured graph applies
+        try:
+            import numpy as np
+            from x2gnn_b200.collate import DeviceDataset
+            an = np.concatenate([[0], np.cumsum(np.bincount(b["batch"], minlength=B))])
+            en = np.concatenate([[0], np.cumsum(b["edge_num"])])
+            mols = [{"x": b["x"][an[g]:an[g + 1]], "atom_pos": b["atom_pos"][an[g]:an[g + 1]],
+                     "edge_index": b["edge_index"][:, en[g]:en[g + 1]] - an[g],
+                     "edge_attr": b["edge_attr"][en[g]:en[g + 1]], "y": 0.0} for g in range(B)]
+            ds = DeviceDataset.from_molecules(mols, dev)
+            ids = torch.arange(B, device=dev)
+
+            def dstep():
+                with torch.no_grad():
+                    rec = ds.collate(ids)
+                    for k in ("x", "atom_pos", "batch", "edge_attr", "edge_num"):
+                        sbuf[k].copy_(rec[k])
+                    ei0.copy_(rec["edge_index"])
+                    net.prepare(dict(data, edge_index=rec["edge_index"]))
+                gs.replay()
+                h_loss.copy_(gs.loss.detach(), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+            for _ in range(3):
+                dstep()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                dstep()
+            e1.record()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            if world > 1:
+                mx = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                ms = float(mx[0])
+            res["graphed_training_step_device_dataset"] = {
+                "ms_per_step": ms, "molecules_per_sec": world * NMOL / (ms * 1e-3), "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 4,
+                "what": "as graphed_training_step, the batch gathered on the device from the resident dataset "
+                        "(device-side collation) instead of collated on the host and copied"}
+        except Exception as exc:
+            res["graphed_training_step_device_dataset"] = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
         del net, gs
     except Exception as exc:
         res["graphed_training_step"] = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}

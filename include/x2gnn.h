@@ -328,6 +328,22 @@ int x2_optim_tail(float* param, const float* grad, float* exp_avg, float* exp_av
                   float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, float ema_decay,
                   float* step, float* norm_out, void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------- device-side batch collation
+ * (the reference collates PyG records of qm9_allprop.py:18 on the host).  The dataset of M
+ * molecules lives on the device in CSR form: atoms of molecule m = rows atom_ptr[m] .. atom_ptr[m+1] of z_all [Na] i64 /
+ * pos_all [Na,3] f32, its bonds = rows edge_ptr[m] .. edge_ptr[m+1] of feat_all [Ea,F] f32 and (optional) columns of
+ * ei_all [2,Ea] i64 with LOCAL atom ids.  ids [B] i64 selects the batch.
+ *   x2_collate_sizes: aoff[B+1], eoff[B+1] int32 exclusive offsets (totals in the last entries); flags[0] = ids out of range
+ *   x2_collate_fill : z[N], pos[N,3], batch[N], edge_num[B], feat[E,F], edge_index[2,E] (global ids; NULL to skip) */
+size_t x2_collate_workspace_bytes(int64_t B);
+int x2_collate_sizes(const int64_t* ids, int64_t B, const int64_t* atom_ptr, const int64_t* edge_ptr, int64_t M,
+                     int32_t* aoff, int32_t* eoff, int32_t* flags, void* ws, size_t ws_bytes, void* stream);
+int x2_collate_fill(const int64_t* ids, int64_t B, int64_t M, const int64_t* atom_ptr, const int64_t* edge_ptr,
+                    const int64_t* z_all, const float* pos_all, const float* feat_all, int32_t F,
+                    const int64_t* ei_all, int64_t Etot_all, const int32_t* aoff, const int32_t* eoff, int64_t* z,
+                    float* pos, int64_t* batch, int64_t* edge_num, float* feat, int64_t* edge_index, int64_t E_total,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

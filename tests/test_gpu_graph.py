@@ -147,3 +147,43 @@ def test_line_graph_meta(mods):
         graph_meta.build(torch.tensor([[0, E], [0, 0]], device="cuda"), E)
     # cache: same tensor object -> same meta object
     assert graph_meta.get(tri, E) is graph_meta.get(tri, E)
+
+
+def test_device_side_collation_matches_host_collation():
+    """x2gnn_b200.collate.DeviceDataset (x2_collate_sizes / x2_collate_fill) against the host collation of the same
+    molecules in the same order (PyG semantics: concatenation, per-graph atom offset on edge_index, batch ids,
+    edge_num) -- bit-exact; repeated and permuted ids; the collated record runs through the harness model."""
+    import numpy as np
+    from x2gnn_b200 import synth
+    from x2gnn_b200.collate import DeviceDataset
+    rng = np.random.default_rng(5)
+    mols = []
+    for i in range(12):
+        pos, z = synth.synth_mol(int(rng.integers(3, 25)), rng)
+        ei = synth.radius_edges(pos)
+        mols.append({"x": z, "atom_pos": pos.astype(np.float32), "edge_index": ei,
+                     "edge_attr": rng.normal(size=(ei.shape[1], 338)).astype(np.float32) * 0.1, "y": float(i)})
+    ds = DeviceDataset.from_molecules(mols, "cuda")
+    for ids in ([3, 1, 7], [0], [11, 11, 2, 5, 5], list(range(12))):
+        got = ds.collate(ids)
+        off, xs, ps, eis, fs, bt, en = 0, [], [], [], [], [], []
+        for g, m in enumerate(mols[i] for i in ids):
+            xs.append(m["x"]); ps.append(m["atom_pos"]); fs.append(m["edge_attr"]); eis.append(m["edge_index"] + off)
+            bt.append(np.full(len(m["x"]), g)); en.append(m["edge_index"].shape[1]); off += len(m["x"])
+        assert torch.equal(got["x"].cpu(), torch.from_numpy(np.concatenate(xs)).long())
+        assert torch.equal(got["atom_pos"].cpu(), torch.from_numpy(np.concatenate(ps)))
+        assert torch.equal(got["edge_attr"].cpu(), torch.from_numpy(np.concatenate(fs)))
+        assert torch.equal(got["edge_index"].cpu(), torch.from_numpy(np.concatenate(eis, axis=1)).long())
+        assert torch.equal(got["batch"].cpu(), torch.from_numpy(np.concatenate(bt)).long())
+        assert got["edge_num"].cpu().tolist() == en and got["num_graphs"] == len(ids)
+        assert got["y"].cpu().tolist() == [float(i) for i in ids]
+    with pytest.raises(IndexError):
+        ds.collate([0, 12])
+    # the stored bonds are the radius graph of the collated atoms (lexicographic, as gen_bonds_mini produces them)
+    from x2gnn_b200 import atom_graph
+    got = ds.collate([4, 9, 2])
+    ei2, en2 = atom_graph.radius_graph(got["atom_pos"], got["batch"], 5.0)
+    assert torch.equal(ei2, got["edge_index"]) and torch.equal(en2, got["edge_num"])
+    from x2gnn_b200.xgnn_model import XGNNPoly
+    net = XGNNPoly(conv_layers=1, sbf_dim=7, rbf_dim=6, in_channels=128, heads=16, embedding_size=128).cuda()
+    assert torch.isfinite(net(got)).all()

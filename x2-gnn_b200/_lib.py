@@ -102,6 +102,10 @@ SIGNATURES = {
     "x2_sbfconv_fwd": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(ConvSaved), _P, _P, _P, _SZ, _P]),
     "x2_sbfconv_bwd": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(ConvSaved), _P, C.POINTER(ConvGrads),
                                  _P, _SZ, _P]),
+    "x2_collate_workspace_bytes": (_SZ, [_I64]),
+    "x2_collate_sizes": (C.c_int, [_P, _I64, _P, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
+    "x2_collate_fill": (C.c_int, [_P, _I64, _I64, _P, _P, _P, _P, _P, _I32, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P,
+                                  _I64, _P]),
     "x2_optim_workspace_bytes": (_SZ, [_I64]),
     "x2_optim_tail": (C.c_int, [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _F, _P, _P, _P, _SZ, _P]),
     "x2_graph_layernorm_fwd": (C.c_int, [_P, _P, _I64, _I32, _F, _P, _P, _P]),

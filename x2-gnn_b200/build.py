@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libx2gnn.so")
-SOURCES = ["api.cu", "graph.cu", "basis.cu", "conv.cu", "norm.cu", "readout.cu", "optim.cu"]
+SOURCES = ["api.cu", "graph.cu", "basis.cu", "conv.cu", "norm.cu", "readout.cu", "optim.cu", "collate.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

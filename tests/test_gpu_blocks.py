@@ -216,3 +216,72 @@ def test_factors_are_dropped_when_they_do_not_apply():
                               return_attention_weights=True)
     assert alpha.shape == (rec["edge_index"].size(1), DIMS[1])
     assert sc.PLAN_COUNTS["factorised"] == before + 1
+
+
+def _random_blocked_graph(seed, nblocks=40, with_gaps=True):
+    """A target-sorted line graph made of closed blocks that are NOT molecule-shaped: block b owns a contiguous run of
+    source nodes and an arbitrary set of target nodes; every target's segment is a sorted subset of its block's
+    sources (with consecutive sources present somewhere, so that the block hangs together), some targets and some
+    sources are unused."""
+    rng = np.random.default_rng(seed)
+    E = 0
+    blocks = []
+    for _ in range(nblocks):
+        ns = int(rng.integers(1, 12))
+        blocks.append((E, ns))
+        E += ns
+    extra = int(rng.integers(0, 5))            # line-nodes that are never a source of anything
+    E += extra
+    tgt_of_block = np.array_split(rng.permutation(E), nblocks)      # every node is a target of some block
+    src, tgt = [], []
+    for (s0, ns), tg in zip(blocks, tgt_of_block):
+        first = True
+        for e in tg:
+            if with_gaps and rng.random() < 0.15 and not first:
+                continue                                            # empty segment
+            if first:
+                seg = np.arange(ns)                                 # one full segment links the block's sources
+                first = False
+            else:
+                seg = np.flatnonzero(rng.random(ns) < 0.6)
+            for k in seg:
+                src.append(s0 + k)
+                tgt.append(int(e))
+    src, tgt = np.array(src), np.array(tgt)
+    order = np.lexsort((src, tgt))
+    return torch.from_numpy(np.stack([src[order], tgt[order]])).long(), E
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_factorised_sbf_on_arbitrary_closed_blocks(seed):
+    """Nothing in the block kernels assumes a molecule: random closed blocks (segments = arbitrary subsets of a block's
+    sources, empty segments, unused sources, nT != nS), factors supplied by hand, against the dense path."""
+    import x2gnn_b200.sbftransformer_conv as sc
+    from x2gnn_b200 import graph_meta
+    from x2gnn_b200.angular_basis_layer import SbfFactors
+    ei, E = _random_blocked_graph(seed)
+    ei = ei.cuda()
+    T = ei.size(1)
+    meta = graph_meta.build(ei, E, want_blocks=True)
+    assert meta.blocks is not None and meta.target_sorted
+    D, H, S, R, A = DIMS
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    table = torch.randn(E, S, device="cuda", generator=g)
+    ang = torch.rand(T, device="cuda", generator=g) * 3.1
+    from x2gnn_b200 import _lib
+    sbf = torch.empty(T, S, device="cuda")
+    _lib.check(_lib.lib().x2_sbf_fwd(_lib.ptr(table), _lib.ptr(ang), _lib.ptr(ei[0].contiguous()), T, E, 7, 6,
+                                     _lib.ptr(sbf), _lib.stream()), "x2_sbf_fwd")
+    sbf._x2_factors = SbfFactors(table, ang, ei[0], 7, 6, sbf._version)
+    rec = dict(x=torch.randn(E, D, device="cuda", generator=g), rbf=torch.rand(E, R, device="cuda", generator=g),
+               edge_attr=torch.randn(T, A, device="cuda", generator=g), edge_index=ei,
+               grad_out=torch.randn(E, D, device="cuda", generator=g))
+    layer = _layer(seed=seed)
+    before = sc.PLAN_COUNTS["factorised"]
+    o_f, g_f = _step(layer, rec, sbf)
+    assert sc.PLAN_COUNTS["factorised"] == before + 1
+    o_d, g_d = _step(layer, rec, sbf.clone())
+    assert relerr(o_f, o_d) < FP32_TOL
+    for k in g_d:
+        if k != "lin_key.bias":
+            assert relerr(g_f[k], g_d[k]) < 2 * FP32_TOL, k

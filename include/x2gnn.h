@@ -13,6 +13,7 @@
  *   x2_radial_fwd / _bwd         replace  radial_basis_layer.py:36-40 (RadialBasis.forward) + autograd
  *   x2_sbf_table / x2_sbf_fwd    replace  angular_basis_layer.py:80-93 (F_B_2D.forward)
  *   x2_angular_fwd               replaces angular_basis_layer.py:28-32 (AngularBasisLayer.forward)
+ *   x2_envelope_bwd / x2_angular_bwd / x2_sbf_bwd   autograd of those three w.r.t. distances / angles
  *   x2_meta_*                    CSR metadata of the line graph (replaces what PyG's
  *                                propagate/softmax/scatter derive from edge_index,
  *                                sbftransformer_conv.py:109,151)
@@ -167,6 +168,22 @@ int x2_sbf_fwd(const float* table, const float* angles, const int64_t* idx, int6
                int32_t L, int32_t R, float* out, void* stream);
 /* angular_basis_layer.py:28-32: out[t,l] = Y_l0(angles[t]). */
 int x2_angular_fwd(const float* angles, int64_t T, int32_t L, float* out, void* stream);
+/* Gradients of the three expansions w.r.t. the geometry.  The reference's bases are torch expressions
+ * (envelop.py:16-21, angular_basis_layer.py:28-32,80-93), so its autograd differentiates them w.r.t. distances
+ * and angles (e.g. forces = -dE/dpos); these are the analytic derivatives of the same formulas, E-scale parts
+ * in fp64 like the forward, deterministic (no atomics).
+ *   x2_envelope_bwd : grad_d[i] = grad_out[i] u'(d_i inv_cutoff) inv_cutoff
+ *   x2_angular_bwd  : grad_angles[t] = sum_l grad_out[t,l] dY_l0/dtheta(angles[t])
+ *   x2_sbf_bwd      : grad_angles[T] and / or grad_d[E] (either may be NULL) of x2_sbf_fwd(x2_sbf_table(d), ..)
+ *                     given grad_out[T, L R]; grad_d needs the triplets grouped by idx: order[T] (stable sort of
+ *                     idx), rowptr[E+1].  L R <= 256. */
+int x2_envelope_bwd(const float* d, const float* grad_out, int64_t n, float inv_cutoff, int32_t p, float a, float b,
+                    float c, float* grad_d, void* stream);
+int x2_angular_bwd(const float* angles, const float* grad_out, int64_t T, int32_t L, float* grad_angles, void* stream);
+int x2_sbf_bwd(const float* d, const float* table, const float* angles, const int64_t* idx, const int64_t* order,
+               const int64_t* rowptr, const float* grad_out, int64_t T, int64_t E, int32_t L, int32_t R,
+               const float* zeros, const float* norm, float cutoff, float env_cutoff, int32_t p, float a, float b,
+               float c, float* grad_d, float* grad_angles, void* stream);
 
 /* ---------------------------------------------------------------- tensor-core Linear building blocks
  * tcgen05 (kind::tf32) GEMMs in 3xTF32 split precision (fp32-accurate), used inside x2_sbfconv_* for

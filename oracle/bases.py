@@ -67,9 +67,28 @@ def bessel_normalizers(zeros: np.ndarray) -> np.ndarray:
     return np.asarray(out)
 
 
+class _SphericalJl(torch.autograd.Function):
+    """j_l(x) through scipy in float64 with its derivative (scipy's spherical_jn(derivative=True)), so that the
+    oracle is differentiable w.r.t. the distances exactly where the reference's lambdified torch closed forms are."""
+
+    @staticmethod
+    def forward(ctx, x, l):
+        ctx.save_for_backward(x)
+        ctx.l = l
+        return torch.from_numpy(sp.spherical_jn(l, x.detach().double().numpy())).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, go):
+        (x,) = ctx.saved_tensors
+        dj = torch.from_numpy(sp.spherical_jn(ctx.l, x.detach().double().numpy(), derivative=True)).to(x.dtype)
+        return go * dj, None
+
+
 def spherical_jl(l: int, x: torch.Tensor) -> torch.Tensor:
     """j_l(x) through scipy in float64 -- mathematically identical to the closed forms
-    of basis_func.py:32-44."""
+    of basis_func.py:32-44 (differentiable, see _SphericalJl)."""
+    if x.requires_grad:
+        return _SphericalJl.apply(x, l)
     return torch.from_numpy(sp.spherical_jn(l, x.detach().double().numpy()))
 
 

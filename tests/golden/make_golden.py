@@ -114,6 +114,23 @@ def main():
         bs[f"zeros_{L}_{R}"] = torch.from_numpy(basis_func.Jn_zeros(L, R))
     ab = angular_basis_layer.AngularBasisLayer(7)
     bs["cbf_7_f64"] = ab(ang.double())
+    # gradients w.r.t. the geometry: autograd through the reference's own (lambdified torch) expressions, fp64
+    gg = torch.Generator().manual_seed(2)
+    dd = d.double().requires_grad_(True)
+    go_e = torch.randn(E, generator=gg, dtype=torch.float64)
+    bs["env_go"] = go_e
+    bs["env_gd_f64"] = torch.autograd.grad(env(dd), dd, go_e)[0]
+    for (L, R) in ((7, 6), (3, 4)):
+        fb = angular_basis_layer.F_B_2D(L, R, 5.0, 5)
+        dd = d.double().requires_grad_(True)
+        aa = ang.double().requires_grad_(True)
+        go_s = torch.randn(T, L * R, generator=gg, dtype=torch.float64)
+        gd, ga = torch.autograd.grad(fb(dd, aa, src), (dd, aa), go_s)
+        bs[f"sbf_{L}_{R}_go"], bs[f"sbf_{L}_{R}_gd_f64"], bs[f"sbf_{L}_{R}_gang_f64"] = go_s, gd, ga
+    aa = ang.double().requires_grad_(True)
+    go_c = torch.randn(T, 7, generator=gg, dtype=torch.float64)
+    bs["cbf_7_go"] = go_c
+    bs["cbf_7_gang_f64"] = torch.autograd.grad(ab(aa), aa, go_c)[0]
     out["bases"] = bs
 
     # ---------------------------------------------------------------- conv layer

@@ -90,6 +90,73 @@ def test_f_b_2d_small_distances_and_sizes():
     assert empty.shape == (0, 42)
 
 
+
+@pytest.mark.parametrize("LR", [(7, 6), (3, 4)])
+def test_geometry_gradients_golden(golden, LR):
+    """x2_sbf_bwd / x2_envelope_bwd / x2_angular_bwd against autograd through the reference's own expressions in
+    fp64 (golden), 1e-5 relative; deterministic (the by-bond sum has a fixed order)."""
+    from x2gnn_b200 import angular_basis_layer as abl, envelop
+    b = golden("bases")
+    L, R = LR
+    layer = abl.F_B_2D(L, R, 5.0, 5)
+    go = b[f"sbf_{L}_{R}_go"].float().cuda()
+    res = []
+    for _ in range(2):
+        d = b["d"].cuda().requires_grad_(True)
+        a = b["angles"].cuda().requires_grad_(True)
+        out = layer(d, a, b["src"].cuda())
+        assert getattr(out, "_x2_factors", None) is None        # the conv must read (and differentiate) the tensor
+        res.append(torch.autograd.grad(out, (d, a), go))
+    assert relerr(out, b[f"sbf_{L}_{R}_f64"]) < 1e-6
+    assert relerr(res[0][0], b[f"sbf_{L}_{R}_gd_f64"]) < 1e-5
+    assert relerr(res[0][1], b[f"sbf_{L}_{R}_gang_f64"]) < 1e-5
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    # only one of the two requested
+    d = b["d"].cuda().requires_grad_(True)
+    (gd,) = torch.autograd.grad(layer(d, b["angles"].cuda(), b["src"].cuda()), d, go)
+    assert torch.equal(gd, res[0][0])
+    a = b["angles"].cuda().requires_grad_(True)
+    (ga,) = torch.autograd.grad(layer(b["d"].cuda(), a, b["src"].cuda()), a, go)
+    assert torch.equal(ga, res[0][1])
+    if LR == (7, 6):
+        d = b["d"].cuda().requires_grad_(True)
+        (ge,) = torch.autograd.grad(envelop.poly_envelop(5.0, 5)(d), d, b["env_go"].float().cuda())
+        assert relerr(ge, b["env_gd_f64"]) < 1e-5
+        a = b["angles"].cuda().requires_grad_(True)
+        (gc,) = torch.autograd.grad(abl.AngularBasisLayer(7)(a), a, b["cbf_7_go"].float().cuda())
+        assert relerr(gc, b["cbf_7_gang_f64"]) < 1e-5
+
+
+def test_geometry_gradients_vs_oracle_sizes():
+    """Small distances (power-series branch of j_l and j_l'), the poles of Y_l0, bonds with no triplet, class-default
+    and wide bases, against the fp64 oracle."""
+    from x2gnn_b200 import angular_basis_layer as abl
+    gen = torch.Generator().manual_seed(5)
+    d0 = torch.cat([torch.tensor([0.05, 0.2, 0.5, 0.94]), 0.9 + 4.1 * torch.rand(300, generator=gen)])
+    T = 2000 + 13
+    ang0 = math.pi * torch.rand(T, generator=gen)
+    ang0[:3] = torch.tensor([0.0, math.pi, math.pi / 2])
+    src = torch.randint(0, d0.numel() - 20, (T,), generator=gen)       # the last 20 bonds are no triplet's source
+    for L, R in ((7, 6), (7, 16), (16, 3), (8, 32)):
+        go = torch.randn(T, L * R, generator=gen)
+        d = d0.cuda().requires_grad_(True)
+        a = ang0.cuda().requires_grad_(True)
+        gd, ga = torch.autograd.grad(abl.F_B_2D(L, R, 5.0, 5)(d, a, src.cuda()), (d, a), go.cuda())
+        d64 = d0.double().requires_grad_(True)
+        a64 = ang0.double().requires_grad_(True)
+        rd, ra = torch.autograd.grad(obases.f_b_2d(d64, a64, src, L, R), (d64, a64), go.double())
+        # the four small-d bonds have gradients 1e3..1e6 times the others: each on its own scale, the rest together
+        gdc = gd.cpu().double()
+        assert relerr(gdc[4:], rd[4:]) < 1e-5, (L, R)
+        for i in range(4):
+            assert abs(float(gdc[i] - rd[i])) < 1e-4 * abs(float(rd[i])), (L, R, i)
+        assert relerr(ga, ra) < 1e-5, (L, R)
+        assert float(gd[-20:].abs().max()) == 0.0
+    with pytest.raises(Exception):
+        d = d0.cuda().requires_grad_(True)
+        torch.autograd.grad(abl.F_B_2D(16, 32, 5.0, 5)(d, ang0.cuda(), src.cuda()).sum(), d)   # L R = 512 > 256
+
+
 def test_dimenet_radialbasis_twin():
     """radial_basis_layer.py:6-17 `radialbasis` (unused by the model, kept importable): sqrt(2/c) sin(n pi r / c) / r
     for one distance and for a column of distances, against the formula in fp64."""

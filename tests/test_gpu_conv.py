@@ -146,6 +146,47 @@ def test_variants(kw):
     _compare(ref, mine, _graph_inputs(3, dims, seed=4))
 
 
+
+@pytest.mark.parametrize("shape", [(48, 2, 16), (16, 1, 16), (24, 3, 8), (200, 16, 8), (64, 4, 8), ((40, 40), 4, 8)])
+@pytest.mark.parametrize("kw", [dict(), dict(concat=False), dict(root_weight=False)])
+def test_shapes_outside_the_kernel_widths(shape, kw):
+    """Reference ctor generality (sbftransformer_conv.py:19,47-48): in_channels != heads*out_channels, widths the
+    kernels are not instantiated for, and a (equal) tuple in_channels run zero-padded at the next kernel width
+    (sbftransformer_conv.padded_width) and must match the UNPADDED fp64 oracle on every output and gradient."""
+    from x2gnn_b200.sbftransformer_conv import SBFTransformerConv
+    in_ch, H, Cc = shape
+    S, R, A = 10, 3, 20
+    width = in_ch if isinstance(in_ch, int) else in_ch[0]
+    torch.manual_seed(7)
+    ref = oconv.OracleSBFTransformerConv(width, Cc, heads=H, sbf_dim=S, rbf_dim=R, edge_dim=A, **kw)
+    with torch.no_grad():
+        for p in ref.parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.2, 0.2)
+    mine = SBFTransformerConv(in_ch, Cc, heads=H, sbf_dim=S, rbf_dim=R, edge_dim=A, **kw)
+    assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.cuda()
+    rec = _graph_inputs(3, (width, H, S, R, A), seed=8)
+    n_out = H * Cc if kw.get("concat", True) else Cc
+    rec["grad_out"] = torch.randn(rec["x"].size(0), n_out, generator=torch.Generator().manual_seed(9))
+    _compare(ref.double(), mine, rec)
+    for k, p in mine.named_parameters():          # gradients have the PARAMETERS' shapes, not the padded ones
+        assert p.grad is None or p.grad.shape == p.shape, k
+
+
+def test_unsupported_shape_raises():
+    from x2gnn_b200.sbftransformer_conv import SBFTransformerConv
+    c = SBFTransformerConv(24, 24, heads=1, sbf_dim=4, rbf_dim=2).cuda()          # out_channels not a power of two
+    x = torch.randn(4, 24, device="cuda")
+    ei = torch.tensor([[0, 1, 2], [1, 2, 3]], device="cuda")
+    with pytest.raises(NotImplementedError):
+        c(torch.randn(3, 4, device="cuda"), torch.randn(4, 2, device="cuda"), x=x, edge_index=ei)
+    with pytest.raises(ValueError):                                                  # x of the wrong width
+        SBFTransformerConv(32, 8, heads=4, sbf_dim=4, rbf_dim=2).cuda()(
+            torch.randn(3, 4, device="cuda"), torch.randn(4, 2, device="cuda"), x=x, edge_index=ei)
+
+
 @pytest.mark.parametrize("heads", [8, 16])       # D = 64 and D = 128 (the latter: staged forward kernel)
 def test_no_edge_dim(heads):
     from x2gnn_b200.sbftransformer_conv import SBFTransformerConv

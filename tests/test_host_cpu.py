@@ -197,3 +197,55 @@ def test_post_conv_entry_points_validate_and_refuse_cpu():
         graph_norm.graph_layer_norm_rows(torch.zeros(5, 8), rp)
     with pytest.raises(_lib.X2Error):
         readout_sum.rbf_readout(torch.zeros(5, 128), torch.zeros(5, 6), torch.zeros(128, 6), None, rp)
+
+
+def test_padded_width_embedding_is_exact_on_the_oracle():
+    """SBFTransformerConv.padded_width: a layer whose in_channels / heads*out_channels the kernels are not
+    instantiated for (reference ctor, sbftransformer_conv.py:19,47-48) is run zero-padded at the next kernel width.
+    Here the SAME padding is applied to the CPU oracle in fp64: outputs, attention weights and every gradient of the
+    padded layer, sliced, must equal the unpadded layer's (that is the exactness claim; the GPU test then checks the
+    kernels at the padded width against the unpadded oracle)."""
+    import torch.nn.functional as F
+    from oracle import conv as oconv
+    from x2gnn_b200 import sbftransformer_conv as sc
+
+    assert sc.padded_width(128, 16, 8) == 128 and sc.padded_width(256, 16, 16) == 256
+    assert sc.padded_width(48, 2, 16) == 64 and sc.padded_width(16, 1, 16) == 32
+    assert sc.padded_width(200, 16, 8) == 256 and sc.padded_width(24, 3, 8) == 32
+    assert sc.padded_width(300, 16, 8) is None and sc.padded_width(24, 1, 24) is None   # too wide / C not 2^k
+
+    torch.manual_seed(0)
+    in_ch, H, C, S, R, A = 24, 3, 8, 5, 3, 7
+    Dp = sc.padded_width(in_ch, H, C)
+    Hk = Dp // C
+    ref = oconv.OracleSBFTransformerConv(in_ch, C, heads=H, sbf_dim=S, rbf_dim=R, edge_dim=A).double()
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in ref.state_dict().items()}
+    E, T = 9, 40
+    g = torch.Generator().manual_seed(1)
+    ei = torch.stack([torch.randint(0, E, (T,), generator=g), torch.randint(0, E, (T,), generator=g).sort().values])
+    x, rbf, sbf, ea = (torch.randn(n, w, generator=g, dtype=torch.float64).requires_grad_(True)
+                       for n, w in ((E, in_ch), (E, R), (T, S), (T, A)))
+    gout = torch.randn(E, H * C, generator=g, dtype=torch.float64)
+
+    o0, a0 = oconv.sbfconv_forward(p, sbf, rbf, x, ei, ea, heads=H, out_channels=C)
+    leaves = [x, rbf, sbf, ea] + list(p.values())
+    g0 = torch.autograd.grad(o0, leaves, gout, allow_unused=True)
+
+    pp = {}
+    for k, v in p.items():
+        if k == "lin_rbf.weight":
+            pp[k] = sc._pad2(v, Dp, v.size(1))
+        elif k in ("lin_edge.weight", "lin_sbf.weight"):
+            pp[k] = sc._pad2(v, Dp, v.size(1))
+        elif v.dim() == 2:
+            pp[k] = sc._pad2(v, Dp, Dp)
+        else:
+            pp[k] = sc._pad1(v, Dp)
+    o1, a1 = oconv.sbfconv_forward(pp, sbf, rbf, F.pad(x, (0, Dp - in_ch)), ei, ea, heads=Hk, out_channels=C)
+    o1, a1 = o1[:, :H * C], a1[:, :H]
+    g1 = torch.autograd.grad(o1, leaves, gout, allow_unused=True)
+    assert torch.allclose(o0, o1, rtol=0, atol=1e-13) and torch.allclose(a0, a1, rtol=0, atol=1e-14)
+    for u, v in zip(g0, g1):
+        assert (u is None) == (v is None)
+        if u is not None:
+            assert torch.allclose(u, v, rtol=0, atol=1e-12)

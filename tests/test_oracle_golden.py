@@ -78,6 +78,25 @@ def test_f_b_2d_vs_reference_fp64(golden, LR):
     assert err32 < 5e-4
 
 
+
+@pytest.mark.parametrize("LR", [(7, 6), (3, 4)])
+def test_basis_gradients_vs_reference_autograd(golden, LR):
+    """d / d(distance) and d / d(angle) of the oracle's expansions against autograd through the REFERENCE's own
+    lambdified expressions in fp64 (tests/golden/make_golden.py): the oracle's j_l' comes from scipy."""
+    _rel = lambda x, y: float((x - y).abs().max() / y.abs().max())
+    b = golden("bases")
+    L, R = LR
+    d = b["d"].double().requires_grad_(True)
+    a = b["angles"].double().requires_grad_(True)
+    gd, ga = torch.autograd.grad(bases.f_b_2d(d, a, b["src"], L, R), (d, a), b[f"sbf_{L}_{R}_go"])
+    assert _rel(gd, b[f"sbf_{L}_{R}_gd_f64"]) < 1e-7      # (float32-rounded zeros / normalisers in both)
+    assert _rel(ga, b[f"sbf_{L}_{R}_gang_f64"]) < 1e-7
+    d = b["d"].double().requires_grad_(True)
+    assert _rel(torch.autograd.grad(bases.poly_envelop(d, 5.0, 5), d, b["env_go"])[0], b["env_gd_f64"]) < 1e-12
+    a = b["angles"].double().requires_grad_(True)
+    assert _rel(torch.autograd.grad(bases.angular_basis(a, 7), a, b["cbf_7_go"])[0], b["cbf_7_gang_f64"]) < 1e-12
+
+
 def test_angular_basis(golden):
     b = golden("bases")
     assert torch.allclose(bases.angular_basis(b["angles"].double(), 7), b["cbf_7_f64"], atol=1e-12)

@@ -92,6 +92,10 @@ SIGNATURES = {
     "x2_sbf_table": (C.c_int, [_P, _I64, _I32, _I32, _P, _P, _F, _F, _I32, _F, _F, _F, _P, _P]),
     "x2_sbf_fwd": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _I32, _P, _P]),
     "x2_angular_fwd": (C.c_int, [_P, _I64, _I32, _P, _P]),
+    "x2_envelope_bwd": (C.c_int, [_P, _P, _I64, _F, _I32, _F, _F, _F, _P, _P]),
+    "x2_angular_bwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
+    "x2_sbf_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _F, _F, _I32, _F, _F, _F,
+                             _P, _P, _P]),
     "x2_tc_gemm_workspace_bytes": (_SZ, [_I32, _I32]),
     "x2_tc_gemm": (C.c_int, [_P, _I64, _I64, _I32, _P, _I64, _I64, _I32, _P, _P, _I64, _I32, _P, _SZ, _P]),
     "x2_tc_wgrad_workspace_bytes": (_SZ, [_I64, _I32]),

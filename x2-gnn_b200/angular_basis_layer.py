@@ -17,20 +17,40 @@ from .basis_func import bessel_tables
 from .envelop import _coeffs
 
 
-def _no_grad_inputs(name, *ts):
-    if torch.is_grad_enabled() and any(t.requires_grad for t in ts):
-        raise NotImplementedError(f"{name}: gradients w.r.t. distances/angles are not implemented "
-                                  "(the reference training graph never needs them)")
-
-
-def _angular(angles: torch.Tensor, L: int) -> torch.Tensor:
-    _no_grad_inputs("AngularBasisLayer", angles)
-    a = _lib.f32(angles, "AngularBasisLayer")
+def _angular_fwd(a, L):
     dev = _lib.require_cuda(a, what="AngularBasisLayer")
     out = torch.empty((a.numel(), L), dtype=torch.float32, device=dev)
     _lib.check(_lib.lib().x2_angular_fwd(_lib.ptr(a), a.numel(), L, _lib.ptr(out), _lib.stream()),
                "x2_angular_fwd")
     return out
+
+
+class _AngularFn(torch.autograd.Function):
+    """Y_l0(theta) with its derivative w.r.t. theta (the reference's expression is differentiable by autograd,
+    angular_basis_layer.py:28-32; needed as soon as a loss is differentiated w.r.t. positions)."""
+
+    @staticmethod
+    def forward(ctx, angles, L):
+        a = _lib.f32(angles, "AngularBasisLayer").reshape(-1)
+        ctx.save_for_backward(a)
+        ctx.L, ctx.shape = L, angles.shape
+        return _angular_fwd(a, L)
+
+    @staticmethod
+    def backward(ctx, go):
+        (a,) = ctx.saved_tensors
+        go = _lib.f32(go, "AngularBasisLayer.backward")
+        _lib.require_cuda(a, go, what="AngularBasisLayer.backward")
+        ga = torch.empty_like(a)
+        _lib.check(_lib.lib().x2_angular_bwd(_lib.ptr(a), _lib.ptr(go), a.numel(), ctx.L, _lib.ptr(ga),
+                                             _lib.stream()), "x2_angular_bwd")
+        return ga.view(ctx.shape), None
+
+
+def _angular(angles: torch.Tensor, L: int) -> torch.Tensor:
+    if torch.is_grad_enabled() and angles.requires_grad:
+        return _AngularFn.apply(angles, L)
+    return _angular_fwd(_lib.f32(angles, "AngularBasisLayer"), L)
 
 
 class AngularBasisLayer(nn.Module):
@@ -108,11 +128,11 @@ class F_B_2D(nn.Module):
                                            _lib.ptr(table), _lib.stream()), "x2_sbf_table")
         return table
 
-    def forward(self, d, Angles, edge_index_1):
-        _no_grad_inputs("F_B_2D", d, Angles)
-        table = self.radial_table(d)
-        ang = _lib.f32(Angles, "F_B_2D")
-        idx = edge_index_1.long().contiguous()
+    def _tables(self, dev):
+        zeros, norm = _device_tables(self.num_spherical, self.num_radial, dev)
+        return zeros, norm, _coeffs(self.envelope_exponent)
+
+    def _expand(self, table, ang, idx):
         dev = _lib.require_cuda(ang, idx, table, what="F_B_2D")
         T = ang.numel()
         if idx.numel() != T:
@@ -124,5 +144,54 @@ class F_B_2D(nn.Module):
         out = torch.empty((T, L * R), dtype=torch.float32, device=dev)
         _lib.check(_lib.lib().x2_sbf_fwd(_lib.ptr(table), _lib.ptr(ang), _lib.ptr(idx), T, E, L, R,
                                          _lib.ptr(out), _lib.stream()), "x2_sbf_fwd")
-        out._x2_factors = SbfFactors(table, ang, edge_index_1, L, R, out._version)
         return out
+
+    def forward(self, d, Angles, edge_index_1):
+        idx = edge_index_1.long().contiguous()
+        if torch.is_grad_enabled() and (d.requires_grad or Angles.requires_grad):
+            # differentiable w.r.t. the geometry, like the reference's lambdified torch expressions (:80-93); the
+            # U0 training graph never takes this branch (sbf does not require grad)
+            # (no `_x2_factors` tag: the conv must read the tensor itself, whose gradient it then owes)
+            return _SbfFn.apply(self, d, Angles, idx)
+        table = self.radial_table(d)
+        ang = _lib.f32(Angles, "F_B_2D")
+        out = self._expand(table, ang, idx)
+        out._x2_factors = SbfFactors(table, ang, edge_index_1, self.num_spherical, self.num_radial, out._version)
+        return out
+
+
+class _SbfFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, d, angles, idx):
+        d_ = _lib.f32(d, "F_B_2D").reshape(-1)
+        ang = _lib.f32(angles, "F_B_2D").reshape(-1)
+        table = mod.radial_table(d_)
+        out = mod._expand(table, ang, idx)
+        ctx.save_for_backward(d_, ang, idx, table)
+        ctx.mod, ctx.d_shape, ctx.a_shape = mod, d.shape, angles.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        d_, ang, idx, table = ctx.saved_tensors
+        mod = ctx.mod
+        L, R = mod.num_spherical, mod.num_radial
+        T, E = ang.numel(), d_.numel()
+        go = _lib.f32(go, "F_B_2D.backward")
+        dev = _lib.require_cuda(d_, ang, idx, table, go, what="F_B_2D.backward")
+        zeros, norm, (p, a, b, c) = mod._tables(dev)
+        need_d, need_a = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        gd = torch.empty(E, dtype=torch.float32, device=dev) if need_d else None
+        ga = torch.empty(T, dtype=torch.float32, device=dev) if need_a else None
+        order = rowptr = None
+        if need_d:            # the triplets grouped by source bond, in a fixed (stable) order: deterministic sum
+            order = torch.sort(idx.clamp(0, max(E - 1, 0)), stable=True).indices.contiguous()
+            rowptr = torch.zeros(E + 1, dtype=torch.int64, device=dev)
+            if T:
+                rowptr[1:] = torch.bincount(idx.clamp(0, max(E - 1, 0)), minlength=E).cumsum(0)
+        _lib.check(_lib.lib().x2_sbf_bwd(
+            _lib.ptr(d_), _lib.ptr(table), _lib.ptr(ang), _lib.ptr(idx), _lib.ptr(order), _lib.ptr(rowptr),
+            _lib.ptr(go), T, E, L, R, _lib.ptr(zeros), _lib.ptr(norm), float(mod.cutoff),
+            float(mod.envelope_cutoff), p, a, b, c, _lib.ptr(gd), _lib.ptr(ga), _lib.stream()), "x2_sbf_bwd")
+        return (None, gd.view(ctx.d_shape) if gd is not None else None,
+                ga.view(ctx.a_shape) if ga is not None else None, None)

@@ -236,6 +236,145 @@ __global__ void k_angular_fwd(const float* __restrict__ angles, int64_t T, int L
   y_l0((double)angles[t], L, out + t * L, 1);
 }
 
+// ------------------------------------------------------------------ gradients w.r.t. the geometry
+// The reference's bases are plain torch expressions (sympy-lambdified closures), so autograd differentiates them
+// w.r.t. distances and angles (force training differentiates the energy w.r.t. positions through them).  The
+// kernels below are the analytic derivatives of the same formulas, E-scale parts in fp64 like the forward.
+
+// u'(x) of envelop.py:16-21: -1/x^2 + (p-1) a x^(p-2) + x^(p-1) (p b + (p+1) c x)
+__device__ __forceinline__ double envelope_dx(double x, int p, double a, double b, double c) {
+  double xp = 1.0;  // x^(p-2)   (p >= 2; for p = 1 the a-term is constant and drops out)
+  for (int i = 0; i < p - 2; ++i) xp *= x;
+  const double xp1 = p >= 2 ? xp * x : 1.0;   // x^(p-1)
+  const double t_a = p >= 2 ? (double)(p - 1) * a * xp : 0.0;
+  return -1.0 / (x * x) + t_a + xp1 * ((double)p * b + (double)(p + 1) * c * x);
+}
+
+__global__ void k_envelope_bwd(const float* __restrict__ d, const float* __restrict__ go, int64_t n,
+                               float inv_cutoff, int p, float a, float b, float c, float* __restrict__ gd) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float xs = d[i] * inv_cutoff;
+  gd[i] = (float)((double)go[i] * envelope_dx((double)xs, p, (double)a, (double)b, (double)c) * (double)inv_cutoff);
+}
+
+// d/dtheta Y_l0(theta) = -sin(theta) sqrt((2l+1)/(4 pi)) P_l'(cos theta), P_l' = P_{l-2}' + (2l-1) P_{l-1}
+// (no division by 1 - c^2: regular at the poles).  Lane l of the calling warp gets its own order.
+__device__ __forceinline__ void y_l0_and_dtheta(double theta, int l, double* y, double* dy) {
+  double s, c;
+  sincos(theta, &s, &c);
+  double p0 = 1.0, p1 = c, q0 = 0.0, q1 = 1.0;     // P_0, P_1, P_0', P_1'
+  double P = l == 0 ? p0 : p1, Q = l == 0 ? q0 : q1;
+  for (int j = 2; j <= l; ++j) {
+    const double pj = ((double)(2 * j - 1) * c * p1 - (double)(j - 1) * p0) / (double)j;
+    const double qj = q0 + (double)(2 * j - 1) * p1;
+    p0 = p1; p1 = pj; q0 = q1; q1 = qj;
+    P = pj; Q = qj;
+  }
+  const double nrm = sqrt((double)(2 * l + 1) * 0.07957747154594767);
+  *y = nrm * P;
+  *dy = -s * nrm * Q;
+}
+
+__global__ void k_angular_bwd(const float* __restrict__ angles, const float* __restrict__ go, int64_t T, int L,
+                              float* __restrict__ gang) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const double th = (double)angles[t];
+  double acc = 0.0;
+  for (int l = 0; l < L; ++l) {
+    double y, dy;
+    y_l0_and_dtheta(th, l, &y, &dy);
+    acc += (double)go[t * L + l] * dy;
+  }
+  gang[t] = (float)acc;
+}
+
+constexpr int kSbfBwdWarps = 8;       // warps per block of the two sbf gradient kernels
+constexpr int kSbfBwdMaxS = 256;      // L R of the gradient kernels (8 column slots per lane)
+
+// d sbf / d theta: one warp per triplet.  g_theta[t] = sum_col go[t, col] table[idx[t], col] Y_l'(theta_t)
+__global__ void __launch_bounds__(kSbfBwdWarps * 32)
+k_sbf_bwd_theta(const float* __restrict__ table, const float* __restrict__ angles, const int64_t* __restrict__ idx,
+                const float* __restrict__ go, int64_t T, int64_t E, int L, int R, float* __restrict__ gang) {
+  __shared__ float dys[kSbfBwdWarps][kMaxL];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * kSbfBwdWarps + w;
+  if (t >= T) return;
+  const int S = L * R;
+  if (lane < L) {
+    double y, dy;
+    y_l0_and_dtheta((double)angles[t], lane, &y, &dy);
+    dys[w][lane] = (float)dy;
+  }
+  __syncwarp();
+  int64_t r = idx[t];
+  r = (r < 0 || r >= E) ? 0 : r;
+  const float* trow = table + r * S;
+  const float* grow = go + t * S;
+  float acc = 0.f;
+  for (int col = lane; col < S; col += 32) acc += grow[col] * __ldg(trow + col) * dys[w][col / R];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) gang[t] = acc;
+}
+
+// d sbf / d d: one warp per bond e, its triplets (order[rowptr[e] .. rowptr[e+1])) in a fixed order =>
+// deterministic, no atomics.  g_table[e, col] = sum_t go[t, col] Y_l(theta_t), then
+// g_d[e] = sum_col g_table[e, col] d table[e, col] / d d, with
+// d table / d d = N (u'(d / c_env) / c_env j_l(x) + u(d / c_env) j_l'(x) z / cutoff),  x = z d / cutoff,
+// j_l' = j_{l-1} - (l + 1) / x j_l  (j_0' = -j_1), all fp64.
+__global__ void __launch_bounds__(kSbfBwdWarps * 32)
+k_sbf_bwd_d(const float* __restrict__ d, const float* __restrict__ angles, const int64_t* __restrict__ order,
+            const int64_t* __restrict__ rowptr, const float* __restrict__ go, int64_t E, int L, int R,
+            const float* __restrict__ zeros, const float* __restrict__ norm, float cutoff, float env_cutoff, int p,
+            float a, float b, float c, float* __restrict__ gd) {
+  __shared__ float ys[kSbfBwdWarps][kMaxL];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * kSbfBwdWarps + w;
+  if (e >= E) return;
+  const int S = L * R;
+  float acc[kSbfBwdMaxS / 32];
+#pragma unroll
+  for (int j = 0; j < kSbfBwdMaxS / 32; ++j) acc[j] = 0.f;
+  for (int64_t k = rowptr[e]; k < rowptr[e + 1]; ++k) {
+    const int64_t t = order[k];
+    __syncwarp();
+    if (lane < L) {
+      double y, dy;
+      y_l0_and_dtheta((double)angles[t], lane, &y, &dy);
+      ys[w][lane] = (float)y;
+    }
+    __syncwarp();
+    const float* grow = go + t * S;
+#pragma unroll
+    for (int j = 0; j < kSbfBwdMaxS / 32; ++j) {
+      const int col = lane + 32 * j;
+      if (col < S) acc[j] += grow[col] * ys[w][col / R];
+    }
+  }
+  const double dd = (double)d[e];
+  const double xe = dd / (double)env_cutoff;
+  const double env = envelope_d(dd, 1.0 / (double)env_cutoff, p, (double)a, (double)b, (double)c);
+  const double denv = envelope_dx(xe, p, (double)a, (double)b, (double)c) / (double)env_cutoff;
+  double g = 0.0;
+#pragma unroll
+  for (int j = 0; j < kSbfBwdMaxS / 32; ++j) {
+    const int col = lane + 32 * j;
+    if (col < S) {
+      const int l = col / R;
+      const double zc = (double)zeros[col] / (double)cutoff;
+      const double x = zc * dd;
+      const double jl = sph_jl(l, x);
+      const double djl = l == 0 ? -sph_jl(1, x) : sph_jl(l - 1, x) - (double)(l + 1) / x * jl;
+      g += (double)acc[j] * (double)norm[col] * (denv * jl + env * djl * zc);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+  if (lane == 0) gd[e] = (float)g;
+}
+
 }  // namespace x2
 
 using namespace x2;
@@ -319,6 +458,48 @@ int x2_angular_fwd(const float* angles, int64_t T, int32_t L, float* out, void* 
   if (T == 0) return X2_OK;
   k_angular_fwd<<<(unsigned)cdiv(T, 256), 256, 0, (cudaStream_t)stream>>>(angles, T, L, out);
   X2_LAUNCH_OK();
+  return X2_OK;
+}
+
+// ---- gradients w.r.t. distances / angles (autograd of the reference's torch expressions; force training)
+int x2_envelope_bwd(const float* d, const float* grad_out, int64_t n, float inv_cutoff, int32_t p, float a, float b,
+                    float c, float* grad_d, void* stream) {
+  X2_CHECK_ARG(n >= 0 && p >= 1, "x2_envelope_bwd: bad arguments");
+  if (n == 0) return X2_OK;
+  k_envelope_bwd<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(d, grad_out, n, inv_cutoff, p, a, b, c, grad_d);
+  X2_LAUNCH_OK();
+  return X2_OK;
+}
+
+int x2_angular_bwd(const float* angles, const float* grad_out, int64_t T, int32_t L, float* grad_angles, void* stream) {
+  X2_CHECK_ARG(T >= 0 && L >= 1 && L <= kMaxL, "x2_angular_bwd: need 1<=L<=%d", kMaxL);
+  if (T == 0) return X2_OK;
+  k_angular_bwd<<<(unsigned)cdiv(T, 256), 256, 0, (cudaStream_t)stream>>>(angles, grad_out, T, L, grad_angles);
+  X2_LAUNCH_OK();
+  return X2_OK;
+}
+
+// grad_angles [T] and / or grad_d [E] of sbf = x2_sbf_fwd(x2_sbf_table(d), angles, idx) given grad_out [T, L R].
+// order [T] / rowptr [E + 1]: the triplets grouped by idx (stable), needed for grad_d only.
+int x2_sbf_bwd(const float* d, const float* table, const float* angles, const int64_t* idx, const int64_t* order,
+               const int64_t* rowptr, const float* grad_out, int64_t T, int64_t E, int32_t L, int32_t R,
+               const float* zeros, const float* norm, float cutoff, float env_cutoff, int32_t p, float a, float b,
+               float c, float* grad_d, float* grad_angles, void* stream) {
+  X2_CHECK_ARG(T >= 0 && E >= 0 && L >= 1 && L <= kMaxL && R >= 1 && R <= 64 && L * R <= kSbfBwdMaxS,
+               "x2_sbf_bwd: need 1<=L<=%d, 1<=R<=64, L*R<=%d", kMaxL, kSbfBwdMaxS);
+  X2_CHECK_ARG(!grad_d || (order && rowptr), "x2_sbf_bwd: grad_d needs the triplets grouped by idx (order, rowptr)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (grad_angles && T > 0) {
+    k_sbf_bwd_theta<<<(unsigned)cdiv(T, kSbfBwdWarps), kSbfBwdWarps * 32, 0, st>>>(table, angles, idx, grad_out, T, E,
+                                                                                 L, R, grad_angles);
+    X2_LAUNCH_OK();
+  }
+  if (grad_d && E > 0) {
+    k_sbf_bwd_d<<<(unsigned)cdiv(E, kSbfBwdWarps), kSbfBwdWarps * 32, 0, st>>>(d, angles, order, rowptr, grad_out, E, L,
+                                                                             R, zeros, norm, cutoff, env_cutoff, p, a,
+                                                                             b, c, grad_d);
+    X2_LAUNCH_OK();
+  }
   return X2_OK;
 }
 

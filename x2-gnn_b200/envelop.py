@@ -13,16 +13,41 @@ def _coeffs(exponent: int):
     return p, -(p + 1) * (p + 2) / 2, p * (p + 2), -p * (p + 1) / 2
 
 
-def _envelope(d: torch.Tensor, inv_cutoff: float, p: int, a: float, b: float, c: float):
-    if d.requires_grad and torch.is_grad_enabled():
-        raise NotImplementedError("poly_envelop: gradients w.r.t. distances are not implemented "
-                                  "(the reference training graph never needs them)")
-    x = _lib.f32(d, "poly_envelop")
+def _envelope_fwd(x, inv_cutoff, p, a, b, c):
     dev = _lib.require_cuda(x, what="poly_envelop")
     out = torch.empty_like(x)
     _lib.check(_lib.lib().x2_envelope_fwd(_lib.ptr(x), x.numel(), inv_cutoff, p, a, b, c, _lib.ptr(out),
                                           _lib.stream()), "x2_envelope_fwd")
     return out
+
+
+class _EnvelopeFn(torch.autograd.Function):
+    """Differentiable w.r.t. the distances like the reference's torch expression (envelop.py:16-21): the U0 training
+    graph never asks for it, force training (dE/dpos) does."""
+
+    @staticmethod
+    def forward(ctx, d, inv_cutoff, p, a, b, c):
+        x = _lib.f32(d, "poly_envelop")
+        ctx.save_for_backward(x)
+        ctx.args = (inv_cutoff, p, a, b, c)
+        return _envelope_fwd(x, inv_cutoff, p, a, b, c)
+
+    @staticmethod
+    def backward(ctx, go):
+        (x,) = ctx.saved_tensors
+        inv_cutoff, p, a, b, c = ctx.args
+        go = _lib.f32(go, "poly_envelop.backward")
+        _lib.require_cuda(x, go, what="poly_envelop.backward")
+        gd = torch.empty_like(x)
+        _lib.check(_lib.lib().x2_envelope_bwd(_lib.ptr(x), _lib.ptr(go), x.numel(), inv_cutoff, p, a, b, c,
+                                              _lib.ptr(gd), _lib.stream()), "x2_envelope_bwd")
+        return gd, None, None, None, None, None
+
+
+def _envelope(d: torch.Tensor, inv_cutoff: float, p: int, a: float, b: float, c: float):
+    if d.requires_grad and torch.is_grad_enabled():
+        return _EnvelopeFn.apply(d, inv_cutoff, p, a, b, c)
+    return _envelope_fwd(_lib.f32(d, "poly_envelop"), inv_cutoff, p, a, b, c)
 
 
 class poly_envelop(nn.Module):

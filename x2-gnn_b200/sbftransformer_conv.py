@@ -59,6 +59,37 @@ def Glorot_Ortho_(tensor: Tensor, scale: float = 2.0) -> Tensor:
     return tensor
 
 
+_NATIVE_D = (32, 64, 128, 256)     # heads*out_channels the kernels are instantiated for (csrc/conv.cu check_desc)
+
+
+def _native_c(Dp: int, Cc: int) -> bool:
+    """csrc/conv.cu check_desc: a lane owns D/32 consecutive channels and a head is a power-of-two group of lanes."""
+    vec = Dp // 32
+    return Cc % vec == 0 and ((Cc // vec) & (Cc // vec - 1)) == 0 and Cc // vec <= 32 and Dp % Cc == 0
+
+
+def padded_width(in_ch: int, H: int, Cc: int):
+    """Width D' >= max(in_channels, heads*out_channels) the kernels run at (None: no such width).  The reference's
+    constructor (sbftransformer_conv.py:19,47-48) takes any in_channels / heads / out_channels; the kernels take
+    x [E, D'] with D' = H'*C in {32, 64, 128, 256}.  Other shapes are embedded EXACTLY: x and the weights are
+    zero-padded (extra input channels contribute 0 to every projection; extra heads have Q = K = V = EA = 0, so their
+    logits are 0, their messages 0 and their output columns 0) and the first heads*out_channels columns of the
+    result are returned.  The padding and the slice are differentiable torch ops, so every gradient is that of the
+    unpadded layer."""
+    for Dp in _NATIVE_D:
+        if Dp >= max(in_ch, H * Cc) and _native_c(Dp, Cc):
+            return Dp
+    return None
+
+
+def _pad2(w, rows: int, cols: int):
+    return w if w is None or (w.size(0) == rows and w.size(1) == cols) else F.pad(w, (0, cols - w.size(1), 0, rows - w.size(0)))
+
+
+def _pad1(b, n: int):
+    return b if b is None or b.size(0) == n else F.pad(b, (0, n - b.size(0)))
+
+
 def _set_groups(desc, groups):
     if groups is None:
         desc.ea_rows, desc.ea_index, desc.ea_rowptr, desc.ea_order = 0, None, None, None
@@ -291,9 +322,20 @@ class SBFTransformerConv(nn.Module):
             raise TypeError("SBFTransformerConv: edge_index must be a [2, T] LongTensor")
         if self.lin_edge is not None and edge_attr is None:
             raise AssertionError("edge_attr is required when edge_dim is set")
-        if self.in_channels != self.heads * self.out_channels and isinstance(self.in_channels, int):
-            raise NotImplementedError("SBFTransformerConv: in_channels must equal heads*out_channels")
         H, Cc = self.heads, self.out_channels
+        in_ch = self.in_channels if isinstance(self.in_channels, int) else self.in_channels[0]
+        if not isinstance(self.in_channels, int) and self.in_channels[0] != self.in_channels[1]:
+            # (x_src = x * lin_rbf(rbf) and lin_query(x) take the same Tensor x in the reference, :98-107)
+            raise ValueError("SBFTransformerConv: a Tensor `x` needs in_channels[0] == in_channels[1]")
+        if x.dim() != 2 or x.size(1) != in_ch:
+            raise ValueError(f"SBFTransformerConv: x must be [E, {in_ch}], got {tuple(x.shape)}")
+        Dp = padded_width(in_ch, H, Cc)
+        if Dp is None:
+            raise NotImplementedError(
+                f"SBFTransformerConv: no kernel width for in_channels={in_ch}, heads={H}, out_channels={Cc} "
+                "(need max(in_channels, heads*out_channels) <= 256 and out_channels a power of two; INTEGRATION.md)")
+        Hk = Dp // Cc                              # heads the kernels see (H, or H + zero heads when padded)
+        padded = Dp != in_ch or Dp != H * Cc
         # (the closed blocks of the line graph are only built when the factorised lin_sbf can use them)
         meta = graph_meta.get(edge_index, x.size(0),
                               want_blocks=USE_FACTORS and USE_BLOCKS and getattr(sbf, "_x2_factors", None) is not None)
@@ -303,8 +345,8 @@ class SBFTransformerConv(nn.Module):
             raise RuntimeError("SBFTransformerConv: attention dropout inside a CUDA graph capture would replay one "
                                "frozen mask (the seed is drawn on the host); capture with dropout = 0")
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0 else 0
-        mode = default_mode(H * Cc) if self.precision is None else self.precision
-        cfg = dict(heads=H, out_channels=Cc, mode=mode, dropout_p=p_drop, seed=seed,
+        mode = default_mode(Dp) if self.precision is None else self.precision
+        cfg = dict(heads=Hk, out_channels=Cc, mode=mode, dropout_p=p_drop, seed=seed,
                    want_alpha=isinstance(return_attention_weights, bool))
         if edge_attr_index is not None and self.lin_edge is not None:
             cfg["ea_groups"] = graph_meta.get_groups(edge_attr_index, edge_attr.size(0))
@@ -316,16 +358,29 @@ class SBFTransformerConv(nn.Module):
                                 or not fac.describes(sbf, edge_index)):
             fac = None
         cfg["sbf_factors"] = fac
-        out, alpha = _SBFConvFn.apply(
-            cfg, meta, x, rbf, sbf, edge_attr if self.lin_edge is not None else None,
-            self.lin_rbf.weight, self.lin_query.weight, self.lin_query.bias, self.lin_key.weight,
-            self.lin_key.bias, self.lin_value.weight, self.lin_value.bias,
-            self.lin_edge.weight if self.lin_edge is not None else None, self.lin_sbf.weight,
-            self.lin_sbf.bias, self.lin_skip.weight if fuse else None,
-            self.lin_skip.bias if fuse else None)
+        w_e = self.lin_edge.weight if self.lin_edge is not None else None
+        w_o, b_o = (self.lin_skip.weight, self.lin_skip.bias) if fuse else (None, None)
+        if not padded:
+            out, alpha = _SBFConvFn.apply(
+                cfg, meta, x, rbf, sbf, edge_attr if self.lin_edge is not None else None,
+                self.lin_rbf.weight, self.lin_query.weight, self.lin_query.bias, self.lin_key.weight,
+                self.lin_key.bias, self.lin_value.weight, self.lin_value.bias, w_e, self.lin_sbf.weight,
+                self.lin_sbf.bias, w_o, b_o)
+        else:      # exact zero-padded embedding into the kernels' width (padded_width above)
+            out, alpha = _SBFConvFn.apply(
+                cfg, meta, F.pad(x, (0, Dp - in_ch)), rbf, sbf, edge_attr if self.lin_edge is not None else None,
+                _pad2(self.lin_rbf.weight, Dp, self.lin_rbf.weight.size(1)), _pad2(self.lin_query.weight, Dp, Dp),
+                _pad1(self.lin_query.bias, Dp), _pad2(self.lin_key.weight, Dp, Dp), _pad1(self.lin_key.bias, Dp),
+                _pad2(self.lin_value.weight, Dp, Dp), _pad1(self.lin_value.bias, Dp),
+                _pad2(w_e, Dp, w_e.size(1)) if w_e is not None else None,
+                _pad2(self.lin_sbf.weight, Dp, self.lin_sbf.weight.size(1)), _pad1(self.lin_sbf.bias, Dp),
+                _pad2(w_o, Dp, Dp), _pad1(b_o, Dp))
+            out = out[:, :H * Cc]
+            if alpha is not None:
+                alpha = alpha[:, :H]
         if not fuse:
             # composite tail for the non-default variants (CUDA torch ops, still no CPU path)
-            out = out.view(-1, H * Cc) if self.concat else out.view(-1, H, Cc).mean(dim=1)
+            out = out.reshape(-1, H * Cc) if self.concat else out.reshape(-1, H, Cc).mean(dim=1)
             if self.root_weight:
                 x_r = self.lin_skip(x)
                 if self.lin_beta is not None:

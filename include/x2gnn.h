@@ -200,6 +200,19 @@ int x2_tc_gemm(const float* A, int64_t lda, int64_t M, int32_t K, const float* W
 size_t x2_tc_wgrad_workspace_bytes(int64_t rows, int32_t N);
 int x2_tc_wgrad(const float* Y, int64_t ldy, const float* X, int64_t ldx, int64_t rows, int32_t N, float* dW,
                 int64_t lddw, float* db, void* ws, size_t ws_bytes, void* stream);
+/* Several weight gradients over the same `rows` and N in as few launches as possible (16 problems per k_tc_wgrad
+ * launch, the CTAs dealt over the problems).  A training step defers the weight gradients of its torch.nn.Linear
+ * layers (residual_layer.py, readout.py, model.py:16-20 around the conv layers) to the end of the backward and
+ * flushes them through this entry point: nothing downstream of a Linear's backward needs dW before the optimizer.
+ * Same workspace bound as x2_tc_wgrad. */
+typedef struct {
+  const float* Y; int64_t ldy;     /* grad of the Linear's output block [rows, 128] */
+  const float* X; int64_t ldx;     /* the Linear's input block [rows, N] */
+  float* dW; int64_t lddw;         /* [128, N] block of weight.grad */
+  float* db;                       /* [128] block of bias.grad or NULL */
+} x2_wgrad_job;
+int x2_tc_wgrad_batch(const x2_wgrad_job* jobs, int32_t njobs, int64_t rows, int32_t N, void* ws, size_t ws_bytes,
+                      void* stream);
 
 /* ---------------------------------------------------------------- SBFTransformerConv
  * Shapes: x[E,D] rbf[E,R] sbf[T,S] edge_attr[T,A] (A=0 => no lin_edge); D = H*C.

@@ -225,3 +225,58 @@ def test_graphed_train_step_torch_tail_still_available():
         gs = GraphedTrainStep(net, data, y, lr=1e-3, warmup=2, fused_tail=fused)
         losses[fused] = [float(gs.replay()) for _ in range(3)]
     assert losses[True] == pytest.approx(losses[False], rel=2e-4)
+
+
+def test_deferred_weight_gradients_match_the_immediate_ones():
+    """tc_linear.DeferredWgrads / x2_tc_wgrad_batch: the TCLinear weight gradients of one backward computed together at
+    the end, straight into the optimizer's flat buffer, against the per-layer x2_tc_wgrad launches through autograd
+    (and both against fp64 autograd of the same stack): every gradient, 1e-5 relative."""
+    from x2gnn_b200.optim_tail import FusedTail
+    from x2gnn_b200.tc_linear import TCLinear
+    torch.manual_seed(0)
+    rows = 30011                     # > 16 problems x 768 rows: the batched launch runs the accumulation periods
+
+    class Stack(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.inp = TCLinear(338, 256)                 # K blocks 128 | 128 | 82, rows of 1 352 bytes (not 16-aligned)
+            self.mid = torch.nn.ModuleList([TCLinear(256 if i == 0 else 128, 128, bias=(i % 3 != 2)) for i in range(19)])
+            self.small = TCLinear(128, 64)                # out_features the kernels do not take: ordinary path
+            self.out = torch.nn.Linear(64, 1)
+
+        def forward(self, x):
+            h = torch.nn.functional.silu(self.inp(x))
+            for m in self.mid:
+                h = torch.nn.functional.silu(m(h)) + (h if h.size(1) == 128 else 0)
+            return self.out(self.small(h))
+
+    net = Stack().cuda()
+    x = torch.randn(rows, 338, device="cuda")
+    grads = {}
+    for defer in (False, True):
+        tail = FusedTail(net.parameters(), lr=1e-3, max_norm=0.0)
+        n = tail.defer_wgrads(net, defer)
+        assert n == (2 * 20 - 6 if defer else 0)         # 20 deferring layers, 6 of them without bias... see below
+        tail.zero_grad()
+        tail.backward(net(x).square().mean())
+        if defer:
+            assert net.inp.weight.grad is None and net.small.weight.grad is not None
+            assert len(tail.queue.pending) == 20
+        tail._pack()
+        assert not tail.queue.pending
+        grads[defer] = [v.clone() for v in tail.grad_views]
+        tail.defer_wgrads(net, False)
+    ref = Stack().double().cuda()
+    ref.load_state_dict({k: v.double() for k, v in net.state_dict().items()})
+    ref(x.double()).square().mean().backward()
+    for (k, p), a, b in zip(ref.named_parameters(), grads[False], grads[True]):
+        assert relerr(b, p.grad) < 1e-5, k
+        assert relerr(a, p.grad) < 1e-5, k
+    # a weight used twice in one backward cannot defer
+    tail = FusedTail(net.parameters(), lr=1e-3, max_norm=0.0)
+    tail.defer_wgrads(net, True)
+    h = torch.randn(64, 128, device="cuda")
+    with pytest.raises(RuntimeError):
+        tail.backward((net.mid[3](h) + net.mid[3](h * 2)).sum())
+    tail.queue.flush(h.device)
+    tail.defer_wgrads(net, False)

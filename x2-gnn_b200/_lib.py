@@ -26,6 +26,11 @@ c_i64p = C.c_void_p
 c_stream = C.c_void_p
 
 
+class WgradJob(C.Structure):      # x2_wgrad_job
+    _fields_ = [("Y", C.c_void_p), ("ldy", C.c_int64), ("X", C.c_void_p), ("ldx", C.c_int64),
+                ("dW", C.c_void_p), ("lddw", C.c_int64), ("db", C.c_void_p)]
+
+
 class ConvDesc(C.Structure):
     _fields_ = [
         ("E", C.c_int64), ("T", C.c_int64),
@@ -100,6 +105,7 @@ SIGNATURES = {
     "x2_tc_gemm": (C.c_int, [_P, _I64, _I64, _I32, _P, _I64, _I64, _I32, _P, _P, _I64, _I32, _P, _SZ, _P]),
     "x2_tc_wgrad_workspace_bytes": (_SZ, [_I64, _I32]),
     "x2_tc_wgrad": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _P, _I64, _P, _P, _SZ, _P]),
+    "x2_tc_wgrad_batch": (C.c_int, [_P, _I32, _I64, _I32, _P, _SZ, _P]),
     "x2_sbfconv_plan": (C.c_int, [C.POINTER(ConvDesc)]),
     "x2_sbfconv_fwd_workspace_bytes": (_SZ, [C.POINTER(ConvDesc)]),
     "x2_sbfconv_bwd_workspace_bytes": (_SZ, [C.POINTER(ConvDesc)]),

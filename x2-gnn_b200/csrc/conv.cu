@@ -1100,6 +1100,26 @@ int x2_tc_wgrad(const float* Y, int64_t ldy, const float* X, int64_t ldx, int64_
   return tc::tc_wgrad(Y, ldy, X, ldx, rows, N, dW, lddw, db, static_cast<float*>(ws), (cudaStream_t)stream);
 }
 
+// njobs weight gradients over the same `rows` and N, kMaxProbG2 per launch (each launch: one k_tc_wgrad with the CTAs
+// dealt over its problems + one fixed-order reduction).  The same workspace serves every launch (stream order).
+int x2_tc_wgrad_batch(const x2_wgrad_job* jobs, int32_t njobs, int64_t rows, int32_t N, void* ws, size_t ws_bytes,
+                      void* stream) {
+  X2_CHECK_ARG(jobs && njobs >= 1 && rows >= 0, "x2_tc_wgrad_batch: bad arguments");
+  X2_CHECK_ARG(N >= 1 && N <= 128, "x2_tc_wgrad_batch: need 1 <= N <= 128 (got %d)", N);
+  if (ws_bytes < x2_tc_wgrad_workspace_bytes(rows, N)) { set_error("x2_tc_wgrad_batch: workspace too small"); return X2_EWORKSPACE; }
+  for (int32_t i = 0; i < njobs; i += tc::kMaxProbG2) {
+    tc::G2Job g[tc::kMaxProbG2];
+    const int n = njobs - i < tc::kMaxProbG2 ? njobs - i : tc::kMaxProbG2;
+    for (int j = 0; j < n; ++j) {
+      const x2_wgrad_job& q = jobs[i + j];
+      X2_CHECK_ARG(q.Y && q.X && q.dW, "x2_tc_wgrad_batch: null pointer in job %d", i + j);
+      g[j] = tc::G2Job{q.Y, q.ldy, q.X, q.ldx, q.dW, q.lddw, q.db};
+    }
+    X2_TRY(tc::tc_wgrad_batch(g, n, rows, N, static_cast<float*>(ws), (cudaStream_t)stream));
+  }
+  return X2_OK;
+}
+
 int x2_sbfconv_plan(const x2_conv_desc* d) {
   if (!d) return 0;
   return sgf_usable(d) ? (X2_PLAN_BLOCKS | X2_PLAN_FACTORISED_SBF) : 0;

@@ -311,6 +311,7 @@ constexpr int kTmemWHi = 256;        // TMEM columns [256, 384): W_hi ; [384, 51
 constexpr int kTmemWLo = 384;
 
 constexpr int kMaxProb = 4;
+constexpr int kMaxProbG2 = 16;       // weight gradients of one k_tc_wgrad launch (x2_tc_wgrad_batch: deferred wgrads)
 constexpr int kG1Flight = 4;         // chunks of global loads in flight per producer thread
 struct G1Prob {
   const float* A;        // streamed activations X[M, K]
@@ -703,10 +704,11 @@ struct G2Prob {
   float* partial;        // [ctas per problem][128][N]
   float* colsum;         // [ctas per problem][128] or NULL
 };
-// Up to kMaxProb weight gradients of identical shape (the four node-level ones: dW_q, dW_k, dW_v,
-// dW_skip) share one launch: CTA b works on problem b % nprob, row slab b / nprob.
+// Up to kMaxProbG2 weight gradients of identical shape (the four node-level ones: dW_q, dW_k, dW_v,
+// dW_skip; the deferred weight gradients of a training step, x2_tc_wgrad_batch) share one launch: CTA b
+// works on problem b % nprob, row slab b / nprob.
 struct G2Params {
-  G2Prob prob[kMaxProb];
+  G2Prob prob[kMaxProbG2];
   int nprob;
   int N, N_pad;          // N_pad multiple of 32, <= 128
   int64_t rows, rows_per_cta;   // rows_per_cta multiple of 32
@@ -1227,14 +1229,14 @@ struct G2Job {           // one weight gradient: dW[128,N] = Y^T X ; db[128] = c
 };
 
 struct ReduceBatch {
-  const float* partial[kMaxProb];
-  const float* colsum[kMaxProb];
-  float* out[kMaxProb];
-  float* bias[kMaxProb];
-  int64_t ldo[kMaxProb];
+  const float* partial[kMaxProbG2];
+  const float* colsum[kMaxProbG2];
+  float* out[kMaxProbG2];
+  float* bias[kMaxProbG2];
+  int64_t ldo[kMaxProbG2];
 };
 
-// Fixed-order reduction of the per-CTA partial tiles of up to kMaxProb weight gradients
+// Fixed-order reduction of the per-CTA partial tiles of up to kMaxProbG2 weight gradients
 // (blockIdx.y = problem).  Same summation tree as k_splitk_reduce: warp g sums the splits g, g+8, ...
 // and the eight warp sums are added in order.
 __global__ void __launch_bounds__(256)
@@ -1280,7 +1282,7 @@ k_splitk_reduce_batch(const ReduceBatch b, int splits, int64_t M, int N) {
 // ws: tc_wgrad_workspace_floats
 static int tc_wgrad_batch(const G2Job* jobs, int nprob, int64_t rows, int N, float* ws, cudaStream_t st,
                           int single = 0) {
-  if (N < 1 || N > 128 || nprob < 1 || nprob > kMaxProb) { set_error("tc_wgrad: unsupported N=%d nprob=%d", N, nprob); return X2_EINVAL; }
+  if (N < 1 || N > 128 || nprob < 1 || nprob > kMaxProbG2) { set_error("tc_wgrad: unsupported N=%d nprob=%d", N, nprob); return X2_EINVAL; }
   const int N_pad = ceil_to(N, 32);
   const int cpp = wgrad_ctas(rows, nprob);                              // CTAs per problem
   const int64_t rpc = cdiv(cdiv(rows > 0 ? rows : 1, cpp), kChunkK) * kChunkK;

@@ -8,7 +8,7 @@ are gathered by ONE multi-tensor copy) and `x2_optim_tail` reads and writes ever
 parallelism the flat gradient is the all-reduce buffer.
 
     tail = FusedTail(model.parameters(), lr=1e-3, max_norm=100.0, ema_decay=0.95)
-    tail.zero_grad(); loss.backward(); tail.allreduce(); tail.step()
+    tail.zero_grad(); tail.backward(loss); tail.allreduce(); tail.step()      # (loss.backward() works too)
 
 Sync-free and allocation-free after construction: capturable in a CUDA graph (the step count lives on the device).
 """
@@ -62,6 +62,39 @@ class FusedTail:
         self._ws = _lib.workspace(_lib.lib().x2_optim_workspace_bytes(n), dev)
         self._world = 1
         self._packed = False
+        self.active, self.defer, self.queue, self._deferred_ids, self._bias_of = False, False, None, set(), {}
+
+    def defer_wgrads(self, model, on: bool = True):
+        """Route the weight / bias gradients of the model's TCLinear layers around autograd: their backward records the
+        operands, `_pack` computes all of them in a few batched launches (tc_linear.DeferredWgrads) straight into the
+        flat gradient buffer.  Only layers whose out_features the tensor-core kernels take (a multiple of 128) defer;
+        everything else keeps the ordinary path."""
+        from .tc_linear import DeferredWgrads, TCLinear, WgradSlots
+        view = {id(p): v for p, v in zip(self.params, self.grad_views)}
+        self.queue = DeferredWgrads()
+        self.defer = bool(on)          # `active` is only raised around a backward pass (backward_scope)
+        self._deferred_ids = set()
+        for m in model.modules():
+            if isinstance(m, TCLinear):
+                gw = view.get(id(m.weight))
+                gb = view.get(id(m.bias)) if m.bias is not None else None
+                ok = on and gw is not None and m.out_features % 128 == 0 and (m.bias is None or gb is not None)
+                m._x2_slots = WgradSlots(self, gw, gb) if ok else None
+                if ok:
+                    self._deferred_ids.add(id(m.weight))
+                    if m.bias is not None:
+                        self._deferred_ids.add(id(m.bias))
+                        self._bias_of[id(m.bias)] = gw.data_ptr()
+        return len(self._deferred_ids)
+
+    def backward(self, loss):
+        """loss.backward() with the TCLinear weight gradients deferred to _pack (when defer_wgrads attached them).
+        Only a backward pass run through here defers: any other use of the model's autograd graph is untouched."""
+        self.active = self.defer
+        try:
+            loss.backward()
+        finally:
+            self.active = False
 
     def zero_grad(self):
         """Gradients are produced by autograd as usual (fresh tensors, no accumulation kernels) and gathered into
@@ -74,11 +107,23 @@ class FusedTail:
         if self._packed:
             return
         have = [(v, p.grad) for v, p in zip(self.grad_views, self.params) if p.grad is not None]
-        if len(have) != len(self.params):
+        pend = self.queue.pending if self.queue is not None else ()
+        n_def = sum(1 for v, p in zip(self.grad_views, self.params)
+                    if p.grad is None and id(p) in self._deferred_ids and self._covered(p, v, pend)) if pend else 0
+        if len(have) + n_def != len(self.params):
             self.flat_g.zero_()                    # parameters without a gradient this step
+        if pend:
+            self.queue.flush(self.flat_g.device)   # deferred TCLinear weight gradients -> their blocks of flat_g
         if have:
             torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
         self._packed = True
+
+    def _covered(self, p, v, pend):
+        """True iff the deferred queue holds this parameter's gradient (a bias rides with its weight)."""
+        if v.data_ptr() in pend:
+            return True
+        w = self._bias_of.get(id(p))
+        return w is not None and w in pend
 
     def allreduce(self):
         """Sum over the ranks; the division by the world size is folded into step()."""

@@ -26,7 +26,7 @@ def fused_dense_step(model, tail, data, prep, y):
     (optim_tail.FusedTail / x2_optim_tail) instead of ~300."""
     tail.zero_grad()
     loss = torch.nn.functional.smooth_l1_loss(model(data, prep), y)
-    loss.backward()
+    tail.backward(loss)
     tail.allreduce()
     tail.step()
     return loss
@@ -52,7 +52,7 @@ def dense_step(model, opt, params, data, prep, y, ema_params=None, ema_decay=0.9
 class GraphedTrainStep:
     def __init__(self, model, data: dict, y: torch.Tensor, lr: float = 1e-3, ema_decay: float = 0.95,
                  bucket: "ddp.FlatGradBucket | None" = None, max_norm: float = 100.0, warmup: int = 3,
-                 fused_tail: bool = True):
+                 fused_tail: bool = True, defer_wgrads: bool = True):
         """fused_tail: parameters / gradients / Adam moments / EMA in flat buffers, updated by x2_optim_tail (two
         launches; the flat gradient is also the all-reduce buffer, `bucket` is then only a flag that the step is
         data-parallel).  False: torch's capturable fused Adam + foreach clip / lerp, as in round 1."""
@@ -66,6 +66,9 @@ class GraphedTrainStep:
         if fused_tail:
             from .optim_tail import FusedTail
             self.tail = FusedTail(self.params, lr=lr, max_norm=max_norm, ema_decay=ema_decay)
+            # the weight gradients of the TCLinear layers: recorded during the backward, computed in a few batched
+            # launches by the tail (tc_linear.DeferredWgrads), written straight into the flat gradient buffer
+            self.deferred = self.tail.defer_wgrads(model, defer_wgrads)
             self.opt = None
             self.ema_params = self.tail.ema_views
             run = lambda: fused_dense_step(model, self.tail, data, self.prep, y)

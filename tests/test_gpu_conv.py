@@ -391,7 +391,7 @@ def test_loud_failures():
     with pytest.raises(TypeError):          # fp64 is not silently down-cast
         c(rec["sbf"].cuda().double(), rec["rbf"].cuda().double(), x=rec["x"].cuda().double(),
           edge_index=rec["edge_index"].cuda(), edge_attr=rec["edge_attr"].cuda().double())
-    bad = SBFTransformerConv(96, 12, heads=8, sbf_dim=10, rbf_dim=3, edge_dim=20).cuda()   # D=96 unsupported
-    with pytest.raises(_lib.X2Error):
+    bad = SBFTransformerConv(96, 12, heads=8, sbf_dim=10, rbf_dim=3, edge_dim=20).cuda()   # C = 12: not a power of two
+    with pytest.raises(NotImplementedError):
         bad(rec["sbf"].cuda(), rec["rbf"].cuda(), x=torch.randn(rec["x"].size(0), 96, device="cuda"),
             edge_index=rec["edge_index"].cuda(), edge_attr=rec["edge_attr"].cuda())

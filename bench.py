@@ -307,7 +307,10 @@ def _train_step_graph(dev, world, rank, steps, data, y, nmine):
     model = XGNNPoly(**HPARAMS).to(dev)
     bucket = ddp.FlatGradBucket(model.parameters()) if world > 1 else None
     gs = GraphedTrainStep(model, data, y, lr=1e-3, bucket=bucket)
-    prep_stream = torch.cuda.Stream(device=dev)
+    # high priority: the few small integer kernels (each followed by a size read-back on the host) are scheduled ahead
+    # of the replay's queued CTAs instead of behind a whole persistent kernel -- prepare() then takes ~2 ms of host
+    # time beside a replay in flight instead of ~8, and the loop is paced by the GPU, not by the read-backs
+    prep_stream = torch.cuda.Stream(device=dev, priority=-1)
     prep_stream.wait_stream(torch.cuda.current_stream(dev))
 
     def step():
@@ -1100,8 +1103,14 @@ def run_ours(args):
     # with the digest of the sources the .so was built from; a file of another build is refused, not reused)
     traffic, traffic_src, phase_rates = None, None, None
     tpath = os.path.join(ROOT, "profiles", "r2_step_traffic.json")
-    dpath = os.path.join(ROOT, "x2-gnn_b200", "lib", "libx2gnn.sha256")
-    lib_digest = open(dpath).read().strip() if os.path.exists(dpath) else None
+    # (the stamp written next to the binary by build.py, libx2gnn.so.digest, wins over the tracked libx2gnn.sha256:
+    # a `git checkout` can restore the latter without rebuilding the former)
+    lib_digest = None
+    for dpath in (os.path.join(ROOT, "x2-gnn_b200", "lib", "libx2gnn.so.digest"),
+                  os.path.join(ROOT, "x2-gnn_b200", "lib", "libx2gnn.sha256")):
+        if os.path.exists(dpath):
+            lib_digest = open(dpath).read().strip()
+            break
     if os.path.exists(tpath):
         tj = json.load(open(tpath)).get(args.mode)
         if not tj:

@@ -81,7 +81,9 @@ for k, n in enumerate(names):
     elif k > i_src:
         after = k - i_src
         ph["trow_dgrad" if after == 1 else "trow_wgrad" if after <= 5 else "node_bwd"] += mb[k]
-sha = open(os.path.join(ROOT, "x2-gnn_b200", "lib", "libx2gnn.sha256")).read().strip()
+_libdir = os.path.join(ROOT, "x2-gnn_b200", "lib")
+_stamp = os.path.join(_libdir, "libx2gnn.so.digest")         # written next to the binary by build.py
+sha = open(_stamp if os.path.exists(_stamp) else os.path.join(_libdir, "libx2gnn.sha256")).read().strip()
 try:
     git = subprocess.run(["git", "-C", ROOT, "rev-parse", "HEAD"], capture_output=True, text=True).stdout.strip()
 except Exception:

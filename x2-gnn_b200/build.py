@@ -44,8 +44,12 @@ def _digest() -> str:
 def build(force: bool = False, verbose: bool = True) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "libx2gnn.sha256")
+    # the stamp that travels WITH the binary (git-ignored like the .so): libx2gnn.sha256 is tracked, so a
+    # `git checkout` can restore a stamp that no longer describes the .so on disk
+    built = LIB + ".digest"
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+    if (not force and os.path.exists(LIB) and os.path.exists(built) and open(built).read() == digest
+            and os.path.exists(stamp) and open(stamp).read() == digest):
         return LIB
     nvcc = _nvcc()
     objs = []
@@ -67,9 +71,18 @@ def build(force: bool = False, verbose: bool = True) -> str:
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)
-    with open(stamp, "w") as f:
-        f.write(digest)
+    for path in (stamp, built):
+        with open(path, "w") as f:
+            f.write(digest)
     return LIB
+
+
+def built_digest() -> str | None:
+    """Digest of the sources the .so ON DISK was built from (None: unknown build)."""
+    for path in (LIB + ".digest", os.path.join(LIBDIR, "libx2gnn.sha256")):
+        if os.path.exists(path):
+            return open(path).read().strip()
+    return None
 
 
 def sass_summary(path: str = None) -> str:

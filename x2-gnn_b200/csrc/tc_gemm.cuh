@@ -508,10 +508,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
             if (m0 + kTileM <= p.M) {
 #pragma unroll
               for (int i = 0; i < NP; ++i) cp_async<PIECE>(base + soff[i], src + i * row_step);
-            } else {                                         // rows past M keep stale data: row-local, never stored
+            } else {                                         // rows past M: zeros (row-local, never stored)
 #pragma unroll
-              for (int i = 0; i < NP; ++i)
+              for (int i = 0; i < NP; ++i) {
                 if (m0 + r0 + RS * i < p.M) cp_async<PIECE>(base + soff[i], src + i * row_step);
+                else if constexpr (PIECE == 16) sts128(base + soff[i], make_uint4(0u, 0u, 0u, 0u));
+                else sts64(base + soff[i], 0u, 0u);
+              }
             }
           } else {                                           // k >= K inside the last k-step: zeros
 #pragma unroll
@@ -658,6 +661,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const G1Params p) {
       const int64_t row0 = tile * kTileM;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128;
       for (int c0 = half * 16; c0 < kTileM; c0 += 16 * kEpiHalves) {
+        if (row0 + c0 >= p.M) break;                   // the rest of a partial last tile
         float v[16];
         tmem_ld16(taddr + c0, v);
         if (nvalid) {

@@ -395,3 +395,18 @@ def test_loud_failures():
     with pytest.raises(NotImplementedError):
         bad(rec["sbf"].cuda(), rec["rbf"].cuda(), x=torch.randn(rec["x"].size(0), 96, device="cuda"),
             edge_index=rec["edge_index"].cuda(), edge_attr=rec["edge_attr"].cuda())
+
+
+def test_inplace_modification_between_forward_and_backward_is_an_error():
+    """The layer's inputs / buffers are saved through save_for_backward: changing an input in place after the forward
+    must raise in the backward instead of producing a gradient of something else."""
+    dims = (64, 8, 10, 3, 20)
+    _, mine = _oracle_pair(dims, seed=11)
+    rec = _graph_inputs(2, dims, seed=12)
+    x = rec["x"].cuda().requires_grad_(True)
+    xin = x * 1.0
+    out = mine(rec["sbf"].cuda(), rec["rbf"].cuda(), x=xin, edge_index=rec["edge_index"].cuda(),
+               edge_attr=rec["edge_attr"].cuda())
+    xin.add_(1.0)
+    with pytest.raises(RuntimeError, match="inplace|in-place"):
+        out.sum().backward()

@@ -196,8 +196,10 @@ class _SBFConvFn(torch.autograd.Function):
                                     _lib.ptr(ws), ws.numel(), _lib.stream()), "x2_sbfconv_fwd")
         ctx.cfg, ctx.meta, ctx.dims = cfg, meta, dims
         ctx.groups = groups
-        ctx.tensors = t            # inputs + weights (kept alive; plain references, no graph)
-        ctx.saved_bufs = (qkvs, attn, lse, ea, sg, xs)
+        # inputs, weights and the forward's buffers go through save_for_backward: an in-place modification of any of
+        # them between forward and backward is then an autograd error instead of a silently wrong gradient
+        ctx.names = names
+        ctx.save_for_backward(*[t[n] for n in names], qkvs, attn, lse, ea, sg, xs)
         if alpha is not None:
             ctx.mark_non_differentiable(alpha)
             return out, alpha
@@ -205,9 +207,10 @@ class _SBFConvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout, _galpha):
-        t, meta = ctx.tensors, ctx.meta
+        saved = ctx.saved_tensors
+        t, meta = dict(zip(ctx.names, saved[:len(ctx.names)])), ctx.meta
         E, T, D, H, Cc, S, R, A, fuse = ctx.dims
-        qkvs, attn, lse, ea, sg, xs = ctx.saved_bufs
+        qkvs, attn, lse, ea, sg, xs = saved[len(ctx.names):]
         gout = _lib.f32(gout, "SBFTransformerConv.backward")
         dev = gout.device
         cfg = ctx.cfg

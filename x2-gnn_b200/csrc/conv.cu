@@ -573,7 +573,7 @@ k_attn_bwd_tgt(const float* __restrict__ qkvs, int ldq, const float* __restrict_
       }
       stv<VEC>(dsg + (int64_t)rw.t * D + ch, o_sg);
       if (leader) {
-        al[(int64_t)rw.t * H + head] = alpha_d;
+        if (al) al[(int64_t)rw.t * H + head] = alpha_d;      // (NULL: the by-source pass reads dEA instead)
         da_out[(int64_t)rw.t * H + head] = da;
       }
     };
@@ -665,6 +665,56 @@ k_attn_bwd_src(const float* __restrict__ qkvs, int ldq, const float* __restrict_
   }
   stv<VEC>(dqkv + f * ldg + D + ch, dk);
   stv<VEC>(dqkv + f * ldg + 2 * D + ch, dv);
+}
+
+// The same pass when the by-target pass has written dEA_t = dkk_t + dvv_t per triplet (edge_attr [T, A]):
+// dK[s] = sum_t sigma da_t Q[e] as above, and dV[s] = sum_t dvv_t = sum_t (dEA_t - dkk_t) -- one streamed row (dEA) and
+// one gathered row (Q) per triplet instead of one streamed (Sg) and two gathered (Q, G) plus alpha: the pass is bound
+// by L1 / L2 requests (1.66 kB per triplet, ~10 TB/s with the gathers), not by DRAM.  The subtraction costs at most
+// eps (|dEA_t| + |dkk_t|) per term.
+template <int VEC>
+__global__ void __launch_bounds__(128)
+k_attn_bwd_src_dea(const float* __restrict__ qkvs, int ldq, const float* __restrict__ dea,
+                   const float* __restrict__ da_in, const int32_t* __restrict__ tgt,
+                   const int32_t* __restrict__ rowptr_src, const int32_t* __restrict__ order_src,
+                   int64_t E, int H, int C, float scale, float* __restrict__ dqkv, int ldg) {
+  pdl_sync();
+  constexpr int D = 32 * VEC;
+  const int64_t f = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (f >= E) return;
+  const int lane = threadIdx.x & 31;
+  const int ch = lane * VEC;
+  const int head = ch / C;
+  float dk[VEC], ds[VEC];           // ds = sum_t dEA_t
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) dk[i] = ds[i] = 0.f;
+  const int beg = rowptr_src[f], end = rowptr_src[f + 1];
+  for (int base = beg; base < end; base += 32) {
+    const int my = base + lane;
+    int t_l = 0, e_l = 0;
+    if (my < end) {
+      t_l = order_src[my];
+      e_l = tgt[t_l];
+    }
+    const int cnt = min(32, end - base);
+#pragma unroll 8
+    for (int i = 0; i < cnt; ++i) {
+      const int t = __shfl_sync(0xffffffffu, t_l, i);
+      const int e = __shfl_sync(0xffffffffu, e_l, i);
+      float q[VEC], dv_[VEC];
+      ldv<VEC>(qkvs + (int64_t)e * ldq + ch, q);
+      ldv<VEC>(dea + (int64_t)t * D + ch, dv_);
+      const float sda = scale * da_in[(int64_t)t * H + head];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float kk = sda * q[j];             // dkk_t, formed exactly as the by-target pass formed it
+        dk[j] += kk;
+        ds[j] += dv_[j] - kk;                    // dvv_t
+      }
+    }
+  }
+  stv<VEC>(dqkv + f * ldg + D + ch, dk);
+  stv<VEC>(dqkv + f * ldg + 2 * D + ch, ds);
 }
 
 }  // namespace x2
@@ -944,20 +994,27 @@ static int launch_tile_fwd(const x2_conv_desc* d, const x2_conv_saved* s, float*
   return X2_OK;
 }
 
+// by-source pass from dEA (k_attn_bwd_src_dea) whenever edge_attr is [T, A]; X2GNN_SRC_DEA=0: the generic pass (A/B runs)
+static bool src_from_dea() {
+  static const bool on = env_on("X2GNN_SRC_DEA");
+  return on;
+}
+
 template <int VEC, int EA, bool DROP>
 static void launch_attn_bwd_tgt_inst(const x2_conv_desc* d, const x2_conv_saved* s, const float* gout,
                                      const BwdWs& w, cudaStream_t st) {
   const float scale = 1.0f / sqrtf((float)d->C);
   const unsigned grid = (unsigned)cdiv(d->E * 32, 128);
   const int32_t* order = d->tgt_sorted ? nullptr : d->order_tgt;     // sorted: order_tgt is the identity
+  float* al = (EA == kEaTriplet && src_from_dea()) ? nullptr : w.al;  // alpha is only kept for the generic by-source pass
   if (d->C == 2 * VEC)
     launch_k(k_attn_bwd_tgt<VEC, EA, DROP, 2>, dim3(grid), dim3(128), 0, st, 
         s->qkvs, 4 * d->D, s->ea, d->ea_index, s->sg, s->attn, s->lse, gout, d->src, d->rowptr_tgt, order, d->E,
-        d->H, d->C, scale, d->dropout_p, d->seed, w.dqkv, 3 * d->D, w.dea, w.dsg, w.al, w.da);
+        d->H, d->C, scale, d->dropout_p, d->seed, w.dqkv, 3 * d->D, w.dea, w.dsg, al, w.da);
   else
     launch_k(k_attn_bwd_tgt<VEC, EA, DROP, 0>, dim3(grid), dim3(128), 0, st, 
         s->qkvs, 4 * d->D, s->ea, d->ea_index, s->sg, s->attn, s->lse, gout, d->src, d->rowptr_tgt, order, d->E,
-        d->H, d->C, scale, d->dropout_p, d->seed, w.dqkv, 3 * d->D, w.dea, w.dsg, w.al, w.da);
+        d->H, d->C, scale, d->dropout_p, d->seed, w.dqkv, 3 * d->D, w.dea, w.dsg, al, w.da);
 }
 
 template <int VEC>
@@ -983,7 +1040,11 @@ static int launch_attn_bwd(const x2_conv_desc* d, const x2_conv_saved* s, const 
     X2_LAUNCH_OK();
   }
   phase_end(X2_PHASE_ATTN_BWD_TGT, st);
-  launch_k(k_attn_bwd_src<VEC>, dim3(grid), dim3(128), 0, st, s->qkvs, 4 * d->D, s->sg, gout, w.al, w.da, d->tgt,
+  if (ea == kEaTriplet && src_from_dea())
+    launch_k(k_attn_bwd_src_dea<VEC>, dim3(grid), dim3(128), 0, st, s->qkvs, 4 * d->D, w.dea, w.da, d->tgt,
+             d->rowptr_src, d->order_src, d->E, d->H, d->C, scale, w.dqkv, 3 * d->D);
+  else
+    launch_k(k_attn_bwd_src<VEC>, dim3(grid), dim3(128), 0, st, s->qkvs, 4 * d->D, s->sg, gout, w.al, w.da, d->tgt,
                                             d->rowptr_src, d->order_src, d->E, d->H, d->C, scale, w.dqkv,
                                             3 * d->D);
   X2_LAUNCH_OK();

@@ -15,6 +15,8 @@ distinct row per atom -- SURVEY.md §8f row 1; row-wise MLP, so edgenn(emb[a_j])
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -140,6 +142,7 @@ class SBFTransformer(nn.Module):
                                       for _ in range(conv_layers)])
         self.dense_bf_skip = nn.ModuleList([_lin(in_channels, in_channels) for _ in range(conv_layers)])
         self.conv_layers = conv_layers
+        self.overlap_readouts = os.environ.get("X2GNN_OVERLAP_READOUTS", "1") != "0"
 
     def forward(self, x, edge_index, edge_attr, batch, edge_sbf, node_rbf, edge_index_0, atom_batch, num_graphs,
                 edge_attr_index=None, edge_attr_target_index=None, batch_counts=None, batch_rowptr=None,
@@ -156,7 +159,23 @@ class SBFTransformer(nn.Module):
             edge_attr = edge_attr[edge_attr_index]
         out = x
         n_atoms = atom_batch.size(0)
-        results = self.readouts[0](out, node_rbf, n_atoms, edge_index_0, atom_rowptr)
+        # The readouts hang off the main chain (model.py:41,53: their sum only meets it at the very end) and are
+        # atom-scale: ~15 launches of 19-CTA kernels each, forward and backward.  On a side stream they overlap the
+        # bond-scale chain instead of interrupting it (autograd runs a node's backward on its forward's stream; under
+        # CUDA-graph capture the fork / join become parallel branches of the graph).
+        side = self._side_stream(x) if self.overlap_readouts and x.is_cuda else None
+        main = torch.cuda.current_stream(x.device) if side is not None else None
+
+        def readout(i, h):
+            if side is None:
+                return self.readouts[i](h, node_rbf, n_atoms, edge_index_0, atom_rowptr)
+            side.wait_stream(main)                        # h (and everything before it) is ready
+            with torch.cuda.stream(side):
+                r = self.readouts[i](h, node_rbf, n_atoms, edge_index_0, atom_rowptr)
+            h.record_stream(side)
+            return r
+
+        parts = [readout(0, out)]
         for i in range(self.conv_layers):
             res0 = out
             out = self.convs[i](sbf=edge_sbf, rbf=node_rbf, x=out, edge_index=edge_index, edge_attr=edge_attr,
@@ -165,9 +184,27 @@ class SBFTransformer(nn.Module):
             out = self.bf_skip[i](out)
             out = F.silu(self.dense_bf_skip[i](out)) + res0
             out = self.af_skip[i](out)
-            results = results + self.readouts[i + 1](out, node_rbf, n_atoms, edge_index_0, atom_rowptr)
+            parts.append(readout(i + 1, out))
+        if side is not None:
+            main.wait_stream(side)
+            for r in parts:
+                r.record_stream(main)
+        results = parts[0]
+        for r in parts[1:]:
+            results = results + r
         mol = torch.zeros(num_graphs, results.size(1), dtype=results.dtype, device=results.device)
         return mol.index_add(0, atom_batch, results).view(-1)
+
+    @staticmethod
+    def _side_stream(x):
+        key = x.device.index
+        st = _SIDE_STREAMS.get(key)
+        if st is None:
+            st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=x.device)
+        return st
+
+
+_SIDE_STREAMS: dict = {}       # device index -> side stream of the readouts (module-global: never copied with a model)
 
 
 class XGNNPoly(nn.Module):

@@ -168,6 +168,14 @@ int x2_sbf_fwd(const float* table, const float* angles, const int64_t* idx, int6
                int32_t L, int32_t R, float* out, void* stream);
 /* angular_basis_layer.py:28-32: out[t,l] = Y_l0(angles[t]). */
 int x2_angular_fwd(const float* angles, int64_t T, int32_t L, float* out, void* stream);
+/* Geometry of the line graph as the caller computes it before the expansions (xgnn.py:46,60-66):
+ *   d[e]   = | pos[a0[e]] - pos[a1[e]] |
+ *   ang[t] = atan2(| ji x jk |, <ji, jk>),  ji = pos[ai[t]] - pos[aj[t]],  jk = pos[ak[t]] - pos[aj[t]]
+ * pos [N,3] fp32, indices int64 (vertex_to_edge_2's atom ids), fp32 arithmetic in the reference's operation order.
+ * Two launches instead of ~15 gathers / elementwise passes / reductions over [T,3] intermediates. */
+int x2_bond_lengths(const float* pos, const int64_t* a0, const int64_t* a1, int64_t E, float* d, void* stream);
+int x2_triplet_angles(const float* pos, const int64_t* ai, const int64_t* aj, const int64_t* ak, int64_t T, float* ang,
+                      void* stream);
 /* Gradients of the three expansions w.r.t. the geometry.  The reference's bases are torch expressions
  * (envelop.py:16-21, angular_basis_layer.py:28-32,80-93), so its autograd differentiates them w.r.t. distances
  * and angles (e.g. forces = -dE/dpos); these are the analytic derivatives of the same formulas, E-scale parts

@@ -194,3 +194,35 @@ def test_rotation_translation_invariance():
         ang = torch.atan2(torch.linalg.cross(ji, jk).norm(dim=1), (ji * jk).sum(1))
         outs.append(abl.F_B_2D(7, 6, 5.0, 5)(d.float().cuda(), ang.float().cuda(), tri[0].cuda()))
     assert relerr(outs[1], outs[0]) < 2e-5
+
+
+def test_fused_geometry_kernels_match_the_torch_expressions():
+    """x2_bond_lengths / x2_triplet_angles (xgnn.py:46,60-66 as two kernels) against the torch expressions in fp32
+    (same operation order: equal to the last bits) and fp64, on a QM9-shaped batch and on degenerate triplets
+    (collinear, zero-length)."""
+    from x2gnn_b200 import geometry, synth
+    b = synth.qm9_batch(6, seed=4)
+    pos = torch.from_numpy(b["atom_pos"]).cuda()
+    ei = torch.from_numpy(b["edge_index"]).cuda()
+    tri, aj, ai, ak = (torch.from_numpy(a).cuda().long() for a in synth.triplets_host(b["edge_index"], len(b["x"])))
+    d = geometry.bond_lengths(pos, ei[0].contiguous(), ei[1].contiguous())
+    d32 = torch.norm(pos[ei[0]] - pos[ei[1]], dim=1)
+    d64 = torch.norm(pos.double()[ei[0]] - pos.double()[ei[1]], dim=1)
+    assert float((d - d32).abs().max()) <= 2.4e-7 * float(d32.max()) and relerr(d, d64) < 2e-7
+    ang = geometry.triplet_angles(pos, ai, aj, ak)
+    ji, jk = pos[ai] - pos[aj], pos[ak] - pos[aj]
+    a32 = torch.atan2(torch.linalg.cross(ji, jk).norm(dim=1), (ji * jk).sum(1))
+    p64 = pos.double()
+    ji, jk = p64[ai] - p64[aj], p64[ak] - p64[aj]
+    a64 = torch.atan2(torch.linalg.cross(ji, jk).norm(dim=1), (ji * jk).sum(1))
+    assert ang.shape == a32.shape and float((ang - a32).abs().max()) < 1e-6
+    assert float((ang.double() - a64).abs().max()) < 2e-6
+    # degenerate: collinear (0 and pi) and a zero vector (atan2(0, 0) = 0)
+    p = torch.tensor([[0., 0, 0], [1, 0, 0], [2, 0, 0], [-1, 0, 0]], device="cuda")
+    i = torch.tensor([1, 1, 0], device="cuda"); j = torch.tensor([0, 0, 0], device="cuda"); k = torch.tensor([2, 3, 1], device="cuda")
+    got = geometry.triplet_angles(p, i, j, k)
+    assert torch.allclose(got, torch.tensor([0.0, math.pi, 0.0], device="cuda"), atol=1e-7)
+    # positions that require grad keep the differentiable torch path
+    pg = pos.clone().requires_grad_(True)
+    geometry.triplet_angles(pg, ai, aj, ak).sum().backward()
+    assert pg.grad is not None and geometry.bond_lengths(pos[:0], ei[0][:0].contiguous(), ei[1][:0].contiguous()).numel() == 0

@@ -97,6 +97,8 @@ SIGNATURES = {
     "x2_sbf_table": (C.c_int, [_P, _I64, _I32, _I32, _P, _P, _F, _F, _I32, _F, _F, _F, _P, _P]),
     "x2_sbf_fwd": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _I32, _P, _P]),
     "x2_angular_fwd": (C.c_int, [_P, _I64, _I32, _P, _P]),
+    "x2_bond_lengths": (C.c_int, [_P, _P, _P, _I64, _P, _P]),
+    "x2_triplet_angles": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P]),
     "x2_envelope_bwd": (C.c_int, [_P, _P, _I64, _F, _I32, _F, _F, _F, _P, _P]),
     "x2_angular_bwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
     "x2_sbf_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _F, _F, _I32, _F, _F, _F,

@@ -375,6 +375,40 @@ k_sbf_bwd_d(const float* __restrict__ d, const float* __restrict__ angles, const
   if (lane == 0) gd[e] = (float)g;
 }
 
+// ------------------------------------------------------------------ geometry of the line graph (xgnn.py:46,60-66)
+// bond lengths d_e = |pos[a0] - pos[a1]| and triplet angles theta_t = atan2(|ji x jk|, <ji, jk>) with
+// ji = pos[i] - pos[j], jk = pos[k] - pos[j]: ~15 gather / elementwise / reduction launches of the caller as two
+// kernels (no [T, 3] intermediates).  fp32, the reference's operation order; products and sums are not contracted
+// into FMAs across the reference's kernel boundaries (a difference is exact, a product is rounded before it is added).
+__global__ void k_bond_lengths(const float* __restrict__ pos, const int64_t* __restrict__ a0,
+                               const int64_t* __restrict__ a1, int64_t E, float* __restrict__ d) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const float* p = pos + 3 * a0[e];
+  const float* q = pos + 3 * a1[e];
+  const float x = p[0] - q[0], y = p[1] - q[1], z = p[2] - q[2];
+  d[e] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+}
+
+__global__ void k_triplet_angles(const float* __restrict__ pos, const int64_t* __restrict__ ai,
+                                 const int64_t* __restrict__ aj, const int64_t* __restrict__ ak, int64_t T,
+                                 float* __restrict__ ang) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float* pj = pos + 3 * aj[t];
+  const float* pi = pos + 3 * ai[t];
+  const float* pk = pos + 3 * ak[t];
+  const float jx = pj[0], jy = pj[1], jz = pj[2];
+  const float ax = pi[0] - jx, ay = pi[1] - jy, az = pi[2] - jz;      // ji
+  const float bx = pk[0] - jx, by = pk[1] - jy, bz = pk[2] - jz;      // jk
+  const float c = __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+  const float cx = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az, by));
+  const float cy = __fsub_rn(__fmul_rn(az, bx), __fmul_rn(ax, bz));
+  const float cz = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
+  const float s = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
+  ang[t] = atan2f(s, c);
+}
+
 }  // namespace x2
 
 using namespace x2;
@@ -500,6 +534,24 @@ int x2_sbf_bwd(const float* d, const float* table, const float* angles, const in
                                                                              b, c, grad_d);
     X2_LAUNCH_OK();
   }
+  return X2_OK;
+}
+
+// ---- geometry of the line graph (xgnn.py:46,60-66): indices are the caller's int64 tensors, bounds are the caller's
+int x2_bond_lengths(const float* pos, const int64_t* a0, const int64_t* a1, int64_t E, float* d, void* stream) {
+  X2_CHECK_ARG(E >= 0 && (E == 0 || (pos && a0 && a1 && d)), "x2_bond_lengths: bad arguments");
+  if (E == 0) return X2_OK;
+  k_bond_lengths<<<(unsigned)cdiv(E, 256), 256, 0, (cudaStream_t)stream>>>(pos, a0, a1, E, d);
+  X2_LAUNCH_OK();
+  return X2_OK;
+}
+
+int x2_triplet_angles(const float* pos, const int64_t* ai, const int64_t* aj, const int64_t* ak, int64_t T, float* ang,
+                      void* stream) {
+  X2_CHECK_ARG(T >= 0 && (T == 0 || (pos && ai && aj && ak && ang)), "x2_triplet_angles: bad arguments");
+  if (T == 0) return X2_OK;
+  k_triplet_angles<<<(unsigned)cdiv(T, 256), 256, 0, (cudaStream_t)stream>>>(pos, ai, aj, ak, T, ang);
+  X2_LAUNCH_OK();
   return X2_OK;
 }
 

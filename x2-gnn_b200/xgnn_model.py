@@ -24,6 +24,7 @@ from torch import nn
 from .angular_basis_layer import F_B_2D
 from .edge_graph import vertex_to_edge_2
 from .envelop import poly_envelop
+from .geometry import bond_lengths, triplet_angles
 from .graph_norm import graph_layer_norm_rows, rowptr_from_counts
 from .radial_basis_layer import RadialBasis
 from . import readout_sum
@@ -265,13 +266,12 @@ class XGNNPoly(nn.Module):
         pos = data["atom_pos"]
         B = int(data["num_graphs"])
         tri, a_j, a_i, a_k = prep["tri"], prep["a_j"], prep["a_i"], prep["a_k"]
-        d = torch.norm(pos[prep["ei0"]] - pos[prep["ei1"]], dim=1)
+        d = bond_lengths(pos, prep["ei0"], prep["ei1"])
         env = self.envelop_function(d)[:, None]
         neo_x = F.silu(self.mat_trans(data["edge_attr"] * env))
         # [N, A]; the reference gathers [a_j] here (xgnn.py:58)
         atom_emb = self.emb_block(data["x"], prep["z_rows"], prep["z_counts"])
-        ji, jk = pos[a_i] - pos[a_j], pos[a_k] - pos[a_j]
-        ang = torch.atan2(torch.linalg.cross(ji, jk).norm(dim=1), (ji * jk).sum(1))
+        ang = triplet_angles(pos, a_i, a_j, a_k)
         edge_sbf = self.sbf_layer(d, ang, prep["src_bond"])
         node_rbf = self.rbf_layer(d) * env
         neo_x = F.silu(self.emb_trans(neo_x))

@@ -109,7 +109,12 @@ class DeferredWgrads:
         if not self.jobs:
             return 0
         L = _lib.lib()
-        st = torch.cuda.current_stream(dev).cuda_stream
+        cur = torch.cuda.current_stream(dev)
+        st = cur.cuda_stream
+        # operands recorded by a backward node that ran on another stream (the model's side-stream readouts): the
+        # backward has been joined into this stream by autograd, but the allocator must also know they are read here
+        for t in self.keep:
+            t.record_stream(cur)
         n = 0
         for (M, kb, _), lst in self.jobs.items():
             arr = (_lib.WgradJob * len(lst))(*[_lib.WgradJob(*j) for j in lst])

@@ -249,3 +249,26 @@ def test_padded_width_embedding_is_exact_on_the_oracle():
         assert (u is None) == (v is None)
         if u is not None:
             assert torch.allclose(u, v, rtol=0, atol=1e-12)
+
+
+def test_deferred_wgrad_bookkeeping_without_a_gpu():
+    """tc_linear.WgradSlots never travels with a copied / pickled module (the EMA deepcopy of train_ema.py:45-47 must
+    not drag the optimizer's buffers along); DeferredWgrads groups the 128-blocks of a layer by (rows, block width,
+    alignment) and refuses a weight recorded twice before the flush."""
+    import pickle
+    from x2gnn_b200.tc_linear import DeferredWgrads, TCLinear, WgradSlots
+    lin = TCLinear(338, 256)
+    lin._x2_slots = WgradSlots(object(), torch.zeros(256, 338), torch.zeros(256))
+    c = copy.deepcopy(lin)
+    assert c._x2_slots is None and list(c.state_dict().keys()) == ["weight", "bias"]
+    assert pickle.loads(pickle.dumps(lin._x2_slots)) is None
+    q = DeferredWgrads()
+    gy, x = torch.zeros(10, 256), torch.zeros(10, 338)
+    gw, gb = torch.zeros(256, 338), torch.zeros(256)
+    q.add(gy, x, 10, 256, 338, gw, gb)
+    blocks = sorted((k[1], len(v)) for k, v in q.jobs.items())
+    assert sum(n for _, n in blocks) == 6 and {kb for kb, _ in blocks} == {82, 128}     # 2 N blocks x K blocks 128|128|82
+    jobs = [j for v in q.jobs.values() for j in v]
+    assert sum(1 for j in jobs if j[6]) == 2                      # the bias gradient rides with the first K block only
+    with pytest.raises(RuntimeError):
+        q.add(gy, x, 10, 256, 338, gw, gb)

@@ -331,7 +331,9 @@ def _train_step_graph(dev, world, rank, steps, data, y, nmine):
     # untimed iterations inside the loop (pipeline fill from an idle device), see the eager loop; with NCCL inside
     # the replayed graph the first replays after the barrier are slow for longer (107 / 22 ms at timed positions
     # 0 / 1 with 4 lead-in replays on a 2-GPU box: gpurun_out/r2y_bench_2gpu.json)
-    LEAD = 4 if world == 1 else 12
+    # (N = 1 as well: with 4 lead-in replays the first ~8 TIMED steps still ran 7.6-7.9 ms against 7.07 afterwards,
+    # profiles/r2_bench_1gpu.json of build c8e195d0 -- the device idles through the host-side setup before the loop)
+    LEAD = 12
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(LEAD + steps + 1)]
     gc.collect()
     gc.disable()

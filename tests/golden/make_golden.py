@@ -168,6 +168,28 @@ def main():
                 if (k.endswith("_f32") and k not in ("out_f32",)) or k.startswith("alpha_"):
                     del rec[k]
         cv[tag] = rec
+    # a constructor shape outside the kernel widths (in_channels != heads * out_channels, sbftransformer_conv.py:19,47-48):
+    # the reference's own layer in fp64 pins the oracle there, the kernels run it zero-padded (padded_width)
+    in_ch, H, C, S, R, A = 48, 2, 16, 6, 4, 16
+    torch.manual_seed(101)
+    conv = sbftransformer_conv.SBFTransformerConv(in_ch, C, heads=H, sbf_dim=S, rbf_dim=R, dropout=0, edge_dim=A)
+    ci = synth.conv_inputs(E, tri.numpy(), in_ch, S, R, A, seed=4)
+    inp = {k: torch.from_numpy(v) for k, v in ci.items()}
+    gout = torch.randn(E, H * C, generator=torch.Generator().manual_seed(10))
+    rec = dict(shape=(in_ch, H, C, S, R, A), state_dict={k: v.clone() for k, v in conv.state_dict().items()},
+               grad_out=gout, **inp)
+    c = sbftransformer_conv.SBFTransformerConv(in_ch, C, heads=H, sbf_dim=S, rbf_dim=R, dropout=0, edge_dim=A).double()
+    c.load_state_dict({k: v.double() for k, v in rec["state_dict"].items()})
+    xs = {k: inp[k].detach().clone().double().requires_grad_(True) for k in ("x", "rbf", "sbf", "edge_attr")}
+    o, (_, alpha) = c(xs["sbf"], xs["rbf"], x=xs["x"], edge_index=inp["edge_index"], edge_attr=xs["edge_attr"],
+                      return_attention_weights=True)
+    o.backward(gout.double())
+    rec["out_f64"], rec["alpha_f64"] = o.detach(), alpha.detach()
+    for k in xs:
+        rec[f"grad_{k}_f64"] = xs[k].grad
+    for k, p in c.named_parameters():
+        rec[f"gradp_{k}_f64"] = p.grad
+    cv["odd48"] = rec
     out["conv"] = cv
 
     # ---------------------------------------------------------------- full model (small dims)

@@ -175,6 +175,26 @@ def test_shapes_outside_the_kernel_widths(shape, kw):
         assert p.grad is None or p.grad.shape == p.shape, k
 
 
+def test_shape_outside_kernel_widths_golden(golden):
+    """The same against the REFERENCE's own layer (fp64 golden `odd48`: in 48, heads 2, out 16): the kernels at the
+    padded width 64 (4 heads, two of them zero) against the unpadded reference, every output and gradient."""
+    from x2gnn_b200.sbftransformer_conv import SBFTransformerConv, padded_width
+    rec = golden("conv")["odd48"]
+    in_ch, H, C, S, R, A = rec["shape"]
+    assert padded_width(in_ch, H, C) == 64
+    mine = SBFTransformerConv(in_ch, C, heads=H, sbf_dim=S, rbf_dim=R, dropout=0, edge_dim=A)
+    mine.load_state_dict(rec["state_dict"])
+    mine = mine.cuda()
+    out, alpha, xs = _run(mine, rec, "cuda", torch.float32, want_alpha=True)
+    assert relerr(out, rec["out_f64"]) < FP32_TOL and relerr(alpha, rec["alpha_f64"]) < FP32_TOL
+    for k in INPUTS:
+        assert relerr(xs[k].grad, rec[f"grad_{k}_f64"]) < FP32_TOL, k
+    for k, p in mine.named_parameters():
+        if k == "lin_key.bias":
+            continue
+        assert relerr(p.grad, rec[f"gradp_{k}_f64"]) < FP32_TOL, k
+
+
 def test_unsupported_shape_raises():
     from x2gnn_b200.sbftransformer_conv import SBFTransformerConv
     c = SBFTransformerConv(24, 24, heads=1, sbf_dim=4, rbf_dim=2).cuda()          # out_channels not a power of two

@@ -132,6 +132,27 @@ def test_conv_fp64_fwd_bwd(golden, tag):
     assert c.lin_key.bias.grad.abs().max() < 1e-10
 
 
+def test_conv_shape_outside_kernel_widths_vs_reference_fp64(golden):
+    """in_channels != heads * out_channels (sbftransformer_conv.py:19,47-48): the oracle against the reference's own
+    layer at (in 48, heads 2, out 16) in fp64 -- the case the kernels run zero-padded (padded_width)."""
+    rec = golden("conv")["odd48"]
+    in_ch, H, C, S, R, A = rec["shape"]
+    c = oconv.OracleSBFTransformerConv(in_ch, C, heads=H, sbf_dim=S, rbf_dim=R, dropout=0, edge_dim=A).double()
+    assert list(c.state_dict().keys()) == list(rec["state_dict"].keys())
+    c.load_state_dict({k: v.double() for k, v in rec["state_dict"].items()})
+    xs = {k: rec[k].double().requires_grad_(True) for k in ("x", "rbf", "sbf", "edge_attr")}
+    out, (_, alpha) = c(xs["sbf"], xs["rbf"], x=xs["x"], edge_index=rec["edge_index"],
+                        edge_attr=xs["edge_attr"], return_attention_weights=True)
+    out.backward(rec["grad_out"].double())
+    tol = dict(rtol=1e-10, atol=1e-10)
+    assert out.shape == (rec["x"].size(0), H * C) and torch.allclose(out, rec["out_f64"], **tol)
+    assert torch.allclose(alpha, rec["alpha_f64"], **tol)
+    for k in xs:
+        assert torch.allclose(xs[k].grad, rec[f"grad_{k}_f64"], **tol), k
+    for k, p in c.named_parameters():
+        assert torch.allclose(p.grad, rec[f"gradp_{k}_f64"], **tol), k
+
+
 def test_conv_fp32(golden):
     rec = golden("conv")["cfg"]
     c = _oracle_conv(rec, torch.float32)
